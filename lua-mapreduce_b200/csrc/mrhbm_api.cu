@@ -1,0 +1,795 @@
+// mrhbm_api.cu -- host runtime behind the C ABI of include/mrhbm.h: HBM emit pool, map-job
+// bookkeeping (commit = replace-by-job-id, abort = discard; mapreduce/job.lua:217-221,
+// worker.lua:120-127), the shuffle driver, result iteration.  No CPU fallback anywhere.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mrhbm.h"
+#include "mrhbm_comm.h"
+#include "mrhbm_kernels.h"
+
+using namespace mrhbm;
+
+namespace {
+enum { R_OPEN = 0, R_COMMITTED = 1, R_DEAD = 2 };
+struct Range {
+  uint64_t off, cnt;
+  std::string job;
+  int state;
+  uint64_t owner;  // map handle serial
+};
+constexpr size_t kStageRecs = 1 << 16;
+enum { EV_START, EV_COMBINE, EV_HIST, EV_PLAN, EV_SCATTER, EV_EXCH, EV_SORT, EV_BIG, EV_END, EV_PROBE, EV_N };
+}  // namespace
+
+struct mrhbm_ctx {
+  mrhbm_config cfg{};
+  int dev = 0, rb = 16, kb = 8, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // HBM emit pool: committed + open map output, record granularity
+  void* pool = nullptr;
+  uint64_t pool_cap = 0, pool_used = 0;
+  std::vector<Range> ranges;
+  uint64_t map_serial = 0;
+  // shuffle state
+  ShuffleBuffers sb{};
+  uint64_t B_cap = 0, mid_cap = 0, out_cap = 0;
+  uint32_t B = 0, S = 1, ordered = 1, cap = 0;
+  uint64_t N = 0, groups = 0;
+  bool shuffled = false;
+  std::vector<uint32_t> h_bin_off, h_uoff;
+  void* ckeys = nullptr;
+  uint64_t* csums = nullptr;
+  uint64_t c_cap = 0;
+  bool compacted = false;
+  uint64_t* d_acc = nullptr;       // 8 x u64 scratch
+  uint32_t* h_counters = nullptr;  // pinned, 8 x u32
+  uint64_t* h_acc = nullptr;       // pinned, 8 x u64
+  // zipf table cache
+  uint64_t* d_table = nullptr;
+  uint64_t d_table_V = 0, d_table_first = 0, d_table_last = 0;
+  mrhbm_stats stats{};
+  cudaEvent_t ev[EV_N]{};
+  Comm* comm = nullptr;
+  std::string err;
+};
+
+struct mrhbm_map {
+  mrhbm_ctx* ctx;
+  std::string job;
+  uint64_t serial;
+  unsigned char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  bool stage_busy[2] = {false, false};
+  int cur = 0;
+  size_t fill = 0;
+  bool async_reads = false;  // pinned user memory still being read by the copy engine
+};
+
+struct RunCursor {
+  uint64_t pos, end;
+};
+struct mrhbm_iter {
+  mrhbm_ctx* ctx;
+  std::vector<unsigned char> keys;
+  std::vector<uint64_t> sums;
+  std::vector<RunCursor> runs;
+  uint64_t base = 0;
+  unsigned char keybuf[8];
+  bool sorted = true;
+  size_t cur_run = 0;
+};
+
+namespace {
+
+int fail(mrhbm_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(c, expr)                                                                               \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      cudaGetLastError();                                                                         \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? MRHBM_E_NOMEM : MRHBM_E_CUDA,            \
+                  "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,         \
+                  cudaGetErrorString(e_));                                                        \
+    }                                                                                             \
+  } while (0)
+
+int pool_reserve(mrhbm_ctx* c, uint64_t n, uint64_t* off) {
+  if (c->pool_used + n > c->pool_cap) {
+    uint64_t want = std::max<uint64_t>(c->pool_used + n, c->pool_cap * 2);
+    want = std::max<uint64_t>(want, 1 << 16);
+    void* np = nullptr;
+    CU(c, cudaMalloc(&np, want * c->rb));
+    if (c->pool_used) CU(c, cudaMemcpyAsync(np, c->pool, c->pool_used * c->rb, cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->pool) CU(c, cudaFree(c->pool));
+    c->pool = np;
+    c->pool_cap = want;
+  }
+  *off = c->pool_used;
+  c->pool_used += n;
+  return 0;
+}
+
+void add_range(mrhbm_map* m, uint64_t off, uint64_t cnt) {
+  mrhbm_ctx* c = m->ctx;
+  if (!c->ranges.empty()) {
+    Range& r = c->ranges.back();
+    if (r.owner == m->serial && r.state == R_OPEN && r.off + r.cnt == off) {
+      r.cnt += cnt;
+      return;
+    }
+  }
+  c->ranges.push_back(Range{off, cnt, m->job, R_OPEN, m->serial});
+}
+
+int stage_flush(mrhbm_map* m) {
+  mrhbm_ctx* c = m->ctx;
+  if (!m->fill) return 0;
+  uint64_t off;
+  int rc = pool_reserve(c, m->fill, &off);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync((char*)c->pool + off * c->rb, m->stage[m->cur], m->fill * c->rb, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(m->stage_ev[m->cur], c->stream));
+  m->stage_busy[m->cur] = true;
+  add_range(m, off, m->fill);
+  m->fill = 0;
+  m->cur ^= 1;
+  if (m->stage_busy[m->cur]) {
+    CU(c, cudaEventSynchronize(m->stage_ev[m->cur]));
+    m->stage_busy[m->cur] = false;
+  }
+  return 0;
+}
+
+int stage_slot(mrhbm_map* m, unsigned char** slot) {
+  mrhbm_ctx* c = m->ctx;
+  if (!m->stage[0]) {
+    for (int i = 0; i < 2; i++) {
+      CU(c, cudaHostAlloc((void**)&m->stage[i], kStageRecs * c->rb, cudaHostAllocDefault));
+      CU(c, cudaEventCreateWithFlags(&m->stage_ev[i], cudaEventDisableTiming));
+    }
+  }
+  if (m->fill == kStageRecs) {
+    int rc = stage_flush(m);
+    if (rc) return rc;
+  }
+  *slot = m->stage[m->cur] + m->fill * c->rb;
+  m->fill++;
+  return 0;
+}
+
+void map_release(mrhbm_map* m) {
+  for (int i = 0; i < 2; i++) {
+    if (m->stage_busy[i]) cudaEventSynchronize(m->stage_ev[i]);
+    if (m->stage_ev[i]) cudaEventDestroy(m->stage_ev[i]);
+    if (m->stage[i]) cudaFreeHost(m->stage[i]);
+  }
+  delete m;
+}
+
+void invalidate(mrhbm_ctx* c) {
+  c->shuffled = false;
+  c->compacted = false;
+}
+
+int ensure_buffers(mrhbm_ctx* c, uint64_t B, uint64_t N) {
+  if (B + 1 > c->B_cap) {
+    uint64_t nb = B + 1 + (B >> 2);
+    uint32_t** ptrs[] = {&c->sb.hist, &c->sb.bin_off, &c->sb.cursor, &c->sb.ucount, &c->sb.uoff, &c->sb.big_list};
+    for (auto p : ptrs) {
+      if (*p) CU(c, cudaFree(*p));
+      *p = nullptr;
+      CU(c, cudaMalloc((void**)p, nb * sizeof(uint32_t)));
+    }
+    c->B_cap = nb;
+  }
+  if (!c->sb.counters) CU(c, cudaMalloc((void**)&c->sb.counters, 8 * sizeof(uint32_t)));
+  uint64_t need = std::max<uint64_t>(N, 1);
+  if (need > c->mid_cap) {
+    if (c->sb.mid) CU(c, cudaFree(c->sb.mid));
+    c->sb.mid = nullptr;
+    c->mid_cap = 0;
+    CU(c, cudaMalloc(&c->sb.mid, need * c->rb));
+    c->mid_cap = need;
+  }
+  if (need > c->out_cap) {
+    if (c->sb.out_keys) CU(c, cudaFree(c->sb.out_keys));
+    if (c->sb.out_sums) CU(c, cudaFree(c->sb.out_sums));
+    c->sb.out_keys = nullptr;
+    c->sb.out_sums = nullptr;
+    c->out_cap = 0;
+    CU(c, cudaMalloc(&c->sb.out_keys, need * c->kb));
+    CU(c, cudaMalloc((void**)&c->sb.out_sums, need * sizeof(uint64_t)));
+    c->out_cap = need;
+  }
+  return 0;
+}
+
+// committed ranges, adjacent ones merged
+std::vector<std::pair<uint64_t, uint64_t>> live_ranges(const mrhbm_ctx* c) {
+  std::vector<std::pair<uint64_t, uint64_t>> v;
+  for (const Range& r : c->ranges) {
+    if (r.state != R_COMMITTED || !r.cnt) continue;
+    if (!v.empty() && v.back().first + v.back().second == r.off)
+      v.back().second += r.cnt;
+    else
+      v.emplace_back(r.off, r.cnt);
+  }
+  return v;
+}
+
+int ensure_compact(mrhbm_ctx* c) {
+  if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
+  if (c->compacted) return 0;
+  uint64_t need = std::max<uint64_t>(c->groups, 1);
+  if (need > c->c_cap) {
+    if (c->ckeys) CU(c, cudaFree(c->ckeys));
+    if (c->csums) CU(c, cudaFree(c->csums));
+    c->ckeys = nullptr;
+    c->csums = nullptr;
+    c->c_cap = 0;
+    CU(c, cudaMalloc(&c->ckeys, need * c->kb));
+    CU(c, cudaMalloc((void**)&c->csums, need * sizeof(uint64_t)));
+    c->c_cap = need;
+  }
+  launch_compact(c->rb, c->sb, c->B, c->ckeys, c->csums, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->compacted = true;
+  return 0;
+}
+
+float ev_ms(mrhbm_ctx* c, int a, int b) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrhbm_abi_version(void) { return MRHBM_ABI_VERSION; }
+
+int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
+  if (!cfg || !out || cfg->struct_size != sizeof(mrhbm_config)) return MRHBM_E_INVAL;
+  *out = nullptr;
+  mrhbm_ctx* c = new mrhbm_ctx();
+  *out = c;  // returned even on failure so that the caller can read last_error, then destroy
+  c->cfg = *cfg;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(c, MRHBM_E_NODEVICE, "no CUDA device (%s): mrhbm has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  int dev = cfg->device;
+  if (dev < 0) CU(c, cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(c, MRHBM_E_INVAL, "device %d out of range (%d devices)", dev, ndev);
+  CU(c, cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU(c, cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(c, MRHBM_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                prop.major, prop.minor);
+  c->dev = dev;
+  c->sm_count = prop.multiProcessorCount;
+  if (cfg->num_partitions == 0) return fail(c, MRHBM_E_INVAL, "num_partitions must be >= 1");
+  if (cfg->key_kind == MRHBM_KEY_U64) {
+    c->rb = 16;
+    c->kb = 8;
+    if (cfg->partitioner > MRHBM_PART_WORDHASH) return fail(c, MRHBM_E_INVAL, "unknown partitioner");
+  } else if (cfg->key_kind == MRHBM_KEY_STR) {
+    uint32_t m = cfg->max_key_bytes ? cfg->max_key_bytes : 27;
+    if (m <= 27) c->rb = 32;
+    else if (m <= 59) c->rb = 64;
+    else if (m <= 123) c->rb = 128;
+    else return fail(c, MRHBM_E_KEY, "max_key_bytes %u exceeds the largest record class (123)", m);
+    c->kb = c->rb - 4;
+    if (cfg->partitioner != MRHBM_PART_FNV_LUA && cfg->partitioner != MRHBM_PART_WORDHASH)
+      return fail(c, MRHBM_E_INVAL, "string keys need partitioner FNV_LUA or WORDHASH");
+  } else
+    return fail(c, MRHBM_E_INVAL, "unknown key_kind %u", cfg->key_kind);
+  if (cfg->reducer != MRHBM_RED_SUM) return fail(c, MRHBM_E_INVAL, "unknown reducer %u", cfg->reducer);
+  CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < EV_N; i++) CU(c, cudaEventCreate(&c->ev[i]));
+  CU(c, kernels_configure());
+  CU(c, cudaMalloc((void**)&c->d_acc, 8 * sizeof(uint64_t)));
+  CU(c, cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+  CU(c, cudaHostAlloc((void**)&c->h_acc, 8 * sizeof(uint64_t), cudaHostAllocDefault));
+  c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
+  if (cfg->reserve_pairs) {
+    uint64_t off;
+    int rc = pool_reserve(c, cfg->reserve_pairs, &off);
+    if (rc) return rc;
+    c->pool_used = 0;
+  }
+  return MRHBM_OK;
+}
+
+void mrhbm_destroy(mrhbm_ctx* c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm) comm_destroy(c->comm);
+  void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
+                   c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
+                   c->csums,       c->d_acc,       c->d_table};
+  for (void* p : frees)
+    if (p) cudaFree(p);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_acc) cudaFreeHost(c->h_acc);
+  for (int i = 0; i < EV_N; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaGetLastError();
+  delete c;
+}
+
+const char* mrhbm_last_error(const mrhbm_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+uint32_t mrhbm_record_bytes(const mrhbm_ctx* c) { return c ? (uint32_t)c->rb : 0; }
+
+void* mrhbm_host_alloc(mrhbm_ctx* c, size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    if (c) c->err = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+void mrhbm_host_free(mrhbm_ctx*, void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------
+// map side
+// ---------------------------------------------------------------------------
+int mrhbm_map_begin(mrhbm_ctx* c, const char* job, mrhbm_map** out) {
+  if (!c || !job || !out) return MRHBM_E_INVAL;
+  if (!c->stream) return fail(c, MRHBM_E_INVAL, "ctx failed to initialise");
+  mrhbm_map* m = new mrhbm_map();
+  m->ctx = c;
+  m->job = job;
+  m->serial = ++c->map_serial;
+  *out = m;
+  return MRHBM_OK;
+}
+
+int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
+  if (!m) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "ctx holds u64 keys");
+  if (klen >= (size_t)c->kb)
+    return fail(c, MRHBM_E_KEY, "key of %zu bytes does not fit the %d-byte record class", klen, c->rb);
+  if (klen && memchr(key, 0, klen)) return fail(c, MRHBM_E_KEY, "keys with embedded NUL are not supported");
+  unsigned char* slot;
+  int rc = stage_slot(m, &slot);
+  if (rc) return rc;
+  memcpy(slot, key, klen);
+  memset(slot + klen, 0, c->kb - klen);
+  memcpy(slot + c->kb, &value, 4);
+  return MRHBM_OK;
+}
+
+int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint32_t value) {
+  if (!m) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (c->cfg.key_kind != MRHBM_KEY_U64) return fail(c, MRHBM_E_INVAL, "ctx holds string keys");
+  unsigned char* slot;
+  int rc = stage_slot(m, &slot);
+  if (rc) return rc;
+  uint32_t zero = 0;
+  memcpy(slot, &key, 8);
+  memcpy(slot + 8, &value, 4);
+  memcpy(slot + 12, &zero, 4);
+  return MRHBM_OK;
+}
+
+int mrhbm_emit_batch(mrhbm_map* m, const void* recs, size_t n) {
+  if (!m || (!recs && n)) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (!n) return MRHBM_OK;
+  int rc = stage_flush(m);  // keep emission order
+  if (rc) return rc;
+  uint64_t off;
+  rc = pool_reserve(c, n, &off);
+  if (rc) return rc;
+  cudaPointerAttributes at{};
+  bool pinned = cudaPointerGetAttributes(&at, recs) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  CU(c, cudaMemcpyAsync((char*)c->pool + off * c->rb, recs, n * c->rb, cudaMemcpyHostToDevice, c->stream));
+  if (pinned) m->async_reads = true;  // pageable sources are fully staged before the call returns
+  add_range(m, off, n);
+  return MRHBM_OK;
+}
+
+int mrhbm_emit_device(mrhbm_map* m, const void* drecs, size_t n) {
+  if (!m || (!drecs && n)) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (!n) return MRHBM_OK;
+  int rc = stage_flush(m);
+  if (rc) return rc;
+  uint64_t off;
+  rc = pool_reserve(c, n, &off);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync((char*)c->pool + off * c->rb, drecs, n * c->rb, cudaMemcpyDeviceToDevice, c->stream));
+  add_range(m, off, n);
+  return MRHBM_OK;
+}
+
+int mrhbm_map_gen_u64(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n) {
+  if (!m) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (c->rb != 16) return fail(c, MRHBM_E_INVAL, "gen_u64 needs a u64-key ctx");
+  int rc = stage_flush(m);
+  if (rc) return rc;
+  uint64_t off;
+  rc = pool_reserve(c, n, &off);
+  if (rc) return rc;
+  launch_gen_u64((char*)c->pool + off * c->rb, seed, start, n, c->stream);
+  CU(c, cudaGetLastError());
+  add_range(m, off, n);
+  return MRHBM_OK;
+}
+
+int mrhbm_map_gen_zipf(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n, const uint64_t* table,
+                       uint64_t V) {
+  if (!m || !table || !V) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (c->rb != 32) return fail(c, MRHBM_E_INVAL, "gen_zipf needs 32-byte string records (max_key_bytes <= 27)");
+  if (!c->d_table || c->d_table_V != V || c->d_table_first != table[0] || c->d_table_last != table[V - 1]) {
+    if (c->d_table) CU(c, cudaFree(c->d_table));
+    c->d_table = nullptr;
+    CU(c, cudaMalloc((void**)&c->d_table, V * sizeof(uint64_t)));
+    CU(c, cudaMemcpyAsync(c->d_table, table, V * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->d_table_V = V;
+    c->d_table_first = table[0];
+    c->d_table_last = table[V - 1];
+  }
+  int rc = stage_flush(m);
+  if (rc) return rc;
+  uint64_t off;
+  rc = pool_reserve(c, n, &off);
+  if (rc) return rc;
+  launch_gen_zipf32((char*)c->pool + off * c->rb, seed, start, n, c->d_table, V, c->stream);
+  CU(c, cudaGetLastError());
+  add_range(m, off, n);
+  return MRHBM_OK;
+}
+
+int mrhbm_pool_read(mrhbm_ctx* c, uint64_t first, uint64_t n, void* host_out) {
+  if (!c || (!host_out && n)) return MRHBM_E_INVAL;
+  uint64_t skip = first, done = 0;
+  for (auto& r : live_ranges(c)) {
+    if (done == n) break;
+    if (skip >= r.second) {
+      skip -= r.second;
+      continue;
+    }
+    uint64_t take = std::min<uint64_t>(n - done, r.second - skip);
+    CU(c, cudaMemcpyAsync((char*)host_out + done * c->rb, (char*)c->pool + (r.first + skip) * c->rb, take * c->rb,
+                          cudaMemcpyDeviceToHost, c->stream));
+    done += take;
+    skip = 0;
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (done != n) return fail(c, MRHBM_E_INVAL, "pool_read: only %llu of %llu pairs committed", (unsigned long long)done, (unsigned long long)n);
+  return MRHBM_OK;
+}
+
+int mrhbm_map_commit(mrhbm_map* m) {
+  if (!m) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  int rc = stage_flush(m);
+  if (rc == 0 && m->async_reads) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);  // caller may reuse its pinned buffers now
+    if (e != cudaSuccess) rc = fail(c, MRHBM_E_CUDA, "commit: %s", cudaGetErrorString(e));
+  }
+  if (rc) {
+    mrhbm_map_abort(m);
+    return rc;
+  }
+  for (Range& r : c->ranges) {
+    if (r.state == R_COMMITTED && r.job == m->job) r.state = R_DEAD;  // replace-by-job-id
+  }
+  for (Range& r : c->ranges)
+    if (r.owner == m->serial && r.state == R_OPEN) r.state = R_COMMITTED;
+  invalidate(c);
+  map_release(m);
+  return MRHBM_OK;
+}
+
+void mrhbm_map_abort(mrhbm_map* m) {
+  if (!m) return;
+  mrhbm_ctx* c = m->ctx;
+  cudaStreamSynchronize(c->stream);
+  for (Range& r : c->ranges)
+    if (r.owner == m->serial && r.state == R_OPEN) r.state = R_DEAD;
+  while (!c->ranges.empty() && c->ranges.back().state == R_DEAD &&
+         c->ranges.back().off + c->ranges.back().cnt == c->pool_used) {
+    c->pool_used = c->ranges.back().off;
+    c->ranges.pop_back();
+  }
+  map_release(m);
+}
+
+int mrhbm_reset(mrhbm_ctx* c) {
+  if (!c) return MRHBM_E_INVAL;
+  c->ranges.clear();
+  c->pool_used = 0;
+  invalidate(c);
+  return MRHBM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// shuffle
+// ---------------------------------------------------------------------------
+int mrhbm_shuffle(mrhbm_ctx* c) {
+  if (!c || !c->stream) return MRHBM_E_INVAL;
+  for (const Range& r : c->ranges)
+    if (r.state == R_OPEN) return fail(c, MRHBM_E_INVAL, "map job '%s' is still open", r.job.c_str());
+  if (c->comm) return comm_shuffle_unavailable(c->comm, &c->err);
+  auto live = live_ranges(c);
+  uint64_t N = 0;
+  for (auto& r : live) N += r.second;
+  if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
+  const uint32_t P = c->cfg.num_partitions;
+  // mean bin = 84% of what one CTA sorts in shared memory
+  uint64_t target = std::max<uint64_t>(1, (uint64_t)c->cap * 84 / 100);
+  uint64_t S64 = (N + (uint64_t)P * target - 1) / ((uint64_t)P * target);
+  uint32_t S = (uint32_t)std::max<uint64_t>(1, S64);
+  uint64_t B = (uint64_t)P * S;
+  if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
+  int rc = ensure_buffers(c, B, N);
+  if (rc) return rc;
+  uint32_t ordered = (c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS)) || S == 1;
+  mrhbm_stats st{};
+  st.pairs = N;
+  cudaStream_t s = c->stream;
+  CU(c, cudaEventRecord(c->ev[EV_START], s));
+  uint32_t nbig = 0;
+  for (int attempt = 0;; attempt++) {
+    st.attempts = attempt + 1;
+    CU(c, cudaMemsetAsync(c->sb.hist, 0, B * sizeof(uint32_t), s));
+    CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
+    CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
+    for (auto& r : live)
+      st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->sb.hist, s);
+    CU(c, cudaEventRecord(c->ev[EV_HIST], s));
+    st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->cap, c->sb.big_list,
+                                 c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, s);
+    CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
+    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+    for (auto& r : live)
+      st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->sb.cursor, c->sb.mid, s);
+    CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
+    CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
+    st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+    CU(c, cudaEventRecord(c->ev[EV_SORT], s));
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventSynchronize(c->ev[EV_PROBE]));  // overlaps with scatter / sort on the device
+    nbig = c->h_counters[CNT_NBIG];
+    if (nbig && ordered && S > 1) {
+      // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
+      ordered = 0;
+      continue;
+    }
+    break;
+  }
+  st.launches += launch_big_bins(c->rb, c->sb, nbig, c->cap, s);
+  CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+  st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, 0xffffffffu, nullptr, nullptr,
+                               c->sb.counters + CNT_TOTAL, s);
+  c->h_bin_off.resize(B + 1);
+  c->h_uoff.resize(B + 1);
+  CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->sb.bin_off, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaEventRecord(c->ev[EV_END], s));
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(s));
+  uint32_t ef = c->h_counters[CNT_ERR];
+  if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
+  if (ef & ERRF_SKEW)
+    return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can sort (%u oversized bins)", nbig);
+  c->B = (uint32_t)B;
+  c->S = S;
+  c->ordered = ordered;
+  c->N = N;
+  c->groups = c->h_uoff[B];
+  c->shuffled = true;
+  c->compacted = false;
+  st.bins = (uint32_t)B;
+  st.sub_bins = S;
+  st.big_bins = nbig;
+  st.groups = c->groups;
+  st.ms_total = ev_ms(c, EV_START, EV_END);
+  st.ms_combine = 0;
+  st.ms_hist = ev_ms(c, EV_COMBINE, EV_HIST);
+  st.ms_plan = ev_ms(c, EV_HIST, EV_PLAN);
+  st.ms_scatter = ev_ms(c, EV_PLAN, EV_SCATTER);
+  st.ms_exchange = 0;
+  st.ms_sort_reduce = ev_ms(c, EV_EXCH, EV_SORT);
+  st.ms_bigbins = ev_ms(c, EV_SORT, EV_BIG);
+  c->stats = st;
+  return MRHBM_OK;
+}
+
+int mrhbm_stats_get(mrhbm_ctx* c, mrhbm_stats* out) {
+  if (!c || !out) return MRHBM_E_INVAL;
+  *out = c->stats;
+  return MRHBM_OK;
+}
+
+int mrhbm_partitions(mrhbm_ctx* c, uint32_t* ids, size_t cap, size_t* n) {
+  if (!c || !n) return MRHBM_E_INVAL;
+  if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
+  size_t k = 0;
+  for (uint32_t p = 0; p < c->cfg.num_partitions; p++) {
+    if (c->h_uoff[(uint64_t)(p + 1) * c->S] > c->h_uoff[(uint64_t)p * c->S]) {
+      if (ids && k < cap) ids[k] = p;
+      k++;
+    }
+  }
+  *n = k;
+  return MRHBM_OK;
+}
+
+int mrhbm_result_info_get(mrhbm_ctx* c, mrhbm_result_info* info) {
+  if (!c || !info) return MRHBM_E_INVAL;
+  if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
+  size_t np = 0;
+  mrhbm_partitions(c, nullptr, 0, &np);
+  info->pairs_in = c->N;
+  info->pairs_recv = c->N;
+  info->groups = c->groups;
+  info->key_bytes = (uint32_t)c->kb;
+  info->sorted = (c->ordered || c->S == 1) ? 1 : 0;
+  info->runs_per_partition = c->S;
+  info->partitions_nonempty = (uint32_t)np;
+  return MRHBM_OK;
+}
+
+int mrhbm_result_copy(mrhbm_ctx* c, void* keys, uint64_t* sums, uint64_t* part_off) {
+  if (!c) return MRHBM_E_INVAL;
+  int rc = ensure_compact(c);
+  if (rc) return rc;
+  if (keys && c->groups) CU(c, cudaMemcpyAsync(keys, c->ckeys, c->groups * c->kb, cudaMemcpyDeviceToHost, c->stream));
+  if (sums && c->groups) CU(c, cudaMemcpyAsync(sums, c->csums, c->groups * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (part_off)
+    for (uint32_t p = 0; p <= c->cfg.num_partitions; p++) part_off[p] = c->h_uoff[(uint64_t)p * c->S];
+  CU(c, cudaStreamSynchronize(c->stream));
+  return MRHBM_OK;
+}
+
+int mrhbm_checksum_input(mrhbm_ctx* c, uint64_t in[4]) {
+  if (!c || !in) return MRHBM_E_INVAL;
+  CU(c, cudaMemsetAsync(c->d_acc, 0, 8 * sizeof(uint64_t), c->stream));
+  for (auto& r : live_ranges(c)) launch_checksum_in(c->rb, (char*)c->pool + r.first * c->rb, r.second, c->d_acc, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  memcpy(in, c->h_acc, 4 * sizeof(uint64_t));
+  return MRHBM_OK;
+}
+
+int mrhbm_checksum_result(mrhbm_ctx* c, uint64_t out[6]) {
+  if (!c || !out) return MRHBM_E_INVAL;
+  if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
+  CU(c, cudaMemsetAsync(c->d_acc, 0, 8 * sizeof(uint64_t), c->stream));
+  launch_checksum_out(c->rb, c->sb, c->B, c->cfg.num_partitions, c->S, c->cfg.partitioner, c->ordered, c->d_acc, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_acc, 6 * sizeof(uint64_t));
+  return MRHBM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// reduce side iteration
+// ---------------------------------------------------------------------------
+static inline int slot_cmp(const mrhbm_ctx* c, const unsigned char* a, const unsigned char* b) {
+  if (c->rb == 16) {
+    uint64_t x, y;
+    memcpy(&x, a, 8);
+    memcpy(&y, b, 8);
+    return (x > y) - (x < y);
+  }
+  return memcmp(a, b, c->kb);
+}
+
+int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
+  if (!c || !out) return MRHBM_E_INVAL;
+  if (part >= c->cfg.num_partitions) return fail(c, MRHBM_E_INVAL, "partition %u out of range", part);
+  int rc = ensure_compact(c);
+  if (rc) return rc;
+  mrhbm_iter* it = new mrhbm_iter();
+  it->ctx = c;
+  uint64_t b0 = (uint64_t)part * c->S;
+  uint64_t lo = c->h_uoff[b0], hi = c->h_uoff[b0 + c->S];
+  it->base = lo;
+  it->keys.resize((hi - lo) * c->kb);
+  it->sums.resize(hi - lo);
+  if (hi > lo) {
+    cudaError_t e = cudaMemcpyAsync(it->keys.data(), (char*)c->ckeys + lo * c->kb, (hi - lo) * c->kb, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(it->sums.data(), c->csums + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      delete it;
+      cudaGetLastError();
+      return fail(c, MRHBM_E_CUDA, "groups_open: %s", cudaGetErrorString(e));
+    }
+  }
+  it->sorted = c->ordered || c->S == 1;
+  if (it->sorted) {
+    it->runs.push_back(RunCursor{0, hi - lo});
+  } else {
+    for (uint32_t r = 0; r < c->S; r++) {
+      uint64_t a = c->h_uoff[b0 + r] - lo, b = c->h_uoff[b0 + r + 1] - lo;
+      if (b > a) it->runs.push_back(RunCursor{a, b});
+    }
+  }
+  *out = it;
+  return MRHBM_OK;
+}
+
+int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint64_t** values, size_t* nvalues) {
+  if (!it || !key || !klen || !values || !nvalues) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = it->ctx;
+  // k-way merge over the ascending runs of the partition (a single run when sorted)
+  int best = -1;
+  for (size_t r = 0; r < it->runs.size(); r++) {
+    if (it->runs[r].pos >= it->runs[r].end) continue;
+    if (best < 0 || slot_cmp(c, &it->keys[it->runs[r].pos * c->kb], &it->keys[it->runs[best].pos * c->kb]) < 0) best = (int)r;
+  }
+  if (best < 0) return 0;
+  uint64_t i = it->runs[best].pos++;
+  const unsigned char* k = &it->keys[i * c->kb];
+  if (c->rb == 16) {
+    for (int b = 0; b < 8; b++) it->keybuf[b] = k[7 - b];  // 8-byte big-endian string
+    *key = it->keybuf;
+    *klen = 8;
+  } else {
+    *key = k;
+    *klen = strnlen((const char*)k, c->kb);
+  }
+  *values = &it->sums[i];
+  *nvalues = 1;
+  return 1;
+}
+
+void mrhbm_groups_close(mrhbm_iter* it) { delete it; }
+
+// ---------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------
+int mrhbm_comm_unique_id(mrhbm_ctx* c, void* id) {
+  if (!c || !id) return MRHBM_E_INVAL;
+  return comm_unique_id(id, &c->err);
+}
+int mrhbm_comm_init(mrhbm_ctx* c, const void* id, int rank, int world) {
+  if (!c || !id || world < 1 || rank < 0 || rank >= world) return MRHBM_E_INVAL;
+  if (world == 1) return MRHBM_OK;
+  return comm_create(&c->comm, id, rank, world, c->dev, &c->err);
+}
+
+}  // extern "C"

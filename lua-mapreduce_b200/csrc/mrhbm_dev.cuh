@@ -1,0 +1,212 @@
+// mrhbm_dev.cuh -- device-side record model, key ordering, partitioners.
+//
+// Record layouts (little endian words), see include/mrhbm.h:
+//   RB=16      : w[0..1] = u64 key, w[2..3] = u64 value (emitters store u32 value, zero pad;
+//                in-place partial sums of the big-bin path use all 64 bits)
+//   RB=32/64/128: w[0..KW) = key bytes zero padded (no NUL inside), w[KW] = u32 value
+// Key order = the reference's keys_sorted / merge order (mapreduce/utils.lua:123-128,214):
+// C-locale bytewise, shorter first == big-endian word compare of the zero padded slot;
+// u64 keys are the reference's 8-byte big-endian strings == numeric order.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mrhbm {
+
+template <int RB>
+struct Rec {
+  static constexpr int kWords = RB / 4;
+  static constexpr bool kU64 = (RB == 16);
+  static constexpr int kKeyWords = kU64 ? 2 : kWords - 1;  // 32-bit words of key
+  static constexpr int kKeyBytes = kKeyWords * 4;
+  static constexpr int kVec = RB / 16;  // uint4 per record
+};
+
+struct BinParams {
+  uint32_t P;            // partitions
+  uint32_t S;            // sub-bins per partition
+  uint32_t partitioner;  // MRHBM_PART_*
+  uint32_t ordered;      // 1: sub-bin = top key bits (partition becomes one ascending run)
+                         // 0: sub-bin = further hash bits (partition = S ascending runs)
+};
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  return mix64(x + 0x9E3779B97F4A7C15ull);
+}
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// i-th most significant 32-bit word of the key, as an unsigned big-endian number
+template <int RB>
+__device__ __forceinline__ uint32_t be_word(const uint32_t* r, int i) {
+  if constexpr (Rec<RB>::kU64) {
+    return i == 0 ? r[1] : (i == 1 ? r[0] : 0u);
+  } else {
+    return i < Rec<RB>::kKeyWords ? bswap32(r[i]) : 0u;
+  }
+}
+template <int RB>
+__device__ __forceinline__ uint64_t key_prefix64(const uint32_t* r) {
+  return ((uint64_t)be_word<RB>(r, 0) << 32) | be_word<RB>(r, 1);
+}
+// nbits (<=51) of the key starting `bitpos` bits below the most significant bit
+template <int RB>
+__device__ __forceinline__ uint64_t key_bits(const uint32_t* r, int bitpos, int nbits) {
+  int wi = bitpos >> 5, sh = bitpos & 31;
+  uint64_t hi = ((uint64_t)be_word<RB>(r, wi) << 32) | be_word<RB>(r, wi + 1);
+  uint64_t lo = (uint64_t)be_word<RB>(r, wi + 2) << 32;
+  uint64_t win = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+  return win >> (64 - nbits);
+}
+template <int RB>
+__device__ __forceinline__ int key_cmp(const uint32_t* a, const uint32_t* b) {
+#pragma unroll
+  for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
+    uint32_t x = be_word<RB>(a, i), y = be_word<RB>(b, i);
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return 0;
+}
+template <int RB>
+__device__ __forceinline__ bool key_eq(const uint32_t* a, const uint32_t* b) {
+  bool e = true;
+#pragma unroll
+  for (int i = 0; i < Rec<RB>::kKeyWords; i++) e &= (a[i] == b[i]);
+  return e;
+}
+template <int RB>
+__device__ __forceinline__ uint64_t rec_value(const uint32_t* r) {
+  if constexpr (Rec<RB>::kU64)
+    return (uint64_t)r[2] | ((uint64_t)r[3] << 32);
+  else
+    return r[Rec<RB>::kKeyWords];
+}
+
+// ---- partitioners ---------------------------------------------------------
+// examples/WordCount/partitionfn.lua:8-16 evaluated exactly as Lua 5.2 does, i.e. in IEEE
+// doubles: h*16777619 reaches ~2^56, so the product is rounded to 53 significant bits
+// (round-to-nearest-even) BEFORE "% 2^32".  Emulated with integers so no FP64 is issued.
+__host__ __device__ __forceinline__ uint32_t fnv_lua_step(uint32_t h, uint32_t byte) {
+  uint64_t p = (uint64_t)h * 16777619ull;
+  if (p >> 53) {
+#ifdef __CUDA_ARCH__
+    int sh = 64 - __clzll((long long)p) - 53;
+#else
+    int sh = 64 - __builtin_clzll(p) - 53;
+#endif
+    uint64_t half = 1ull << (sh - 1), rem = p & ((1ull << sh) - 1);
+    p >>= sh;
+    if (rem > half || (rem == half && (p & 1))) p++;
+    p <<= sh;
+  }
+  return (uint32_t)p ^ byte;
+}
+// h over the key bytes (u64 keys: the 8 big-endian bytes; strings: up to the first NUL)
+template <int RB>
+__device__ __forceinline__ uint32_t fnv_lua_hash(const uint32_t* r) {
+  uint32_t h = 2166136261u;
+  if constexpr (Rec<RB>::kU64) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t w = i < 4 ? r[1] : r[0];
+      h = fnv_lua_step(h, (w >> (24 - 8 * (i & 3))) & 0xff);
+    }
+  } else {
+    bool live = true;
+#pragma unroll
+    for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
+      uint32_t w = r[i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t b = (w >> (8 * j)) & 0xff;
+        live = live && (b != 0);
+        if (live) h = fnv_lua_step(h, b);
+      }
+    }
+  }
+  return h;
+}
+// 64-bit word hash over the little-endian u32 words of the key bytes while non-zero
+// (length-exact for NUL-free keys, independent of the slot width)
+template <int RB>
+__device__ __forceinline__ uint64_t word_hash(const uint32_t* r) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  bool live = true;
+#pragma unroll
+  for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
+    uint32_t w;
+    if constexpr (Rec<RB>::kU64)
+      w = bswap32(i == 0 ? r[1] : r[0]);  // LE load of the 8 big-endian key bytes
+    else
+      w = r[i];
+    live = live && (w != 0);
+    if (live) {
+      h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
+      h ^= h >> 29;
+    }
+  }
+  h ^= h >> 32;
+  h *= 0x94D049BB133111EBull;
+  return h;
+}
+
+// partition id and bin (= pid*S + sub) of a record held in registers / smem words
+template <int RB>
+__device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& bp, uint32_t* pid_out) {
+  uint32_t pid;
+  uint64_t frac;  // uniform 64-bit hash independent of pid, feeds the hash sub-bin
+  if (bp.partitioner == 1u && Rec<RB>::kU64) {  // MULHASH
+    uint64_t key = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
+    frac = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);
+  } else if (bp.partitioner == 0u) {  // FNV_LUA
+    pid = fnv_lua_hash<RB>(r) % bp.P;
+    frac = word_hash<RB>(r);
+  } else {  // WORDHASH
+    uint64_t h = word_hash<RB>(r);
+    pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
+    frac = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);
+  }
+  uint32_t sub = 0;
+  if (bp.S > 1) {
+    uint64_t src = bp.ordered ? key_prefix64<RB>(r) : frac;
+    sub = (uint32_t)__umul64hi(src, (uint64_t)bp.S);
+  }
+  if (pid_out) *pid_out = pid;
+  return pid * bp.S + sub;
+}
+
+// checksum mixers over the whole key slot (input and result share the slot format)
+template <int RB>
+__device__ __forceinline__ void key_mix2(const uint32_t* r, uint64_t& f1, uint64_t& f2) {
+  uint64_t a = 0x243F6A8885A308D3ull, b = 0x13198A2E03707344ull;
+#pragma unroll
+  for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
+    a = mix64(a ^ r[i]);
+    b = (b ^ r[i]) * 0x9FB21C651E98DF25ull;
+    b ^= b >> 28;
+  }
+  f1 = a;
+  f2 = mix64(b);
+}
+
+// ---- streaming global access ------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+}  // namespace mrhbm

@@ -1028,3 +1028,68 @@ size_t mro_groupby_rec(const void *recs, size_t n, uint32_t rec_bytes, int parti
   free(a);
   return g;
 }
+
+/* ======================================================================== */
+/* reference-shaped baseline runner                                         */
+/* ======================================================================== */
+#include <time.h>
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+typedef struct {
+  mro_t *o;
+  int kind;
+  uint64_t seed, start, per;
+  uint32_t njobs, next;
+  const uint64_t *table;
+  uint64_t V;
+  pthread_mutex_t mu;
+} sctx_t;
+static void *synthetic_worker(void *arg) {
+  sctx_t *c = (sctx_t *)arg;
+  for (;;) {
+    pthread_mutex_lock(&c->mu);
+    uint32_t j = c->next++;
+    pthread_mutex_unlock(&c->mu);
+    if (j >= c->njobs) break;
+    char name[32];
+    snprintf(name, sizeof name, "%u", j + 1);
+    mro_map_t *m = mro_map_begin(c->o, name);
+    uint64_t base = c->start + (uint64_t)j * c->per;
+    for (uint64_t i = 0; i < c->per; i++) { /* mapfn: emit(k, v) per pair */
+      if (c->kind == 0) {
+        uint64_t k = mro_splitmix64(c->seed + base + i);
+        uint32_t v = (uint32_t)(mro_splitmix64(c->seed + (1ull << 40) + base + i) >> 32);
+        unsigned char be[8];
+        for (int b = 0; b < 8; b++) be[b] = (unsigned char)(k >> (56 - 8 * b));
+        mro_emit_str(m, be, 8, (double)v);
+      } else {
+        char key[32];
+        uint64_t u = mro_splitmix64(c->seed + (1ull << 41) + base + i);
+        size_t l = mro_rank_to_key(mro_zipf_rank(c->table, c->V, u), key);
+        mro_emit_str(m, key, l, 1.0);
+      }
+    }
+    mro_map_commit(m);
+  }
+  return NULL;
+}
+int mro_run_synthetic(mro_t *o, int kind, uint64_t seed, uint64_t start, uint64_t pairs_per_job,
+                      uint32_t njobs, int nthreads, const uint64_t *table, uint64_t V,
+                      double *map_seconds, double *reduce_seconds) {
+  sctx_t c = {o, kind, seed, start, pairs_per_job, njobs, 0, table, V, PTHREAD_MUTEX_INITIALIZER};
+  pthread_t th[64];
+  if (nthreads > 64) nthreads = 64;
+  if (nthreads < 1) nthreads = 1;
+  double t0 = now_s();
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, synthetic_worker, &c);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  double t1 = now_s();
+  int r = mro_reduce_all(o, nthreads);
+  double t2 = now_s();
+  *map_seconds = t1 - t0;
+  *reduce_seconds = t2 - t1;
+  return r < 0 ? -1 : 0;
+}

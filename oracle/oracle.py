@@ -84,6 +84,7 @@ def lib():
     sig("mro_gen_zipf_rec32", None, u64, u64, sz, vp, u64, vp)
     sig("mro_groupby_u64", sz, vp, vp, sz, i, u32, vp, vp, vp)
     sig("mro_groupby_rec", sz, vp, sz, u32, i, u32, vp, vp, vp)
+    sig("mro_run_synthetic", i, vp, i, u64, u64, u64, u32, i, vp, u64, C.POINTER(dbl), C.POINTER(dbl))
     _lib = L
     return L
 
@@ -263,3 +264,16 @@ def groupby_rec(recs, partitioner, nparts):
     g = lib().mro_groupby_rec(recs.ctypes.data, n, rb, partitioner, nparts, okeys.ctypes.data,
                               os_.ctypes.data, po.ctypes.data)
     return okeys[:g].copy(), os_[:g].copy(), po
+
+
+def run_synthetic(engine, kind, seed, start, pairs_per_job, njobs, nthreads, table=None):
+    """bench.py --impl reference: njobs map jobs + all reduce jobs on nthreads workers.
+    Returns (map_seconds, reduce_seconds)."""
+    t = np.ascontiguousarray(table, dtype=np.uint64) if table is not None else None
+    ms, rs = C.c_double(), C.c_double()
+    r = lib().mro_run_synthetic(engine.h, kind, seed, start, pairs_per_job, njobs, nthreads,
+                                t.ctypes.data if t is not None else None, t.size if t is not None else 0,
+                                C.byref(ms), C.byref(rs))
+    if r != 0:
+        raise RuntimeError(lib().mro_error(engine.h).decode())
+    return ms.value, rs.value

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA shuffle/sort/reduce path (through the C ABI) against the CPU oracle on
+the same seeded inputs, against the golden word count, and -- at larger sizes -- through
+size-independent properties (linearity of the sum, sortedness, partition membership)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import mrhbm_loader
+import oracle as O
+from conftest import expand_tokens
+
+mrhbm_loader.load()
+from lua_mapreduce_b200 import mrhbm, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+SEED = synth.SEED
+
+
+def u64_records(keys, vals):
+    recs = np.zeros(keys.size, dtype=mrhbm.record_dtype(mrhbm.KEY_U64))
+    recs["key"], recs["val"] = keys, vals
+    return recs
+
+
+def check_vs_oracle_u64(ctx, keys, vals, P, partitioner=O.PART_MULHASH):
+    ok, osum, po = O.groupby_u64(keys, vals, partitioner, P)
+    info = ctx.result_info()
+    assert info.groups == ok.size and info.pairs_in == keys.size
+    gk, gs, gpo = ctx.result_copy()
+    assert (gpo == po).all()
+    if info.sorted:
+        assert (gk == ok).all() and (gs == osum).all()
+    else:  # partition = several ascending runs: compare as sorted sets per partition
+        for p in range(P):
+            a, b = int(po[p]), int(po[p + 1])
+            order = np.argsort(gk[a:b], kind="stable")
+            assert (gk[a:b][order] == ok[a:b]).all() and (gs[a:b][order] == osum[a:b]).all()
+    # the iterator always yields ascending keys (utils.merge_iterator order), 8-byte BE keys
+    nonempty = [p for p in range(P) if po[p + 1] > po[p]]
+    assert ctx.partitions() == nonempty
+    for p in nonempty[:3] + nonempty[-2:]:
+        got = list(ctx.groups(p))
+        a, b = int(po[p]), int(po[p + 1])
+        assert [int.from_bytes(k, "big") for k, _ in got] == ok[a:b].tolist()
+        assert [v[0] for _, v in got] == osum[a:b].tolist()
+    cin, cout = ctx.checksum_input(), ctx.checksum_result()
+    assert cin[:3] == cout[:3] and cin[3] == keys.size and cout[3] == ok.size and cout[4:] == [0, 0]
+
+
+@pytest.mark.parametrize("n,P", [(1, 1), (37, 4), (5000, 16), (200_000, 16), (1_000_000, 1024)])
+def test_u64_uniform_vs_oracle(n, P):
+    keys, vals = O.gen_u64(SEED, 0, n)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P) as ctx:
+        m = ctx.map_begin("m1")
+        m.emit_batch(u64_records(keys, vals))
+        m.commit()
+        ctx.shuffle()
+        assert ctx.stats()["attempts"] == 1
+        check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def test_device_generator_matches_oracle_stream():
+    n, P = 300_000, 64
+    keys, vals = O.gen_u64(SEED, 12345, n)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P) as ctx:
+        for j in range(3):  # three map jobs over disjoint counter ranges
+            m = ctx.map_begin(j)
+            m.gen_u64(SEED, 12345 + j * 100_000, 100_000)
+            m.commit()
+        ctx.shuffle()
+        check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def test_u64_duplicates_and_hot_key():
+    """few distinct keys + one hot key: key-ordered bins overflow -> hash sub-bins -> big-bin path"""
+    rng = np.random.default_rng(3)
+    n, P = 400_000, 8
+    keys = O.gen_u64(SEED, 0, 2000)[0][rng.integers(0, 2000, n)]
+    keys[rng.random(n) < 0.3] = np.uint64(0xDEADBEEFCAFEF00D)
+    vals = rng.integers(0, 1 << 20, n).astype(np.uint32)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P) as ctx:
+        m = ctx.map_begin("dups")
+        m.emit_batch(u64_records(keys, vals))
+        m.commit()
+        ctx.shuffle()
+        st = ctx.stats()
+        assert st["big_bins"] >= 1
+        check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def test_u64_clustered_keys_fall_back_to_runs():
+    """sequential integers: top key bits are constant, so key-ordered sub-bins cannot balance"""
+    n, P = 300_000, 4
+    keys = np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(17)
+    vals = np.ones(n, dtype=np.uint32)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P) as ctx:
+        m = ctx.map_begin("seq")
+        m.emit_batch(u64_records(keys, vals))
+        m.commit()
+        ctx.shuffle()
+        assert ctx.stats()["attempts"] == 2 and ctx.result_info().sorted == 0
+        check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def test_u64_scalar_emit_path_and_staging_flush():
+    n, P = 150_000, 16  # > 2 staging buffers of 65536 records
+    keys, vals = O.gen_u64(SEED, 777, n)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, flags=mrhbm.F_FORCE_RUNS) as ctx:
+        m = ctx.map_begin("scalar")
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            m.emit(k, v)
+        m.commit()
+        ctx.shuffle()
+        check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def str_records(words, vals, max_key_bytes):
+    recs = np.zeros(len(words), dtype=mrhbm.record_dtype(mrhbm.KEY_STR, max_key_bytes))
+    recs["key"] = words
+    recs["val"] = vals
+    return recs
+
+
+def check_vs_oracle_str(ctx, recs, P, partitioner):
+    raw = recs.view(np.uint8).reshape(len(recs), -1)
+    okeys, osum, po = O.groupby_rec(raw, partitioner, P)
+    info = ctx.result_info()
+    assert info.groups == osum.size
+    gk, gs, gpo = ctx.result_copy()
+    assert (gpo == po).all()
+    want = [bytes(k).rstrip(b"\0") for k in okeys]
+    for p in range(P):
+        a, b = int(po[p]), int(po[p + 1])
+        got = list(ctx.groups(p))
+        assert [k for k, _ in got] == want[a:b]
+        assert [v[0] for _, v in got] == osum[a:b].tolist()
+        assert sorted(zip(gk[a:b].tolist(), gs[a:b].tolist())) == list(zip(want[a:b], osum[a:b].tolist()))
+    cin, cout = ctx.checksum_input(), ctx.checksum_result()
+    assert cin[:3] == cout[:3] and cout[3] == osum.size and cout[4:] == [0, 0]
+
+
+def test_wordcount_golden_through_c_abi(golden_vectors, golden_wordcount):
+    """test.sh:8-53 on the reference's own corpus: 4 map jobs, FNV-in-doubles partitioner mod 15,
+    sum reducer; keys up to 84 bytes -> 128-byte records.  Must equal misc/naive.lua."""
+    with mrhbm.Ctx(mrhbm.KEY_STR, 15, mrhbm.PART_FNV_LUA, max_key_bytes=golden_vectors["max_key_len"]) as ctx:
+        assert ctx.record_bytes == 128
+        for job in range(4):
+            m = ctx.map_begin(job + 1)
+            for t in expand_tokens(golden_wordcount, job):
+                m.emit(t, 1)
+            m.commit()
+        ctx.shuffle()
+        assert ctx.partitions() == list(range(15))
+        got = {}
+        for p in ctx.partitions():
+            ks = []
+            for k, v in ctx.groups(p):
+                assert len(v) == 1
+                got[k] = (p, v[0])
+                ks.append(k)
+            assert ks == sorted(ks)
+        assert got == {k: (p, sum(c)) for k, p, c in golden_wordcount}
+        per = [sum(1 for k in got if got[k][0] == p) for p in range(15)]
+        assert per == golden_vectors["distinct_per_partition"]
+        lines = sorted(b"%d %s\n" % (c, k) for k, (_, c) in got.items())
+        assert hashlib.sha256(b"".join(lines)).hexdigest() == golden_vectors["sha256_sorted_count_word_lines"]
+
+
+@pytest.mark.parametrize("partitioner", [mrhbm.PART_FNV_LUA, mrhbm.PART_WORDHASH])
+def test_zipf_strings_vs_oracle(partitioner):
+    """Zipf(1.1) word stream generated on the device == the oracle's stream; hot keys exercise
+    the big-bin path."""
+    V, n, P = 1 << 14, 400_000, 15
+    table = synth.zipf_table(V)
+    recs = O.gen_zipf_rec32(SEED, 0, n, table)
+    opart = O.PART_FNV_LUA if partitioner == mrhbm.PART_FNV_LUA else O.PART_FNV64
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, partitioner, max_key_bytes=27) as ctx:
+        for j in range(2):
+            m = ctx.map_begin(j)
+            m.gen_zipf(SEED, j * (n // 2), n // 2, table)
+            m.commit()
+        ctx.shuffle()
+        assert ctx.stats()["big_bins"] >= 1
+        check_vs_oracle_str(ctx, recs.view(mrhbm.record_dtype(mrhbm.KEY_STR, 27)).reshape(-1), P, opart)
+
+
+@pytest.mark.parametrize("mkb", [27, 59, 123])
+def test_shared_prefix_keys_take_the_full_key_path(mkb):
+    """keys that agree on their first 8+ bytes force the multi-pass (whole key) ordering"""
+    rng = np.random.default_rng(11)
+    n, P = 60_000, 5
+    stems = [b"internationalisation", b"internat", b"interna", b"x" * (mkb - 6), b""]
+    words = []
+    for i in rng.integers(0, 3000, n):
+        s = stems[i % len(stems)]
+        words.append((s + b"%d" % (i // len(stems)))[:mkb])
+    vals = rng.integers(1, 100, n).astype(np.uint32)
+    recs = str_records(words, vals, mkb)
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_WORDHASH, max_key_bytes=mkb) as ctx:
+        m = ctx.map_begin("p")
+        m.emit_batch(recs)
+        m.commit()
+        ctx.shuffle()
+        check_vs_oracle_str(ctx, recs, P, O.PART_FNV64)
+
+
+def test_small_bins_flag_exercises_overflow_paths():
+    keys, vals = O.gen_u64(SEED, 0, 50_000)
+    keys[::7] = keys[0]
+    with mrhbm.Ctx(mrhbm.KEY_U64, 4, flags=mrhbm.F_SMALL_BINS) as ctx:
+        m = ctx.map_begin("s")
+        m.emit_batch(u64_records(keys, vals))
+        m.commit()
+        ctx.shuffle()
+        assert ctx.stats()["big_bins"] >= 1
+        check_vs_oracle_u64(ctx, keys, vals, 4)
+
+
+def test_commit_replaces_abort_discards_and_empty_shuffle():
+    """job.lua:217-221 (remove_file + build), worker.lua:120-127 (BROKEN job), server.lua:300-324"""
+    with mrhbm.Ctx(mrhbm.KEY_STR, 15, mrhbm.PART_FNV_LUA) as ctx:
+        ctx.shuffle()  # nothing committed
+        assert ctx.partitions() == [] and ctx.result_info().groups == 0
+        m = ctx.map_begin(1)
+        m.emit(b"a", 1)
+        m.emit(b"a", 1)
+        m.commit()
+        m = ctx.map_begin(2)
+        m.emit(b"zzz", 9)
+        m.abort()
+        m = ctx.map_begin(1)  # re-execution of job 1 replaces its output
+        m.emit(b"a", 5)
+        m.commit()
+        m = ctx.map_begin(3)  # a job that emits nothing
+        m.commit()
+        ctx.shuffle()
+        assert ctx.partitions() == [10]  # "a" -> partition 10
+        assert list(ctx.groups(10)) == [(b"a", [5])]
+        with pytest.raises(mrhbm.MrhbmError):
+            m = ctx.map_begin(4)
+            m.emit(b"x" * 28, 1)  # does not fit the 32-byte record class
+        m.abort()
+        with pytest.raises(mrhbm.MrhbmError):
+            ctx.map_begin(5).emit(b"a\0b", 1)
+        ctx.reset()
+        ctx.shuffle()
+        assert ctx.partitions() == []
+
+
+def test_properties_at_10_pow_7():
+    """size-independent parity: sum linearity, strict ascending order, partition membership"""
+    n, P = 10_000_000, 1024
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, reserve_pairs=n) as ctx:
+        m = ctx.map_begin("big")
+        m.gen_u64(SEED, 0, n)
+        m.commit()
+        ctx.shuffle()
+        cin, cout = ctx.checksum_input(), ctx.checksum_result()
+        assert cin[:3] == cout[:3] and cin[3] == n and cout[4:] == [0, 0]
+        keys, vals = O.gen_u64(SEED, 0, n)
+        assert cout[3] == np.unique(keys).size and cin[2] == int(vals.astype(np.uint64).sum())
+        assert ctx.result_info().sorted == 1
