@@ -2,8 +2,10 @@
 // bookkeeping (commit = replace-by-job-id, abort = discard; mapreduce/job.lua:217-221,
 // worker.lua:120-127), the shuffle driver, result iteration.  No CPU fallback anywhere.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,7 +40,8 @@ struct mrhbm_ctx {
   // shuffle state
   ShuffleBuffers sb{};
   uint64_t B_cap = 0, mid_cap = 0, out_cap = 0;
-  uint32_t B = 0, S = 1, ordered = 1, cap = 0;
+  uint32_t B = 0, S = 1, ordered = 1, cap = 0, ctr_shift = 3;
+  uint64_t ctr_cap = 0;
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
   std::vector<uint32_t> h_bin_off, h_uoff;
@@ -188,13 +191,23 @@ void invalidate(mrhbm_ctx* c) {
 int ensure_buffers(mrhbm_ctx* c, uint64_t B, uint64_t N) {
   if (B + 1 > c->B_cap) {
     uint64_t nb = B + 1 + (B >> 2);
-    uint32_t** ptrs[] = {&c->sb.hist, &c->sb.bin_off, &c->sb.cursor, &c->sb.ucount, &c->sb.uoff, &c->sb.big_list};
+    uint32_t** ptrs[] = {&c->sb.bin_off, &c->sb.ucount, &c->sb.uoff, &c->sb.big_list};
     for (auto p : ptrs) {
       if (*p) CU(c, cudaFree(*p));
       *p = nullptr;
       CU(c, cudaMalloc((void**)p, nb * sizeof(uint32_t)));
     }
     c->B_cap = nb;
+  }
+  if ((B << c->ctr_shift) > c->ctr_cap) {  // spread-out atomic counters
+    uint64_t nc = (B + (B >> 2) + 1) << c->ctr_shift;
+    uint32_t** ptrs[] = {&c->sb.hist, &c->sb.cursor};
+    for (auto p : ptrs) {
+      if (*p) CU(c, cudaFree(*p));
+      *p = nullptr;
+      CU(c, cudaMalloc((void**)p, nc * sizeof(uint32_t)));
+    }
+    c->ctr_cap = nc;
   }
   if (!c->sb.counters) CU(c, cudaMalloc((void**)&c->sb.counters, 8 * sizeof(uint32_t)));
   uint64_t need = std::max<uint64_t>(N, 1);
@@ -315,6 +328,7 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   CU(c, cudaHostAlloc((void**)&c->h_acc, 8 * sizeof(uint64_t), cudaHostAllocDefault));
   c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
+  if (const char* e = getenv("MRHBM_CTR_SHIFT")) c->ctr_shift = (uint32_t)std::min(7, std::max(0, atoi(e)));  // tuning hook
   if (cfg->reserve_pairs) {
     uint64_t off;
     int rc = pool_reserve(c, cfg->reserve_pairs, &off);
@@ -552,35 +566,41 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
   for (auto& r : live) N += r.second;
   if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
   const uint32_t P = c->cfg.num_partitions;
-  // mean bin = 84% of what one CTA sorts in shared memory
-  uint64_t target = std::max<uint64_t>(1, (uint64_t)c->cap * 84 / 100);
+  // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill
+  uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap));
   uint64_t S64 = (N + (uint64_t)P * target - 1) / ((uint64_t)P * target);
   uint32_t S = (uint32_t)std::max<uint64_t>(1, S64);
-  uint64_t B = (uint64_t)P * S;
-  if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
-  int rc = ensure_buffers(c, B, N);
-  if (rc) return rc;
-  uint32_t ordered = (c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS)) || S == 1;
+  int rc = 0;
+  uint32_t nbig = 0;
   mrhbm_stats st{};
   st.pairs = N;
   cudaStream_t s = c->stream;
+  uint32_t ordered = 1;
+  uint64_t B = 0;
   CU(c, cudaEventRecord(c->ev[EV_START], s));
-  uint32_t nbig = 0;
+  // A bin that holds more distinct keys than one CTA sorts (ERRF_SKEW) is retried with
+  // twice the sub-bins: distinct keys spread, hot keys keep collapsing in k_big_bins.
+  for (int widen = 0;; widen++) {
+  B = (uint64_t)P * S;
+  if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
+  rc = ensure_buffers(c, B, N);
+  if (rc) return rc;
+  ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
   for (int attempt = 0;; attempt++) {
-    st.attempts = attempt + 1;
-    CU(c, cudaMemsetAsync(c->sb.hist, 0, B * sizeof(uint32_t), s));
+    st.attempts++;
+    CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     for (auto& r : live)
-      st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->sb.hist, s);
+      st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->ctr_shift, c->sb.hist, s);
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
     st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->cap, c->sb.big_list,
-                                 c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, s);
+                                 c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
     CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
     CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
     for (auto& r : live)
-      st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->sb.cursor, c->sb.mid, s);
+      st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->ctr_shift, c->sb.cursor, c->sb.mid, s);
     CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
@@ -598,7 +618,7 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
   st.launches += launch_big_bins(c->rb, c->sb, nbig, c->cap, s);
   CU(c, cudaEventRecord(c->ev[EV_BIG], s));
   st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, 0xffffffffu, nullptr, nullptr,
-                               c->sb.counters + CNT_TOTAL, s);
+                               c->sb.counters + CNT_TOTAL, 0, s);
   c->h_bin_off.resize(B + 1);
   c->h_uoff.resize(B + 1);
   CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->sb.bin_off, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
@@ -609,8 +629,15 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
   CU(c, cudaStreamSynchronize(s));
   uint32_t ef = c->h_counters[CNT_ERR];
   if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
-  if (ef & ERRF_SKEW)
+  if (ef & ERRF_SKEW) {
+    if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
+      S *= 2;
+      continue;
+    }
     return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can sort (%u oversized bins)", nbig);
+  }
+  break;
+  }  // widen
   c->B = (uint32_t)B;
   c->S = S;
   c->ordered = ordered;

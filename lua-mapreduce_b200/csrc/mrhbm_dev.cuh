@@ -28,6 +28,8 @@ struct BinParams {
   uint32_t partitioner;  // MRHBM_PART_*
   uint32_t ordered;      // 1: sub-bin = top key bits (partition becomes one ascending run)
                          // 0: sub-bin = further hash bits (partition = S ascending runs)
+  uint32_t ctr_shift;    // hist / cursor counters live at index bin << ctr_shift: the L2
+                         // atomic unit serialises per 32 B sector, so counters are spread out
 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -64,6 +66,10 @@ __device__ __forceinline__ uint64_t key_bits(const uint32_t* r, int bitpos, int 
 }
 template <int RB>
 __device__ __forceinline__ int key_cmp(const uint32_t* a, const uint32_t* b) {
+  if constexpr (Rec<RB>::kU64) {
+    uint64_t x = (uint64_t)a[0] | ((uint64_t)a[1] << 32), y = (uint64_t)b[0] | ((uint64_t)b[1] << 32);
+    return (x > y) - (x < y);
+  }
 #pragma unroll
   for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
     uint32_t x = be_word<RB>(a, i), y = be_word<RB>(b, i);

@@ -11,14 +11,11 @@
 #include "mrhbm_kernels.h"
 
 #include "mrhbm_dev.cuh"
+#include "mrhbm_sort.cuh"
 
 namespace mrhbm {
 
 static int g_sm_count = 148;
-constexpr int kSortThreads = 512;
-constexpr int kIdxBits = 12;  // kCapBytes/16 = 4096 records at most
-constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
-constexpr int kDigitBits = 64 - kIdxBits;
 
 // ============================================================================
 // synthetic device-side mapfn
@@ -92,31 +89,53 @@ __device__ __forceinline__ void load_rec(const uint4* p, uint32_t* w) {
   }
 }
 
+// U records per thread per iteration: all loads first, then all atomics, then all stores, so
+// that each thread keeps U independent memory chains in flight (the loop is latency-bound:
+// load -> L2 atomic -> store).
+template <int RB>
+struct Unroll {
+  static constexpr int U = RB == 16 ? 8 : RB == 32 ? 4 : RB == 64 ? 2 : 1;
+};
+
 template <int RB>
 __global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                               uint32_t* __restrict__ hist) {
+  constexpr int U = Unroll<RB>::U;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t w[Rec<RB>::kWords];
-    load_rec<RB>(recs + i * Rec<RB>::kVec, w);
-    uint32_t bin = bin_of<RB>(w, bp, nullptr);
-    atomicAdd(hist + bin, 1u);  // RED: no return value
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
+    uint32_t w[U][Rec<RB>::kWords];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      if (base + k * stride < n) atomicAdd(hist + ((size_t)bin_of<RB>(w[k], bp, nullptr) << bp.ctr_shift), 1u);  // RED
   }
 }
 
 template <int RB>
 __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                                  uint32_t* __restrict__ cursor, uint4* __restrict__ mid) {
+  constexpr int U = Unroll<RB>::U;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t w[Rec<RB>::kWords];
-    load_rec<RB>(recs + i * Rec<RB>::kVec, w);
-    uint32_t bin = bin_of<RB>(w, bp, nullptr);
-    uint32_t pos = atomicAdd(cursor + bin, 1u);
-    uint4* d = mid + (uint64_t)pos * Rec<RB>::kVec;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
+    uint32_t w[U][Rec<RB>::kWords];
+    uint32_t pos[U];
 #pragma unroll
-    for (int v = 0; v < Rec<RB>::kVec; v++)
-      stg_stream(d + v, make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]));
+    for (int k = 0; k < U; k++)
+      if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      if (base + k * stride < n) pos[k] = atomicAdd(cursor + ((size_t)bin_of<RB>(w[k], bp, nullptr) << bp.ctr_shift), 1u);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (base + k * stride < n) {
+        uint4* d = mid + (uint64_t)pos[k] * Rec<RB>::kVec;
+#pragma unroll
+        for (int v = 0; v < Rec<RB>::kVec; v++)
+          stg_stream(d + v, make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]));
+      }
+    }
   }
 }
 
@@ -126,13 +145,13 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
                                                  uint32_t* __restrict__ out_excl,
                                                  uint32_t* __restrict__ out_copy, uint32_t cap,
                                                  uint32_t* __restrict__ big_list, uint32_t* nbig,
-                                                 uint32_t* total) {
+                                                 uint32_t* total, uint32_t shift) {
   __shared__ uint32_t warp_sums[32];
   const uint32_t T = blockDim.x, tid = threadIdx.x;
   uint32_t per = (n + T - 1) / T;
   uint32_t b0 = tid * per, b1 = min(n, b0 + per);
   uint32_t s = 0;
-  for (uint32_t i = b0; i < b1; i++) s += in[i];
+  for (uint32_t i = b0; i < b1; i++) s += in[(size_t)i << shift];
   uint32_t incl = s;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -153,9 +172,9 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
   __syncthreads();
   uint32_t run = warp_sums[tid >> 5] + incl - s;
   for (uint32_t i = b0; i < b1; i++) {
-    uint32_t c = in[i];
+    uint32_t c = in[(size_t)i << shift];
     out_excl[i] = run;
-    if (out_copy) out_copy[i] = run;
+    if (out_copy) out_copy[(size_t)i << shift] = run;
     if (big_list && c > cap) big_list[atomicAdd(nbig, 1u)] = i;
     run += c;
   }
@@ -163,281 +182,6 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
     out_excl[n] = run;
     if (total) *total = run;
   }
-}
-
-// ============================================================================
-// per-bin sort + segmented reduce in shared memory
-// ============================================================================
-struct SortSmem {
-  uint4* rec;        // cap records
-  uint64_t* comp;    // cap composite words (digit << kIdxBits | index)
-  uint16_t* permA;   // cap
-  uint16_t* permB;   // cap
-  uint64_t* red;     // 64 words of reduction scratch
-};
-__host__ __device__ inline size_t sort_smem_bytes(int rb) {
-  size_t cap = kCapBytes / rb;
-  return (size_t)kCapBytes + cap * 8 + cap * 2 * 2 + 64 * 8;
-}
-__device__ __forceinline__ SortSmem carve(unsigned char* base, int rb) {
-  size_t cap = kCapBytes / rb;
-  SortSmem s;
-  s.rec = (uint4*)base;
-  s.comp = (uint64_t*)(base + kCapBytes);
-  s.permA = (uint16_t*)(base + kCapBytes + cap * 8);
-  s.permB = s.permA + cap;
-  s.red = (uint64_t*)(base + kCapBytes + cap * 8 + cap * 4);
-  return s;
-}
-
-// ascending bitonic sort of comp[0..n2), n2 a power of two >= 64
-__device__ __forceinline__ void bitonic_sort(uint64_t* comp, uint32_t n2) {
-  const uint32_t tid = threadIdx.x, T = blockDim.x, half = n2 >> 1;
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = tid; t < half; t += T) {
-        uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // insert a 0 bit at log2(j)
-        uint32_t l = i | j;
-        uint64_t a = comp[i], b = comp[l];
-        bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          comp[i] = b;
-          comp[l] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// in-place exclusive scan of a[0..n) (n <= 4096) by the whole CTA; returns the total
-__device__ __forceinline__ uint32_t block_exscan(uint32_t* a, uint32_t n, uint32_t* scratch33) {
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
-  uint32_t per = (n + T - 1) / T;
-  uint32_t b0 = min(n, tid * per), b1 = min(n, b0 + per);
-  uint32_t s = 0;
-  for (uint32_t i = b0; i < b1; i++) s += a[i];
-  uint32_t incl = s;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((tid & 31) >= (uint32_t)d) incl += t;
-  }
-  if ((tid & 31) == 31) scratch33[tid >> 5] = incl;
-  __syncthreads();
-  if (tid < 32) {
-    uint32_t w = tid < (T >> 5) ? scratch33[tid] : 0u, wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-      if (tid >= (uint32_t)d) wi += t;
-    }
-    scratch33[tid] = wi - w;
-    if (tid == 31) scratch33[32] = wi;
-  }
-  __syncthreads();
-  uint32_t run = scratch33[tid >> 5] + incl - s;
-  for (uint32_t i = b0; i < b1; i++) {
-    uint32_t c = a[i];
-    a[i] = run;
-    run += c;
-  }
-  uint32_t total = scratch33[32];
-  __syncthreads();
-  return total;
-}
-
-enum { MODE_FINAL = 0, MODE_PARTIAL = 1 };
-struct ChunkOut {
-  void* keys;          // FINAL: key slots; PARTIAL: AoS records (uint4)
-  uint64_t* sums;      // FINAL only
-  uint64_t base;       // element offset into the destination
-  uint32_t* err_flags;
-};
-
-// Sorts cnt (<= cap) records of one bin by key, sums the values of equal keys and writes
-// the groups in ascending key order.  Returns the number of groups.
-template <int RB, int MODE, bool NC>
-__device__ uint32_t process_chunk(const SortSmem& sm, const uint4* __restrict__ src, uint32_t cnt,
-                                  const ChunkOut& out) {
-  using R = Rec<RB>;
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
-  const uint32_t* recw = (const uint32_t*)sm.rec;
-  // 1. coalesced load of the bin
-  for (uint32_t v = tid; v < cnt * R::kVec; v += T) sm.rec[v] = NC ? ldg_stream(src + v) : src[v];
-  __syncthreads();
-  // 2. range of the 64-bit key prefix
-  uint64_t pmin = ~0ull, pmax = 0;
-  for (uint32_t i = tid; i < cnt; i += T) {
-    uint64_t p = key_prefix64<RB>(recw + i * R::kWords);
-    pmin = p < pmin ? p : pmin;
-    pmax = p > pmax ? p : pmax;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    uint64_t a = __shfl_xor_sync(0xffffffffu, pmin, d), b = __shfl_xor_sync(0xffffffffu, pmax, d);
-    pmin = a < pmin ? a : pmin;
-    pmax = b > pmax ? b : pmax;
-  }
-  if ((tid & 31) == 0) {
-    sm.red[tid >> 5] = pmin;
-    sm.red[32 + (tid >> 5)] = pmax;
-  }
-  __syncthreads();
-  pmin = ~0ull;
-  pmax = 0;
-  for (uint32_t w = 0; w < (T >> 5); w++) {
-    uint64_t a = sm.red[w], b = sm.red[32 + w];
-    pmin = a < pmin ? a : pmin;
-    pmax = b > pmax ? b : pmax;
-  }
-  __syncthreads();
-  uint64_t range = pmax - pmin;
-  int bits = range ? 64 - __clzll((long long)range) : 0;
-  int drop = bits > kDigitBits ? bits - kDigitBits : 0;
-  uint32_t n2 = 64;
-  while (n2 < cnt) n2 <<= 1;
-  // 3. composite words: most significant kDigitBits of the normalised prefix + index
-  for (uint32_t i = tid; i < n2; i += T) {
-    uint64_t c = ~0ull;
-    if (i < cnt) c = (((key_prefix64<RB>(recw + i * R::kWords) - pmin) >> drop) << kIdxBits) | i;
-    sm.comp[i] = c;
-  }
-  __syncthreads();
-  bitonic_sort(sm.comp, n2);
-  // 4. permutation + do equal digits hide different keys?
-  int tie = 0;
-  for (uint32_t j = tid; j < cnt; j += T) {
-    uint64_t c = sm.comp[j];
-    sm.permA[j] = (uint16_t)(c & kIdxMask);
-    if (j > 0 && (R::kKeyWords > 2 || drop > 0)) {
-      uint64_t p = sm.comp[j - 1];
-      if ((c >> kIdxBits) == (p >> kIdxBits) &&
-          !key_eq<RB>(recw + (uint32_t)(c & kIdxMask) * R::kWords,
-                      recw + (uint32_t)(p & kIdxMask) * R::kWords))
-        tie = 1;
-    }
-  }
-  uint16_t* perm = sm.permA;
-  uint16_t* other = sm.permB;
-  if (__syncthreads_or(tie)) {
-    // 5. rare: LSD passes over kDigitBits-wide chunks of the whole key; the previous rank
-    //    in the low bits makes every pass stable
-    constexpr int kKeyBits = R::kKeyWords * 32;
-    constexpr int kChunks = (kKeyBits + kDigitBits - 1) / kDigitBits;
-    for (int c = kChunks - 1; c >= 0; c--) {
-      int bitpos = c * kDigitBits;
-      int nb = kKeyBits - bitpos < kDigitBits ? kKeyBits - bitpos : kDigitBits;
-      for (uint32_t j = tid; j < n2; j += T) {
-        uint64_t w = ~0ull;
-        if (j < cnt) w = (key_bits<RB>(recw + (uint32_t)perm[j] * R::kWords, bitpos, nb) << kIdxBits) | j;
-        sm.comp[j] = w;
-      }
-      __syncthreads();
-      bitonic_sort(sm.comp, n2);
-      for (uint32_t j = tid; j < cnt; j += T) other[j] = perm[sm.comp[j] & kIdxMask];
-      __syncthreads();
-      uint16_t* t = perm;
-      perm = other;
-      other = t;
-    }
-  }
-  // 6. group heads and their output slots
-  uint32_t* slot = (uint32_t*)sm.comp;  // comp is free now
-  for (uint32_t j = tid; j < cnt; j += T) {
-    uint32_t head = 1;
-    if (j > 0) head = !key_eq<RB>(recw + (uint32_t)perm[j] * R::kWords, recw + (uint32_t)perm[j - 1] * R::kWords);
-    other[j] = (uint16_t)head;
-    slot[j] = head;
-  }
-  __syncthreads();
-  uint32_t groups = block_exscan(slot, cnt, (uint32_t*)sm.red);
-  // 7. segmented sum by the head thread and write-out
-  for (uint32_t j = tid; j < cnt; j += T) {
-    if (!other[j]) continue;
-    const uint32_t* r = recw + (uint32_t)perm[j] * R::kWords;
-    uint64_t s = rec_value<RB>(r);
-    for (uint32_t k = j + 1; k < cnt && !other[k]; k++) s += rec_value<RB>(recw + (uint32_t)perm[k] * R::kWords);
-    uint64_t o = out.base + slot[j];
-    if (MODE == MODE_FINAL) {
-      if constexpr (R::kU64) {
-        ((uint64_t*)out.keys)[o] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-      } else {
-        uint32_t* d = (uint32_t*)out.keys + o * R::kKeyWords;
-#pragma unroll
-        for (int w = 0; w < R::kKeyWords; w++) d[w] = r[w];
-      }
-      out.sums[o] = s;
-    } else {
-      uint32_t* d = (uint32_t*)out.keys + o * R::kWords;
-#pragma unroll
-      for (int w = 0; w < R::kKeyWords; w++) d[w] = r[w];
-      if constexpr (R::kU64) {
-        d[2] = (uint32_t)s;
-        d[3] = (uint32_t)(s >> 32);
-      } else {
-        if (s > 0xffffffffull) atomicOr(out.err_flags, (uint32_t)ERRF_OVERFLOW);
-        d[R::kKeyWords] = (uint32_t)s;
-      }
-    }
-  }
-  __syncthreads();
-  return groups;
-}
-
-template <int RB>
-__global__ void __launch_bounds__(kSortThreads, 2)
-    k_sort_reduce(ShuffleBuffers b, uint32_t B, uint32_t cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_bin;
-  SortSmem sm = carve(smem_raw, RB);
-  for (;;) {
-    if (threadIdx.x == 0) s_bin = atomicAdd(b.counters + CNT_TICKET, 1u);
-    __syncthreads();
-    uint32_t bin = s_bin;
-    __syncthreads();
-    if (bin >= B) break;
-    uint32_t off = b.bin_off[bin], cnt = b.bin_off[bin + 1] - off;
-    if (cnt > cap) continue;  // k_big_bins
-    if (cnt == 0) {
-      if (threadIdx.x == 0) b.ucount[bin] = 0;
-      continue;
-    }
-    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
-    uint32_t g = process_chunk<RB, MODE_FINAL, true>(sm, (const uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec, cnt, out);
-    if (threadIdx.x == 0) b.ucount[bin] = g;
-  }
-}
-
-// One CTA per oversized bin (hot keys): chunk-wise in-place reduce until the bin fits.
-template <int RB>
-__global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, uint32_t cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortSmem sm = carve(smem_raw, RB);
-  uint32_t bin = b.big_list[blockIdx.x];
-  uint32_t off = b.bin_off[bin], n = b.bin_off[bin + 1] - off;
-  uint4* base = (uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
-  while (n > cap) {
-    uint32_t w = 0;
-    for (uint32_t c = 0; c < n; c += cap) {
-      uint32_t m = n - c < cap ? n - c : cap;
-      ChunkOut out{base, nullptr, w, b.counters + CNT_ERR};
-      // groups of a chunk never outnumber the records consumed so far: w + g <= c + m
-      w += process_chunk<RB, MODE_PARTIAL, false>(sm, base + (uint64_t)c * Rec<RB>::kVec, m, out);
-      __threadfence_block();
-    }
-    if (w == n) {  // nothing merged: more distinct keys than one CTA can sort
-      if (threadIdx.x == 0) {
-        atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_SKEW);
-        b.ucount[bin] = 0;
-      }
-      return;
-    }
-    n = w;
-  }
-  ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
-  uint32_t g = process_chunk<RB, MODE_FINAL, false>(sm, base, n, out);
-  if (threadIdx.x == 0) b.ucount[bin] = g;
 }
 
 // ============================================================================
@@ -587,21 +331,21 @@ int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, cons
   return 1;
 }
 int launch_hist(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                uint32_t ordered, uint32_t* hist, cudaStream_t s) {
+                uint32_t ordered, uint32_t ctr_shift, uint32_t* hist, cudaStream_t s) {
   if (!n) return 0;
-  BinParams bp{P, S, partitioner, ordered};
+  BinParams bp{P, S, partitioner, ordered, ctr_shift};
   DISPATCH_RB(rb, (k_hist<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
   return 1;
 }
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t cap,
-                  uint32_t* big_list, uint32_t* nbig, uint32_t* total, cudaStream_t s) {
-  k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, cap, big_list, nbig, total);
+                  uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift, cudaStream_t s) {
+  k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, cap, big_list, nbig, total, shift);
   return 1;
 }
 int launch_scatter(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                   uint32_t ordered, uint32_t* cursor, void* mid, cudaStream_t s) {
+                   uint32_t ordered, uint32_t ctr_shift, uint32_t* cursor, void* mid, cudaStream_t s) {
   if (!n) return 0;
-  BinParams bp{P, S, partitioner, ordered};
+  BinParams bp{P, S, partitioner, ordered, ctr_shift};
   DISPATCH_RB(rb, (k_scatter<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
                                                                        (uint4*)mid)));
   return 1;
@@ -632,7 +376,7 @@ int launch_checksum_in(int rb, const void* recs, uint64_t n, uint64_t* acc4, cud
 }
 int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t P, uint32_t S,
                         uint32_t partitioner, uint32_t ordered, uint64_t* acc6, cudaStream_t s) {
-  BinParams bp{P, S, partitioner, ordered};
+  BinParams bp{P, S, partitioner, ordered, 0};
   int grid = g_sm_count * 8;
   DISPATCH_RB(rb, (k_checksum_out<RB><<<grid, 256, 0, s>>>(b, B, bp, (unsigned long long*)acc6)));
   return 1;

@@ -7,7 +7,7 @@ namespace mrhbm {
 
 struct BinParams;
 
-constexpr int kCapBytes = 64 * 1024;  // record bytes one CTA sorts in shared memory
+constexpr int kCapBytes = 32 * 1024;  // record bytes one CTA sorts in shared memory (2 CTAs per SM)
 inline uint32_t cap_records(int rb) { return (uint32_t)(kCapBytes / rb); }
 
 struct ShuffleBuffers {
@@ -31,11 +31,12 @@ int launch_gen_u64(void* dst, uint64_t seed, uint64_t start, uint64_t n, cudaStr
 int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, const uint64_t* d_table,
                       uint64_t V, cudaStream_t s);
 int launch_hist(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                uint32_t ordered, uint32_t* hist, cudaStream_t s);
+                uint32_t ordered, uint32_t ctr_shift, uint32_t* hist, cudaStream_t s);
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy,
-                  uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, cudaStream_t s);
+                  uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift,
+                  cudaStream_t s);
 int launch_scatter(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                   uint32_t ordered, uint32_t* cursor, void* mid, cudaStream_t s);
+                   uint32_t ordered, uint32_t ctr_shift, uint32_t* cursor, void* mid, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);

@@ -1,0 +1,415 @@
+// mrhbm_sort.cuh -- per-bin sort + segmented reduce inside one CTA's shared memory.
+//
+// Replaces, for one bin, keys_sorted (mapreduce/utils.lua:123-128), the heap k-way merge that
+// concatenates the values of equal keys (utils.lua:206-271, heap.lua) and the reducer loop
+// (job.lua:264-284) with the built-in sum.
+//
+// Fast path (counting_path): one counting pass over 2*capacity interpolated buckets of the
+// 64-bit key prefix (about one record per bucket) moves the records into bucket order in a
+// second buffer; every record then ranks itself among its few bucket mates by whole-key
+// comparison and lands in its final sorted slot.  All later reads are sequential.
+// General path: bitonic sort of (prefix digit | index) words, with whole-key LSD passes when
+// equal digits hide different keys (heavy duplicates, clustered or long common prefixes).
+#pragma once
+#include "mrhbm_dev.cuh"
+#include "mrhbm_kernels.h"
+
+namespace mrhbm {
+
+constexpr int kSortThreads = 512;
+constexpr int kIdxBits = 12;  // kCapBytes/16 records at most
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
+constexpr int kDigitBits = 64 - kIdxBits;
+static_assert(kCapBytes / 16 <= (1 << kIdxBits), "index bits");
+
+struct SortSmem {
+  uint4* rec;     // cap records: the loaded bin, later the sorted bin
+  uint4* rec2;    // cap records in bucket order (fast path) / permutations + flags (general path)
+  uint32_t* cnt;  // 2*cap words: bucket counters -> offsets; general path: cap composite u64
+  uint64_t* red;  // 80 words of reduction / scan scratch
+};
+__host__ __device__ inline size_t sort_smem_bytes(int rb) {
+  size_t cap = kCapBytes / rb;
+  return (size_t)kCapBytes * 2 + cap * 8 + 80 * 8 + cap * 2;
+}
+__device__ __forceinline__ SortSmem carve(unsigned char* base, int rb) {
+  size_t cap = kCapBytes / rb;
+  SortSmem s;
+  s.rec = (uint4*)base;
+  s.rec2 = (uint4*)(base + kCapBytes);
+  s.cnt = (uint32_t*)(base + 2 * kCapBytes);
+  s.red = (uint64_t*)(base + 2 * kCapBytes + cap * 8);
+  return s;
+}
+
+// ascending bitonic sort of comp[0..n2), n2 a power of two >= 64
+__device__ __forceinline__ void bitonic_sort(uint64_t* comp, uint32_t n2) {
+  const uint32_t tid = threadIdx.x, T = blockDim.x, half = n2 >> 1;
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < half; t += T) {
+        uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // insert a 0 bit at log2(j)
+        uint32_t l = i | j;
+        uint64_t a = comp[i], b = comp[l];
+        bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          comp[i] = b;
+          comp[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// in-place exclusive scan of a[0..n) by the whole CTA (thread t owns a[t*PER .. t*PER+PER)),
+// PER * blockDim.x >= n required; returns the total.  scratch: 33 words.
+template <int PER, typename T_>
+__device__ __forceinline__ uint32_t block_exscan(T_* a, uint32_t n, uint32_t* /*unused*/) {
+  __shared__ uint32_t scratch[40];  // static: keeps the address arithmetic away from the carve
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint32_t v[PER];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    uint32_t i = tid * PER + k;
+    v[k] = i < n ? (uint32_t)a[i] : 0u;
+    s += v[k];
+  }
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nwarps ? scratch[lane] : 0u, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= (uint32_t)d) wi += t;
+    }
+    scratch[lane] = wi - w;
+    if (lane == 31) scratch[32] = wi;
+  }
+  __syncthreads();
+  uint32_t run = scratch[warp] + incl - s;
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    uint32_t i = tid * PER + k;
+    if (i < n) a[i] = (T_)run;
+    run += v[k];
+  }
+  uint32_t total = scratch[32];
+  __syncthreads();
+  return total;
+}
+
+enum { MODE_FINAL = 0, MODE_PARTIAL = 1 };
+struct ChunkOut {
+  void* keys;      // FINAL: key slots; PARTIAL: AoS records
+  uint64_t* sums;  // FINAL only
+  uint64_t base;   // element offset into the destination
+  uint32_t* err_flags;
+};
+
+template <int RB, int MODE>
+__device__ __forceinline__ void write_group(const ChunkOut& out, uint64_t o, const uint32_t* r, uint64_t s) {
+  using R = Rec<RB>;
+  if (MODE == MODE_FINAL) {
+    if constexpr (R::kU64) {
+      ((uint64_t*)out.keys)[o] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+    } else {
+      uint32_t* d = (uint32_t*)out.keys + o * R::kKeyWords;
+#pragma unroll
+      for (int w = 0; w < R::kKeyWords; w++) d[w] = r[w];
+    }
+    out.sums[o] = s;
+  } else {
+    uint32_t* d = (uint32_t*)out.keys + o * R::kWords;
+#pragma unroll
+    for (int w = 0; w < R::kKeyWords; w++) d[w] = r[w];
+    if constexpr (R::kU64) {
+      d[2] = (uint32_t)s;
+      d[3] = (uint32_t)(s >> 32);
+    } else {
+      if (s > 0xffffffffull) atomicOr(out.err_flags, (uint32_t)ERRF_OVERFLOW);
+      d[R::kKeyWords] = (uint32_t)s;
+    }
+  }
+}
+
+// Shared epilogue: the bin is in ascending key order (position j holds record at(j)).  When
+// !HAVE_FLAGS, mark the first record of every key; then number the groups, let each head sum
+// its run and write it out.  flags: CAP u16, slot: CAP u32 (slot[j] = flags[j] on entry when
+// HAVE_FLAGS).
+template <int RB, int MODE, bool HAVE_FLAGS, typename At>
+__device__ __forceinline__ uint32_t reduce_sorted(At at, uint32_t cnt, uint16_t* flags, uint32_t* slot,
+                                                  uint32_t* scratch33, const ChunkOut& out) {
+  constexpr int CAP = kCapBytes / RB;
+  constexpr int PER = (CAP + kSortThreads - 1) / kSortThreads;
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  if (!HAVE_FLAGS) {
+    for (uint32_t j = tid; j < cnt; j += T) {
+      uint32_t head = 1;
+      if (j > 0) head = !key_eq<RB>(at(j), at(j - 1));
+      flags[j] = (uint16_t)head;
+      slot[j] = head;
+    }
+    __syncthreads();
+  }
+  uint32_t groups = block_exscan<PER>(slot, cnt, scratch33);
+  for (uint32_t j = tid; j < cnt; j += T) {
+    if (!flags[j]) continue;
+    const uint32_t* r = at(j);
+    uint64_t s = rec_value<RB>(r);
+    for (uint32_t k = j + 1; k < cnt && !flags[k]; k++) s += rec_value<RB>(at(k));
+    write_group<RB, MODE>(out, out.base + slot[j], r, s);
+  }
+  __syncthreads();
+  return groups;
+}
+
+constexpr uint32_t kFixMax = 8;  // largest bucket the rank-among-mates step accepts
+constexpr uint32_t kNoFastPath = 0xffffffffu;
+
+template <int RB, int MODE>
+__device__ uint32_t counting_path(const SortSmem& sm, uint32_t cnt, uint64_t pmin, uint64_t pmax,
+                                  const ChunkOut& out) {
+  using R = Rec<RB>;
+  constexpr uint32_t CAP = kCapBytes / RB;
+  constexpr uint32_t NB = 2 * CAP;
+  constexpr int ITEMS = (CAP + kSortThreads - 1) / kSortThreads;
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  const uint32_t* recw = (const uint32_t*)sm.rec;
+  const uint32_t* rec2w = (const uint32_t*)sm.rec2;
+  uint32_t* bcnt = sm.cnt;
+  uint16_t* heads = (uint16_t*)sm.red + 4 * 80;  // CAP u16 after the scratch words (see sort_smem_bytes)
+  uint64_t range = pmax - pmin;
+  // monotone map prefix -> [0, NB): drop just enough low bits of (prefix - pmin)
+  int bits = range ? 64 - __clzll((long long)range) : 0;
+  constexpr int kLogNB = 31 - __builtin_clz(NB);
+  static_assert((1u << kLogNB) == NB, "NB must be a power of two");
+  const int sh = bits > kLogNB ? bits - kLogNB : 0;
+  auto bucket_of = [&](const uint32_t* r) -> uint32_t {
+    return (uint32_t)((key_prefix64<RB>(r) - pmin) >> sh);
+  };
+  constexpr int ZPER = (NB + kSortThreads - 1) / kSortThreads;
+#pragma unroll
+  for (int k = 0; k < ZPER; k++)
+    if (tid * ZPER + k < NB) bcnt[tid * ZPER + k] = 0;
+  __syncthreads();
+  uint32_t br[ITEMS];
+  int over = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    uint32_t i = tid + k * T;
+    br[k] = 0;
+    if (i < cnt) {
+      uint32_t b = bucket_of(recw + i * R::kWords);
+      uint32_t r = atomicAdd(bcnt + b, 1u);
+      br[k] = (b << 4) | (r & 15u);
+      if (r >= kFixMax) over = 1;
+    }
+  }
+  if (__syncthreads_or(over)) return kNoFastPath;
+  block_exscan<ZPER>(bcnt, NB, (uint32_t*)sm.red);  // bcnt[b] = first position of bucket b
+  // records into bucket order
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    uint32_t i = tid + k * T;
+    if (i < cnt) {
+      uint32_t pos = bcnt[br[k] >> 4] + (br[k] & 15u);
+#pragma unroll
+      for (int v = 0; v < R::kVec; v++) sm.rec2[pos * R::kVec + v] = sm.rec[i * R::kVec + v];
+    }
+  }
+  __syncthreads();
+  // rank among the bucket mates -> final sorted slot (equal keys keep their bucket order)
+  for (uint32_t j = tid; j < cnt; j += T) {
+    const uint32_t* r = rec2w + j * R::kWords;
+    uint32_t b = bucket_of(r);
+    uint32_t s = bcnt[b], e = (b + 1 < NB) ? bcnt[b + 1] : cnt;
+    uint32_t rank = 0, head = 1;
+    for (uint32_t m = s; m < e; m++) {
+      if (m == j) continue;
+      int c = key_cmp<RB>(rec2w + m * R::kWords, r);
+      bool eq_before = (c == 0 && m < j);
+      rank += (c < 0) || eq_before;
+      if (eq_before) head = 0;  // an equal key sits earlier: not the first of its group
+    }
+#pragma unroll
+    for (int v = 0; v < R::kVec; v++) sm.rec[(s + rank) * R::kVec + v] = sm.rec2[j * R::kVec + v];
+    heads[s + rank] = (uint16_t)head;
+  }
+  __syncthreads();
+  // bucket offsets are dead: reuse the words as group slots (slot[j] = head flag of position j)
+  for (uint32_t j = tid; j < CAP; j += T) bcnt[j] = j < cnt ? (uint32_t)heads[j] : 0u;
+  __syncthreads();
+  auto at = [&](uint32_t j) -> const uint32_t* { return recw + j * R::kWords; };
+  return reduce_sorted<RB, MODE, true>(at, cnt, heads, bcnt, (uint32_t*)sm.red, out);
+}
+
+// Sorts cnt (<= cap) records of one bin by key, sums the values of equal keys and writes
+// the groups in ascending key order.  Returns the number of groups.
+template <int RB, int MODE, bool NC>
+__device__ uint32_t process_chunk(const SortSmem& sm, const uint4* __restrict__ src, uint32_t cnt,
+                                  const ChunkOut& out) {
+  using R = Rec<RB>;
+  constexpr uint32_t CAP = kCapBytes / RB;
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  const uint32_t* recw = (const uint32_t*)sm.rec;
+  // 1. coalesced load of the bin
+  for (uint32_t v = tid; v < cnt * R::kVec; v += T) sm.rec[v] = NC ? ldg_stream(src + v) : src[v];
+  __syncthreads();
+  // 2. range of the 64-bit key prefix
+  uint64_t pmin = ~0ull, pmax = 0;
+  for (uint32_t i = tid; i < cnt; i += T) {
+    uint64_t p = key_prefix64<RB>(recw + i * R::kWords);
+    pmin = p < pmin ? p : pmin;
+    pmax = p > pmax ? p : pmax;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    uint64_t a = __shfl_xor_sync(0xffffffffu, pmin, d), b = __shfl_xor_sync(0xffffffffu, pmax, d);
+    pmin = a < pmin ? a : pmin;
+    pmax = b > pmax ? b : pmax;
+  }
+  if ((tid & 31) == 0) {
+    sm.red[tid >> 5] = pmin;
+    sm.red[32 + (tid >> 5)] = pmax;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    pmin = tid < (T >> 5) ? sm.red[tid] : ~0ull;
+    pmax = tid < (T >> 5) ? sm.red[32 + tid] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      uint64_t a = __shfl_xor_sync(0xffffffffu, pmin, d), b = __shfl_xor_sync(0xffffffffu, pmax, d);
+      pmin = a < pmin ? a : pmin;
+      pmax = b > pmax ? b : pmax;
+    }
+    if (tid == 0) {
+      sm.red[64] = pmin;
+      sm.red[65] = pmax;
+    }
+  }
+  __syncthreads();
+  pmin = sm.red[64];
+  pmax = sm.red[65];
+  __syncthreads();
+  {
+    uint32_t g = counting_path<RB, MODE>(sm, cnt, pmin, pmax, out);
+    if (g != kNoFastPath) return g;
+  }
+  // general path: bitonic sort of (prefix digit | index) words, whole-key passes on ties
+  uint64_t* comp = (uint64_t*)sm.cnt;
+  uint16_t* perm = (uint16_t*)sm.rec2;
+  uint16_t* other = perm + CAP;
+  uint64_t range = pmax - pmin;
+  int bits = range ? 64 - __clzll((long long)range) : 0;
+  int drop = bits > kDigitBits ? bits - kDigitBits : 0;
+  uint32_t n2 = 64;
+  while (n2 < cnt) n2 <<= 1;
+  for (uint32_t i = tid; i < n2; i += T) {
+    uint64_t c = ~0ull;
+    if (i < cnt) c = (((key_prefix64<RB>(recw + i * R::kWords) - pmin) >> drop) << kIdxBits) | i;
+    comp[i] = c;
+  }
+  __syncthreads();
+  bitonic_sort(comp, n2);
+  int tie = 0;
+  for (uint32_t j = tid; j < cnt; j += T) {
+    uint64_t c = comp[j];
+    perm[j] = (uint16_t)(c & kIdxMask);
+    if (j > 0 && (R::kKeyWords > 2 || drop > 0)) {
+      uint64_t p = comp[j - 1];
+      if ((c >> kIdxBits) == (p >> kIdxBits) &&
+          !key_eq<RB>(recw + (uint32_t)(c & kIdxMask) * R::kWords, recw + (uint32_t)(p & kIdxMask) * R::kWords))
+        tie = 1;
+    }
+  }
+  if (__syncthreads_or(tie)) {
+    // LSD passes over kDigitBits-wide chunks of the whole key; the previous rank in the low
+    // bits makes every pass stable
+    constexpr int kKeyBits = R::kKeyWords * 32;
+    constexpr int kChunks = (kKeyBits + kDigitBits - 1) / kDigitBits;
+    for (int c = kChunks - 1; c >= 0; c--) {
+      int bitpos = c * kDigitBits;
+      int nb = kKeyBits - bitpos < kDigitBits ? kKeyBits - bitpos : kDigitBits;
+      for (uint32_t j = tid; j < n2; j += T) {
+        uint64_t w = ~0ull;
+        if (j < cnt) w = (key_bits<RB>(recw + (uint32_t)perm[j] * R::kWords, bitpos, nb) << kIdxBits) | j;
+        comp[j] = w;
+      }
+      __syncthreads();
+      bitonic_sort(comp, n2);
+      for (uint32_t j = tid; j < cnt; j += T) other[j] = perm[comp[j] & kIdxMask];
+      __syncthreads();
+      uint16_t* t = perm;
+      perm = other;
+      other = t;
+    }
+  }
+  const uint16_t* pp = perm;
+  auto at = [&](uint32_t j) -> const uint32_t* { return recw + (uint32_t)pp[j] * R::kWords; };
+  return reduce_sorted<RB, MODE, false>(at, cnt, other, (uint32_t*)comp, (uint32_t*)sm.red, out);
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers b, uint32_t B, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_bin;
+  SortSmem sm = carve(smem_raw, RB);
+  for (;;) {
+    if (threadIdx.x == 0) s_bin = atomicAdd(b.counters + CNT_TICKET, 1u);
+    __syncthreads();
+    uint32_t bin = s_bin;
+    __syncthreads();
+    if (bin >= B) break;
+    uint32_t off = b.bin_off[bin], cnt = b.bin_off[bin + 1] - off;
+    if (cnt > cap) continue;  // k_big_bins
+    if (cnt == 0) {
+      if (threadIdx.x == 0) b.ucount[bin] = 0;
+      continue;
+    }
+    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
+    uint32_t g = process_chunk<RB, MODE_FINAL, true>(sm, (const uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec, cnt, out);
+    if (threadIdx.x == 0) b.ucount[bin] = g;
+  }
+}
+
+// One CTA per oversized bin (hot keys): chunk-wise in-place reduce until the bin fits.
+template <int RB>
+__global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortSmem sm = carve(smem_raw, RB);
+  uint32_t bin = b.big_list[blockIdx.x];
+  uint32_t off = b.bin_off[bin], n = b.bin_off[bin + 1] - off;
+  uint4* base = (uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
+  while (n > cap) {
+    uint32_t w = 0;
+    for (uint32_t c = 0; c < n; c += cap) {
+      uint32_t m = n - c < cap ? n - c : cap;
+      ChunkOut out{base, nullptr, w, b.counters + CNT_ERR};
+      // groups of a chunk never outnumber the records consumed so far: w + g <= c + m
+      w += process_chunk<RB, MODE_PARTIAL, false>(sm, base + (uint64_t)c * Rec<RB>::kVec, m, out);
+      __threadfence_block();
+    }
+    if (w == n) {  // nothing merged: more distinct keys than one CTA can sort
+      if (threadIdx.x == 0) {
+        atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_SKEW);
+        b.ucount[bin] = 0;
+      }
+      return;
+    }
+    n = w;
+  }
+  ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
+  uint32_t g = process_chunk<RB, MODE_FINAL, false>(sm, base, n, out);
+  if (threadIdx.x == 0) b.ucount[bin] = g;
+}
+
+}  // namespace mrhbm

@@ -1,0 +1,96 @@
+"""Map and reduce job bodies (mapreduce/job.lua) over the HBM shuffle.
+
+Map job (job.lua:83-97,166-227): `emit(k, v)` goes to mrhbm_emit_* instead of the Lua table;
+keys_sorted / combiner / partitionfn / text spill are what mrhbm_shuffle does on the device.
+Reduce job (job.lua:230-296): the (key, values) stream of utils.merge_iterator becomes
+mrhbm_groups_next; the reducer algebra (job.lua:264-284) is kept."""
+import importlib
+import time
+
+from .utils import STATUS
+
+_initialized = set()
+_funcs = {}
+
+
+def get_func(fname, func, args):
+    """job.lua:64-76: require(fname), run its init once per process, return the module."""
+    m = _funcs.get(fname)
+    if m is None:
+        m = importlib.import_module(fname)
+        init = getattr(m, "init", None)
+        if init is not None and init not in _initialized:
+            init(args)
+            _initialized.add(init)
+        assert hasattr(m, func), "Module %s must provide %s" % (fname, func)
+        _funcs[fname] = m
+    return m
+
+
+def _key_bytes(k):
+    if isinstance(k, bytes):
+        return k
+    if isinstance(k, str):
+        return k.encode()
+    raise TypeError("hbm storage takes string keys (or ints with key_kind='u64'), got %r" % type(k))
+
+
+class Job:
+    def __init__(self, board, ns, doc, config):
+        self.board, self.ns, self.doc, self.cfg = board, ns, doc, config
+        self.written = False
+
+    def get_id(self):
+        return self.doc["_id"]
+
+    def execute(self):
+        t0 = time.process_time()
+        self.t = time.time()
+        (self._map if self.ns == "map_jobs" else self._reduce)()
+        return time.process_time() - t0
+
+    # ---- job.lua:166-227
+    def _map(self):
+        cfg, ctx = self.cfg, self.board.ctx
+        mapfn = get_func(cfg["mapfn"], "mapfn", None).mapfn  # init(nil): the job.lua:369 quirk
+        m = ctx.map_begin(self.get_id())
+        try:
+            if cfg["hbm"]["key_kind"] == "u64":
+                def emit(key, value=1):
+                    m.emit(int(key), int(value))
+            else:
+                def emit(key, value=1):
+                    m.emit(_key_bytes(key), int(value))
+            mapfn(self.get_id(), self.doc["value"], emit)  # job.lua:182
+            self.board.mark(self.doc, STATUS.FINISHED, finished_time=time.time())
+            m.commit()  # atomic publish; replaces an earlier attempt (job.lua:217-221)
+        except BaseException:
+            m.abort()   # BROKEN job: nothing becomes visible (worker.lua:120-127)
+            raise
+        self.written = True
+        self.board.mark(self.doc, STATUS.WRITTEN, written_time=time.time(), real_time=time.time() - self.t)
+
+    # ---- job.lua:230-296
+    def _reduce(self):
+        cfg, ctx = self.cfg, self.board.ctx
+        mod = get_func(cfg["reducefn"], "reducefn", None)
+        aci = all(getattr(mod, f, False) for f in
+                  ("associative_reducer", "commutative_reducer", "idempotent_reducer"))
+        part = int(self.doc["_id"])
+        out, result = [], []
+
+        def emit(v):
+            result.append(v)
+
+        for key, values in ctx.groups(part):
+            # The device applied the declared built-in (combiner semantics).  The reference
+            # skips the reducer on singletons when the ACI flags are set (job.lua:264-274),
+            # otherwise it always calls it (job.lua:275-284).
+            if not (aci and len(values) == 1):
+                del result[:]
+                mod.reducefn(key, values, emit)
+                values = list(result)
+            out.append((key, values))
+        self.doc["value"]["pairs"] = out  # stands in for the GridFS file result.P<kk> (job.lua:287)
+        self.written = True
+        self.board.mark(self.doc, STATUS.WRITTEN, written_time=time.time(), real_time=time.time() - self.t)

@@ -1,0 +1,176 @@
+"""The reference-facing task API (server / worker / plugin modules) mirrored in
+lua-mapreduce_b200/mapreduce: test.sh's four plugin configurations against misc/naive.lua's
+answer (the golden word count).  CPU tests run the host logic over a stand-in ctx (tests only);
+the gpu-marked tests run the same scripts over the CUDA path."""
+import threading
+
+import pytest
+
+import mrhbm_loader
+from conftest import expand_tokens
+
+mrhbm_loader.load()
+from lua_mapreduce_b200.mapreduce import server, worker, utils, task  # noqa: E402
+from lua_mapreduce_b200.mapreduce.examples.WordCount import init as WordCount  # noqa: E402
+
+WC = "lua_mapreduce_b200.mapreduce.examples.WordCount"
+WCI = WC + ".init"
+
+
+class StandInCtx:
+    """Dict-based stand-in for mrhbm.Ctx so that the HOST logic is testable without a GPU.
+    Lives in tests/ only; the product has no CPU path."""
+
+    class _Map:
+        def __init__(self, ctx, job):
+            self.ctx, self.job, self.buf = ctx, job, []
+
+        def emit(self, k, v=1):
+            self.buf.append((k, v))
+
+        def commit(self):
+            self.ctx.jobs[self.job] = self.buf
+
+        def abort(self):
+            self.buf = None
+
+    def __init__(self, h):
+        self.P, self.jobs, self.parts = h["num_partitions"], {}, {}
+
+    def map_begin(self, job):
+        return self._Map(self, str(job))
+
+    def reset(self):
+        self.jobs, self.parts = {}, {}
+
+    def shuffle(self):
+        self.parts = {}
+        for buf in self.jobs.values():
+            for k, v in buf:
+                d = self.parts.setdefault(WordCount.partitionfn(k), {})
+                d[k] = d.get(k, 0) + v
+
+    def partitions(self):
+        return sorted(self.parts)
+
+    def groups(self, p):
+        for k in sorted(self.parts.get(p, {})):
+            yield k, [self.parts[p][k]]
+
+    def stats(self):
+        return {}
+
+
+@pytest.fixture
+def corpus(tmp_path, golden_wordcount):
+    files = []
+    for job in range(4):
+        toks = expand_tokens(golden_wordcount, job)
+        p = tmp_path / ("file%d.txt" % job)
+        lines = [b" ".join(toks[i:i + 7]) for i in range(0, len(toks), 7)]
+        p.write_bytes(b"\n".join(lines) + b"\n\t \n")
+        files.append(str(p))
+    WordCount.FILES[:] = files
+    WordCount.RESULT.clear()
+    return files
+
+
+CONFIGS = {  # test.sh:9-71
+    "combiner+aci": dict(reducefn=WC + ".reducefn", combinerfn=WC + ".reducefn"),
+    "aci": dict(reducefn=WC + ".reducefn"),
+    "general": dict(reducefn=WC + ".reducefn2"),
+    "init-script": dict(taskfn=WCI, mapfn=WCI, partitionfn=WCI, reducefn=WCI, finalfn=WCI, combinerfn=WCI),
+}
+
+
+def run_config(name, dbname, ctx_factory=None, with_worker=False):
+    params = dict(taskfn=WC + ".taskfn", mapfn=WC + ".mapfn", partitionfn=WC + ".partitionfn",
+                  finalfn=WC + ".finalfn", storage="hbm")
+    params.update(CONFIGS[name])
+    s = server.new("hbm://local", dbname)
+    s.ctx_factory = ctx_factory
+    s.configure(params)
+    th = None
+    if with_worker:
+        w = worker.new("hbm://local", dbname)
+        w.configure({"max_iter": 2000, "max_tasks": 1})
+        s.board.workers += 1
+        th = threading.Thread(target=w.execute, daemon=True)
+        th.start()
+    s.loop()
+    if th:
+        th.join(timeout=60)
+        assert not th.is_alive()
+    return s
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_wordcount_configs_host_logic(name, corpus, golden_wordcount):
+    s = run_config(name, "cpu-" + name, ctx_factory=StandInCtx)
+    assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
+    assert s.stats["map_count"] == 4 and s.stats["reduce_count"] == 15 and s.stats["failed_maps"] == 0
+    assert [j["value"]["result"] for j in s.results] == ["result.P%02d" % p for p in range(15)]
+
+
+def test_worker_thread_takes_the_jobs(corpus, golden_wordcount):
+    s = run_config("aci", "cpu-worker", ctx_factory=StandInCtx, with_worker=True)
+    assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
+    assert {j["worker"] for j in s.board.jobs["map_jobs"]} != {"server-inline"}
+
+
+def test_configure_errors_and_storage_strings():
+    s = server.new("hbm://local", "cfg")
+    with pytest.raises(AssertionError, match="mandatory"):
+        s.configure({"taskfn": WC})
+    with pytest.raises(ValueError, match="Given incorrect storage"):
+        utils.get_storage_from("floppy")
+    assert utils.get_storage_from("hbm:/tmp/x") == ("hbm", "/tmp/x")
+    assert utils.get_storage_from(None)[0] == "hbm"
+    with pytest.raises(AssertionError, match="Call to server:configure"):
+        server.new("hbm://local", "cfg2").loop()
+    w = worker.new("hbm://local", "cfg")
+    with pytest.raises(AssertionError, match="Unknown parameter"):
+        w.configure({"bogus": 1})
+
+
+def test_wire_format_helpers(golden_vectors):  # utils.lua:345-349
+    for v, want in golden_vectors["escape"]:
+        assert utils.escape(v) == want.encode()
+    for vals, want in golden_vectors["serialize_table_ipairs"]:
+        assert utils.serialize_table_ipairs(vals) == want.encode()
+    assert utils.result_line(b"a", [3]) == b'return "a",{3}\n'
+    for n, d in golden_vectors["count_digits"]:
+        assert utils.count_digits(n) == d
+
+
+def test_broken_map_job_is_retried_then_failed(corpus):
+    """worker.lua:112-138 / server.lua:194-213: a job that raises is BROKEN, retried, and
+    counted FAILED after MAX_JOB_RETRIES; its partial emits never become visible."""
+    import types, sys
+    mod = types.ModuleType("bad_mapfn")
+    calls = []
+
+    def mapfn(key, value, emit):
+        calls.append(key)
+        emit(b"ghost", 1)
+        if key == "2":
+            raise RuntimeError("boom")
+        emit(b"ok", 1)
+    mod.mapfn, mod.init = mapfn, lambda a=None: None
+    sys.modules["bad_mapfn"] = mod
+    s = server.new("hbm://local", "cpu-broken")
+    s.ctx_factory = StandInCtx
+    s.configure(dict(taskfn=WC + ".taskfn", mapfn="bad_mapfn", partitionfn=WC + ".partitionfn",
+                     reducefn=WC + ".reducefn", finalfn=WC + ".finalfn", storage="hbm"))
+    s.loop()
+    assert calls.count("2") == utils.MAX_JOB_RETRIES and s.stats["failed_maps"] == 1
+    assert WordCount.RESULT == {b"ghost": 3, b"ok": 3}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_wordcount_configs_on_gpu(name, corpus, golden_wordcount):
+    s = run_config(name, "gpu-" + name)
+    assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
+    assert s.stats["reduce_count"] == 15 and s.stats["shuffle"]["pairs"] == 4989
+    s.board.ctx.close()
