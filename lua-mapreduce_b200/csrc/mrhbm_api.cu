@@ -42,6 +42,16 @@ struct mrhbm_ctx {
   uint64_t B_cap = 0, mid_cap = 0, out_cap = 0;
   uint32_t B = 0, S = 1, ordered = 1, cap = 0, ctr_shift = 3;
   uint64_t ctr_cap = 0;
+  ShuffleBuffers rv{};  // view the result accessors use (single GPU: == sb)
+  // multi-GPU (one ctx per rank; partition p is owned by rank p % world)
+  int world = 1, rank = 0;
+  uint32_t Pl = 0, pbase[9] = {0}, bin_base = 0;
+  uint64_t N_recv = 0;
+  uint32_t *d_hd = nullptr, *d_hall = nullptr, *d_tot = nullptr, *d_outoff = nullptr, *d_segoff = nullptr;
+  uint64_t hd_cap = 0, bl_cap = 0;
+  void *recvbuf = nullptr, *bigbuf = nullptr;
+  uint64_t recv_cap = 0, big_cap = 0;
+  uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
   std::vector<uint32_t> h_bin_off, h_uoff;
@@ -258,7 +268,7 @@ int ensure_compact(mrhbm_ctx* c) {
     CU(c, cudaMalloc((void**)&c->csums, need * sizeof(uint64_t)));
     c->c_cap = need;
   }
-  launch_compact(c->rb, c->sb, c->B, c->ckeys, c->csums, c->stream);
+  launch_compact(c->rb, c->rv, c->B, c->ckeys, c->csums, c->stream);
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));
   c->compacted = true;
@@ -327,6 +337,10 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaMalloc((void**)&c->d_acc, 8 * sizeof(uint64_t)));
   CU(c, cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   CU(c, cudaHostAlloc((void**)&c->h_acc, 8 * sizeof(uint64_t), cudaHostAllocDefault));
+  CU(c, cudaMalloc((void**)&c->d_small, 64 * sizeof(uint32_t)));
+  CU(c, cudaHostAlloc((void**)&c->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
+  c->Pl = cfg->num_partitions;
+  for (int r = 1; r <= 8; r++) c->pbase[r] = cfg->num_partitions;
   c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
   if (const char* e = getenv("MRHBM_CTR_SHIFT")) c->ctr_shift = (uint32_t)std::min(7, std::max(0, atoi(e)));  // tuning hook
   if (cfg->reserve_pairs) {
@@ -344,11 +358,13 @@ void mrhbm_destroy(mrhbm_ctx* c) {
   if (c->comm) comm_destroy(c->comm);
   void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
-                   c->csums,       c->d_acc,       c->d_table};
+                   c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
+                   c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_acc) cudaFreeHost(c->h_acc);
+  if (c->h_small) cudaFreeHost(c->h_small);
   for (int i = 0; i < EV_N; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -553,95 +569,196 @@ int mrhbm_reset(mrhbm_ctx* c) {
   return MRHBM_OK;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------
 // shuffle
 // ---------------------------------------------------------------------------
-int mrhbm_shuffle(mrhbm_ctx* c) {
-  if (!c || !c->stream) return MRHBM_E_INVAL;
-  for (const Range& r : c->ranges)
-    if (r.state == R_OPEN) return fail(c, MRHBM_E_INVAL, "map job '%s' is still open", r.job.c_str());
-  if (c->comm) return comm_shuffle_unavailable(c->comm, &c->err);
+namespace {
+
+BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered) {
+  BinParams bp{};
+  bp.P = c->cfg.num_partitions;
+  bp.S = S;
+  bp.partitioner = c->cfg.partitioner;
+  bp.ordered = ordered;
+  bp.ctr_shift = c->ctr_shift;
+  bp.world = (uint32_t)c->world;
+  for (int r = 0; r <= 8; r++) bp.pbase[r] = c->pbase[r];
+  return bp;
+}
+
+// all ranks: one u32 from every rank (host value in, host values out); synchronises the stream
+int gather_u32(mrhbm_ctx* c, uint32_t mine, uint32_t* all) {
+  if (c->world == 1) {
+    all[0] = mine;
+    return 0;
+  }
+  c->h_small[0] = mine;
+  CU(c, cudaMemcpyAsync(c->d_small, c->h_small, 4, cudaMemcpyHostToDevice, c->stream));
+  int rc = comm_allgather_u32(c->comm, c->d_small, c->d_small + 16, 1, c->stream, &c->err);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_small + 16, c->d_small + 16, 4 * c->world, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < c->world; r++) all[r] = c->h_small[16 + r];
+  return 0;
+}
+
+int ensure_multi_buffers(mrhbm_ctx* c, uint64_t B, uint64_t Bl) {
+  const int G = c->world;
+  if (B > c->hd_cap) {
+    uint64_t nb = B + (B >> 2) + 1;
+    for (uint32_t** p : {&c->d_hd, &c->d_hall}) {
+      if (*p) CU(c, cudaFree(*p));
+      *p = nullptr;
+    }
+    CU(c, cudaMalloc((void**)&c->d_hd, nb * 4));
+    CU(c, cudaMalloc((void**)&c->d_hall, nb * 4 * G));
+    c->hd_cap = nb;
+  }
+  if (Bl + 1 > c->bl_cap) {
+    uint64_t nb = Bl + (Bl >> 2) + 2;
+    for (uint32_t** p : {&c->d_tot, &c->d_outoff, &c->d_segoff}) {
+      if (*p) CU(c, cudaFree(*p));
+      *p = nullptr;
+    }
+    CU(c, cudaMalloc((void**)&c->d_tot, nb * 4));
+    CU(c, cudaMalloc((void**)&c->d_outoff, nb * 4));
+    CU(c, cudaMalloc((void**)&c->d_segoff, nb * 4 * G));
+    c->bl_cap = nb;
+  }
+  return 0;
+}
+
+int ensure_records(mrhbm_ctx* c, void** buf, uint64_t* cap, uint64_t need) {
+  need = std::max<uint64_t>(need, 1);
+  if (need <= *cap) return 0;
+  if (*buf) CU(c, cudaFree(*buf));
+  *buf = nullptr;
+  *cap = 0;
+  CU(c, cudaMalloc(buf, need * c->rb));
+  *cap = need;
+  return 0;
+}
+
+int ensure_out(mrhbm_ctx* c, uint64_t need) {
+  need = std::max<uint64_t>(need, 1);
+  if (need <= c->out_cap) return 0;
+  if (c->sb.out_keys) CU(c, cudaFree(c->sb.out_keys));
+  if (c->sb.out_sums) CU(c, cudaFree(c->sb.out_sums));
+  c->sb.out_keys = nullptr;
+  c->sb.out_sums = nullptr;
+  c->out_cap = 0;
+  CU(c, cudaMalloc(&c->sb.out_keys, need * c->kb));
+  CU(c, cudaMalloc((void**)&c->sb.out_sums, need * sizeof(uint64_t)));
+  c->out_cap = need;
+  return 0;
+}
+
+uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
+  // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill
+  uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap));
+  uint64_t P = c->cfg.num_partitions;
+  return (uint32_t)std::max<uint64_t>(1, (n_total + P * target - 1) / (P * target));
+}
+
+void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
+  st.ms_total = ev_ms(c, EV_START, EV_END);
+  st.ms_combine = 0;
+  st.ms_hist = ev_ms(c, EV_COMBINE, EV_HIST);
+  st.ms_plan = ev_ms(c, EV_HIST, EV_PLAN);
+  st.ms_scatter = ev_ms(c, EV_PLAN, EV_SCATTER);
+  st.ms_sort_reduce = ev_ms(c, EV_EXCH, EV_SORT);
+  st.ms_bigbins = ev_ms(c, EV_SORT, EV_BIG);
+  c->stats = st;
+}
+
+// ---- one GPU: hist -> scan -> scatter -> sort+reduce ---------------------------------------
+int shuffle_single(mrhbm_ctx* c) {
   auto live = live_ranges(c);
   uint64_t N = 0;
   for (auto& r : live) N += r.second;
   if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
   const uint32_t P = c->cfg.num_partitions;
-  // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill
-  uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap));
-  uint64_t S64 = (N + (uint64_t)P * target - 1) / ((uint64_t)P * target);
-  uint32_t S = (uint32_t)std::max<uint64_t>(1, S64);
+  uint32_t S = pick_sub_bins(c, N);
   int rc = 0;
-  uint32_t nbig = 0;
+  uint32_t nbig = 0, ordered = 1;
   mrhbm_stats st{};
   st.pairs = N;
   cudaStream_t s = c->stream;
-  uint32_t ordered = 1;
   uint64_t B = 0;
   CU(c, cudaEventRecord(c->ev[EV_START], s));
   // A bin that holds more distinct keys than one CTA sorts (ERRF_SKEW) is retried with
   // twice the sub-bins: distinct keys spread, hot keys keep collapsing in k_big_bins.
   for (int widen = 0;; widen++) {
-  B = (uint64_t)P * S;
-  if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
-  rc = ensure_buffers(c, B, N);
-  if (rc) return rc;
-  ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
-  for (int attempt = 0;; attempt++) {
-    st.attempts++;
-    CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
-    CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
-    CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-    for (auto& r : live)
-      st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->ctr_shift, c->sb.hist, s);
-    CU(c, cudaEventRecord(c->ev[EV_HIST], s));
-    st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->cap, c->sb.big_list,
-                                 c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
+    B = (uint64_t)P * S;
+    if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
+    rc = ensure_buffers(c, B, N);
+    if (rc) return rc;
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
+    for (int attempt = 0;; attempt++) {
+      st.attempts++;
+      BinParams bp = make_bp(c, S, ordered);
+      CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+      CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
+      CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
+      for (auto& r : live) st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.hist, s);
+      CU(c, cudaEventRecord(c->ev[EV_HIST], s));
+      st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
+                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
+      CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
+      CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+      for (auto& r : live)
+        st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.cursor, c->sb.mid, s);
+      CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
+      CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
+      c->sb.src = c->sb.mid;
+      c->sb.nseg = 1;
+      c->sb.seg_off[0] = c->sb.bin_off;
+      c->sb.seg_base[0] = 0;
+      st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+      CU(c, cudaEventRecord(c->ev[EV_SORT], s));
+      CU(c, cudaGetLastError());
+      CU(c, cudaEventSynchronize(c->ev[EV_PROBE]));  // overlaps with scatter / sort on the device
+      nbig = c->h_counters[CNT_NBIG];
+      if (nbig && ordered && S > 1) {
+        // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
+        ordered = 0;
+        continue;
+      }
+      break;
+    }
+    st.launches += launch_big_bins(c->rb, c->sb, nbig, c->cap, s);
+    CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+    st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
+                                 c->sb.counters + CNT_TOTAL, 0, s);
+    c->h_bin_off.resize(B + 1);
+    c->h_uoff.resize(B + 1);
+    CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->sb.bin_off, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
     CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
-    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-    for (auto& r : live)
-      st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, P, S, c->cfg.partitioner, ordered, c->ctr_shift, c->sb.cursor, c->sb.mid, s);
-    CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
-    CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
-    st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
-    CU(c, cudaEventRecord(c->ev[EV_SORT], s));
+    CU(c, cudaEventRecord(c->ev[EV_END], s));
     CU(c, cudaGetLastError());
-    CU(c, cudaEventSynchronize(c->ev[EV_PROBE]));  // overlaps with scatter / sort on the device
-    nbig = c->h_counters[CNT_NBIG];
-    if (nbig && ordered && S > 1) {
-      // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
-      ordered = 0;
-      continue;
+    CU(c, cudaStreamSynchronize(s));
+    uint32_t ef = c->h_counters[CNT_ERR];
+    if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
+    if (ef & ERRF_SKEW) {
+      if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
+        S *= 2;
+        continue;
+      }
+      return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can sort (%u oversized bins)", nbig);
     }
     break;
   }
-  st.launches += launch_big_bins(c->rb, c->sb, nbig, c->cap, s);
-  CU(c, cudaEventRecord(c->ev[EV_BIG], s));
-  st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, 0xffffffffu, nullptr, nullptr,
-                               c->sb.counters + CNT_TOTAL, 0, s);
-  c->h_bin_off.resize(B + 1);
-  c->h_uoff.resize(B + 1);
-  CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->sb.bin_off, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
-  CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
-  CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CU(c, cudaEventRecord(c->ev[EV_END], s));
-  CU(c, cudaGetLastError());
-  CU(c, cudaStreamSynchronize(s));
-  uint32_t ef = c->h_counters[CNT_ERR];
-  if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
-  if (ef & ERRF_SKEW) {
-    if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
-      S *= 2;
-      continue;
-    }
-    return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can sort (%u oversized bins)", nbig);
-  }
-  break;
-  }  // widen
+  c->rv = c->sb;
   c->B = (uint32_t)B;
   c->S = S;
   c->ordered = ordered;
   c->N = N;
+  c->N_recv = N;
+  c->bin_base = 0;
   c->groups = c->h_uoff[B];
   c->shuffled = true;
   c->compacted = false;
@@ -649,16 +766,180 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
   st.sub_bins = S;
   st.big_bins = nbig;
   st.groups = c->groups;
-  st.ms_total = ev_ms(c, EV_START, EV_END);
-  st.ms_combine = 0;
-  st.ms_hist = ev_ms(c, EV_COMBINE, EV_HIST);
-  st.ms_plan = ev_ms(c, EV_HIST, EV_PLAN);
-  st.ms_scatter = ev_ms(c, EV_PLAN, EV_SCATTER);
   st.ms_exchange = 0;
-  st.ms_sort_reduce = ev_ms(c, EV_EXCH, EV_SORT);
-  st.ms_bigbins = ev_ms(c, EV_SORT, EV_BIG);
-  c->stats = st;
+  finish_stats(c, st);
   return MRHBM_OK;
+}
+
+// ---- several GPUs: hist -> all-gather counts -> scatter (destination-major) -> all-to-all
+//      -> sort+reduce of the owned partitions, each bin gathered from one segment per source
+int shuffle_multi(mrhbm_ctx* c) {
+  const int G = c->world, me = c->rank;
+  auto live = live_ranges(c);
+  uint64_t N = 0;
+  for (auto& r : live) N += r.second;
+  if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
+  const uint32_t P = c->cfg.num_partitions;
+  uint32_t all[8];
+  int rc = gather_u32(c, (uint32_t)N, all);
+  if (rc) return rc;
+  uint64_t Nglobal = 0;
+  for (int r = 0; r < G; r++) Nglobal += all[r];
+  uint32_t S = pick_sub_bins(c, Nglobal);
+  uint32_t nbig = 0, ordered = 1;
+  mrhbm_stats st{};
+  st.pairs = N;
+  cudaStream_t s = c->stream;
+  uint64_t B = 0, Bl = 0, total_recv = 0;
+  uint64_t send_off[9], send_cnt[8], recv_off[9], recv_cnt[8];
+  ShuffleBuffers v{};
+  CU(c, cudaEventRecord(c->ev[EV_START], s));
+  for (int widen = 0;; widen++) {
+    B = (uint64_t)P * S;
+    Bl = (uint64_t)c->Pl * S;
+    const uint32_t bin_base = c->pbase[me] * S;
+    if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
+    rc = ensure_buffers(c, B, N);
+    if (rc) return rc;
+    rc = ensure_multi_buffers(c, B, Bl);
+    if (rc) return rc;
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
+    for (int attempt = 0;; attempt++) {
+      st.attempts++;
+      BinParams bp = make_bp(c, S, ordered);
+      CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+      CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
+      CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
+      for (auto& r : live) st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.hist, s);
+      CU(c, cudaEventRecord(c->ev[EV_HIST], s));
+      // send layout (destination-major bins) + dense counts for the all-gather
+      st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->d_hd, 0xffffffffu, nullptr,
+                                   nullptr, nullptr, c->ctr_shift, s);
+      rc = comm_allgather_u32(c->comm, c->d_hd, c->d_hall, B, s, &c->err);
+      if (rc) return rc;
+      // receive layout: per owned bin the total and the per-source offsets
+      st.launches += launch_sum_src(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_tot, s);
+      st.launches += launch_exscan(c->d_tot, (uint32_t)Bl, c->d_outoff, nullptr, nullptr, c->cap, c->sb.big_list,
+                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, 0, s);
+      for (int r = 0; r < G; r++)
+        st.launches += launch_exscan(c->d_hall + (uint64_t)r * B + bin_base, (uint32_t)Bl, c->d_segoff + (uint64_t)r * (Bl + 1),
+                                     nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small + 32 + r, 0, s);
+      for (int d = 0; d <= G; d++)
+        CU(c, cudaMemcpyAsync(c->h_small + 48 + d, c->sb.bin_off + (uint64_t)c->pbase[d] * S, 4, cudaMemcpyDeviceToHost, s));
+      CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
+      CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+      for (auto& r : live)
+        st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.cursor, c->sb.mid, s);
+      CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
+      CU(c, cudaGetLastError());
+      CU(c, cudaStreamSynchronize(s));
+      nbig = c->h_counters[CNT_NBIG];
+      total_recv = c->h_counters[CNT_TOTAL];
+      rc = gather_u32(c, (nbig && ordered && S > 1) ? 1u : 0u, all);  // collective decision
+      if (rc) return rc;
+      bool redo = false;
+      for (int r = 0; r < G; r++) redo |= all[r] != 0;
+      if (redo) {
+        ordered = 0;
+        continue;
+      }
+      break;
+    }
+    send_off[0] = 0;
+    recv_off[0] = 0;
+    st.bytes_exchanged = 0;
+    for (int d = 0; d < G; d++) {
+      send_off[d] = (uint64_t)c->h_small[48 + d] * c->rb;
+      send_cnt[d] = (uint64_t)(c->h_small[48 + d + 1] - c->h_small[48 + d]) * c->rb;
+      recv_cnt[d] = (uint64_t)c->h_small[32 + d] * c->rb;
+      recv_off[d + 1] = recv_off[d] + recv_cnt[d];
+      if (d != me) st.bytes_exchanged += send_cnt[d];
+    }
+    rc = ensure_records(c, &c->recvbuf, &c->recv_cap, total_recv);
+    if (rc) return rc;
+    rc = ensure_out(c, total_recv);
+    if (rc) return rc;
+    if (nbig) {
+      rc = ensure_records(c, &c->bigbuf, &c->big_cap, total_recv);
+      if (rc) return rc;
+    }
+    // one grouped send/recv over NVLink replaces the GridFS / scp store-and-forward
+    rc = comm_alltoallv(c->comm, c->sb.mid, send_off, send_cnt, c->recvbuf, recv_off, recv_cnt, s, &c->err);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
+    v = c->sb;
+    v.bin_off = c->d_outoff;
+    v.src = c->recvbuf;
+    v.mid = nbig ? c->bigbuf : c->recvbuf;
+    v.nseg = (uint32_t)G;
+    for (int r = 0; r < G; r++) {
+      v.seg_off[r] = c->d_segoff + (uint64_t)r * (Bl + 1);
+      v.seg_base[r] = recv_off[r] / c->rb;
+    }
+    st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
+    CU(c, cudaEventRecord(c->ev[EV_SORT], s));
+    st.launches += launch_big_bins(c->rb, v, nbig, c->cap, s);
+    CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+    st.launches += launch_exscan(c->sb.ucount, (uint32_t)Bl, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
+                                 c->sb.counters + CNT_TOTAL, 0, s);
+    c->h_bin_off.resize(Bl + 1);
+    c->h_uoff.resize(Bl + 1);
+    CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->d_outoff, (Bl + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (Bl + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->ev[EV_END], s));
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(s));
+    uint32_t ef = c->h_counters[CNT_ERR];
+    rc = gather_u32(c, ef, all);  // every rank must take the same branch
+    if (rc) return rc;
+    uint32_t ef_any = 0;
+    for (int r = 0; r < G; r++) ef_any |= all[r];
+    if (ef_any & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
+    if (ef_any & ERRF_SKEW) {
+      if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
+        S *= 2;
+        continue;
+      }
+      return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can sort");
+    }
+    break;
+  }
+  c->rv = v;
+  c->B = (uint32_t)Bl;
+  c->S = S;
+  c->ordered = ordered;
+  c->N = N;
+  c->N_recv = total_recv;
+  c->bin_base = c->pbase[me] * S;
+  c->groups = c->h_uoff[Bl];
+  c->shuffled = true;
+  c->compacted = false;
+  st.bins = (uint32_t)Bl;
+  st.sub_bins = S;
+  st.big_bins = nbig;
+  st.groups = c->groups;
+  st.ms_exchange = ev_ms(c, EV_SCATTER, EV_EXCH);
+  finish_stats(c, st);
+  return MRHBM_OK;
+}
+
+// partition p -> local slot on this rank, or -1 when another rank owns it
+inline int64_t slot_of(const mrhbm_ctx* c, uint32_t p) {
+  return (p % (uint32_t)c->world) == (uint32_t)c->rank ? (int64_t)(p / (uint32_t)c->world) : -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrhbm_shuffle(mrhbm_ctx* c) {
+  if (!c || !c->stream) return MRHBM_E_INVAL;
+  for (const Range& r : c->ranges)
+    if (r.state == R_OPEN) return fail(c, MRHBM_E_INVAL, "map job '%s' is still open", r.job.c_str());
+  invalidate(c);
+  return c->world > 1 ? shuffle_multi(c) : shuffle_single(c);
 }
 
 int mrhbm_stats_get(mrhbm_ctx* c, mrhbm_stats* out) {
@@ -671,9 +952,9 @@ int mrhbm_partitions(mrhbm_ctx* c, uint32_t* ids, size_t cap, size_t* n) {
   if (!c || !n) return MRHBM_E_INVAL;
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   size_t k = 0;
-  for (uint32_t p = 0; p < c->cfg.num_partitions; p++) {
-    if (c->h_uoff[(uint64_t)(p + 1) * c->S] > c->h_uoff[(uint64_t)p * c->S]) {
-      if (ids && k < cap) ids[k] = p;
+  for (uint32_t i = 0; i < c->Pl; i++) {
+    if (c->h_uoff[(uint64_t)(i + 1) * c->S] > c->h_uoff[(uint64_t)i * c->S]) {
+      if (ids && k < cap) ids[k] = (uint32_t)c->rank + i * (uint32_t)c->world;
       k++;
     }
   }
@@ -687,7 +968,7 @@ int mrhbm_result_info_get(mrhbm_ctx* c, mrhbm_result_info* info) {
   size_t np = 0;
   mrhbm_partitions(c, nullptr, 0, &np);
   info->pairs_in = c->N;
-  info->pairs_recv = c->N;
+  info->pairs_recv = c->N_recv;
   info->groups = c->groups;
   info->key_bytes = (uint32_t)c->kb;
   info->sorted = (c->ordered || c->S == 1) ? 1 : 0;
@@ -703,7 +984,11 @@ int mrhbm_result_copy(mrhbm_ctx* c, void* keys, uint64_t* sums, uint64_t* part_o
   if (keys && c->groups) CU(c, cudaMemcpyAsync(keys, c->ckeys, c->groups * c->kb, cudaMemcpyDeviceToHost, c->stream));
   if (sums && c->groups) CU(c, cudaMemcpyAsync(sums, c->csums, c->groups * 8, cudaMemcpyDeviceToHost, c->stream));
   if (part_off)
-    for (uint32_t p = 0; p <= c->cfg.num_partitions; p++) part_off[p] = c->h_uoff[(uint64_t)p * c->S];
+    for (uint32_t p = 0; p <= c->cfg.num_partitions; p++) {
+      // groups of the owned partitions with id < p (other ranks' partitions are empty ranges here)
+      uint64_t slots = p <= (uint32_t)c->rank ? 0 : ((uint64_t)p - c->rank + c->world - 1) / c->world;
+      part_off[p] = c->h_uoff[std::min<uint64_t>(slots, c->Pl) * c->S];
+    }
   CU(c, cudaStreamSynchronize(c->stream));
   return MRHBM_OK;
 }
@@ -723,7 +1008,7 @@ int mrhbm_checksum_result(mrhbm_ctx* c, uint64_t out[6]) {
   if (!c || !out) return MRHBM_E_INVAL;
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   CU(c, cudaMemsetAsync(c->d_acc, 0, 8 * sizeof(uint64_t), c->stream));
-  launch_checksum_out(c->rb, c->sb, c->B, c->cfg.num_partitions, c->S, c->cfg.partitioner, c->ordered, c->d_acc, c->stream);
+  launch_checksum_out(c->rb, c->rv, c->B, make_bp(c, c->S, c->ordered), c->bin_base, c->d_acc, c->stream);
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -749,9 +1034,11 @@ int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
   if (part >= c->cfg.num_partitions) return fail(c, MRHBM_E_INVAL, "partition %u out of range", part);
   int rc = ensure_compact(c);
   if (rc) return rc;
+  int64_t slot = slot_of(c, part);
+  if (slot < 0) return fail(c, MRHBM_E_INVAL, "partition %u is owned by rank %u", part, part % (uint32_t)c->world);
   mrhbm_iter* it = new mrhbm_iter();
   it->ctx = c;
-  uint64_t b0 = (uint64_t)part * c->S;
+  uint64_t b0 = (uint64_t)slot * c->S;
   uint64_t lo = c->h_uoff[b0], hi = c->h_uoff[b0 + c->S];
   it->base = lo;
   it->keys.resize((hi - lo) * c->kb);
@@ -815,8 +1102,22 @@ int mrhbm_comm_unique_id(mrhbm_ctx* c, void* id) {
 }
 int mrhbm_comm_init(mrhbm_ctx* c, const void* id, int rank, int world) {
   if (!c || !id || world < 1 || rank < 0 || rank >= world) return MRHBM_E_INVAL;
+  if (world > 8) return fail(c, MRHBM_E_INVAL, "at most 8 ranks (one NVSwitch box)");
+  if (c->world != 1) return fail(c, MRHBM_E_INVAL, "communicator already initialised");
   if (world == 1) return MRHBM_OK;
-  return comm_create(&c->comm, id, rank, world, c->dev, &c->err);
+  int rc = comm_create(&c->comm, id, rank, world, c->dev, &c->err);
+  if (rc) return rc;
+  c->world = world;
+  c->rank = rank;
+  const uint32_t P = c->cfg.num_partitions;
+  c->pbase[0] = 0;
+  for (int r = 0; r < 8; r++) {
+    uint32_t owned = r < world && (uint32_t)r < P ? (P - (uint32_t)r + (uint32_t)world - 1) / (uint32_t)world : 0;
+    c->pbase[r + 1] = c->pbase[r] + owned;
+  }
+  c->Pl = c->pbase[rank + 1] - c->pbase[rank];
+  invalidate(c);
+  return MRHBM_OK;
 }
 
 }  // extern "C"

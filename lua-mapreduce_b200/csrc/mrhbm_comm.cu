@@ -142,9 +142,4 @@ int comm_alltoallv(Comm* c, const void* send, const uint64_t* send_off, const ui
   return 0;
 }
 
-int comm_shuffle_unavailable(Comm*, std::string* err) {
-  if (err) *err = "multi-GPU shuffle is not wired into this build yet";
-  return MRHBM_E_NCCL;
-}
-
 }  // namespace mrhbm

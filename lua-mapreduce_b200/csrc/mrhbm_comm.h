@@ -18,5 +18,4 @@ int comm_allgather_u32(Comm*, const uint32_t* send, uint32_t* recv, size_t count
 // all-to-all-v in bytes: send_off/recv_off/… are per-peer byte offsets and counts (host arrays)
 int comm_alltoallv(Comm*, const void* send, const uint64_t* send_off, const uint64_t* send_cnt, void* recv,
                    const uint64_t* recv_off, const uint64_t* recv_cnt, cudaStream_t s, std::string* err);
-int comm_shuffle_unavailable(Comm*, std::string* err);
 }  // namespace mrhbm

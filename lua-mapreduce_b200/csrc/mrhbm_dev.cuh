@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "mrhbm_kernels.h"
+
 namespace mrhbm {
 
 template <int RB>
@@ -20,16 +22,6 @@ struct Rec {
   static constexpr int kKeyWords = kU64 ? 2 : kWords - 1;  // 32-bit words of key
   static constexpr int kKeyBytes = kKeyWords * 4;
   static constexpr int kVec = RB / 16;  // uint4 per record
-};
-
-struct BinParams {
-  uint32_t P;            // partitions
-  uint32_t S;            // sub-bins per partition
-  uint32_t partitioner;  // MRHBM_PART_*
-  uint32_t ordered;      // 1: sub-bin = top key bits (partition becomes one ascending run)
-                         // 0: sub-bin = further hash bits (partition = S ascending runs)
-  uint32_t ctr_shift;    // hist / cursor counters live at index bin << ctr_shift: the L2
-                         // atomic unit serialises per 32 B sector, so counters are spread out
 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -69,13 +61,14 @@ __device__ __forceinline__ int key_cmp(const uint32_t* a, const uint32_t* b) {
   if constexpr (Rec<RB>::kU64) {
     uint64_t x = (uint64_t)a[0] | ((uint64_t)a[1] << 32), y = (uint64_t)b[0] | ((uint64_t)b[1] << 32);
     return (x > y) - (x < y);
-  }
+  } else {
 #pragma unroll
-  for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
-    uint32_t x = be_word<RB>(a, i), y = be_word<RB>(b, i);
-    if (x != y) return x < y ? -1 : 1;
+    for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
+      uint32_t x = be_word<RB>(a, i), y = be_word<RB>(b, i);
+      if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
   }
-  return 0;
 }
 template <int RB>
 __device__ __forceinline__ bool key_eq(const uint32_t* a, const uint32_t* b) {
@@ -184,7 +177,7 @@ __device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& b
     sub = (uint32_t)__umul64hi(src, (uint64_t)bp.S);
   }
   if (pid_out) *pid_out = pid;
-  return pid * bp.S + sub;
+  return partition_slot(bp, pid) * bp.S + sub;
 }
 
 // checksum mixers over the whole key slot (input and result share the slot format)

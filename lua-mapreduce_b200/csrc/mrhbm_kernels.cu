@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
 // out_copy (scatter cursors), optional list of entries larger than cap
 __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in, uint32_t n,
                                                  uint32_t* __restrict__ out_excl,
-                                                 uint32_t* __restrict__ out_copy, uint32_t cap,
+                                                 uint32_t* __restrict__ out_copy,
+                                                 uint32_t* __restrict__ out_dense, uint32_t cap,
                                                  uint32_t* __restrict__ big_list, uint32_t* nbig,
                                                  uint32_t* total, uint32_t shift) {
   __shared__ uint32_t warp_sums[32];
@@ -175,12 +176,22 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
     uint32_t c = in[(size_t)i << shift];
     out_excl[i] = run;
     if (out_copy) out_copy[(size_t)i << shift] = run;
+    if (out_dense) out_dense[i] = c;
     if (big_list && c > cap) big_list[atomicAdd(nbig, 1u)] = i;
     run += c;
   }
   if (tid == T - 1) {
     out_excl[n] = run;
     if (total) *total = run;
+  }
+}
+
+__global__ void k_sum_src(const uint32_t* __restrict__ all, uint32_t world, uint32_t stride, uint32_t base,
+                          uint32_t n, uint32_t* __restrict__ tot) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    uint32_t t = 0;
+    for (uint32_t s = 0; s < world; s++) t += all[(size_t)s * stride + base + b];
+    tot[b] = t;
   }
 }
 
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(256) k_checksum_in(const uint4* __restrict__ r
 
 template <int RB>
 __global__ void __launch_bounds__(256) k_checksum_out(ShuffleBuffers b, uint32_t B, BinParams bp,
-                                                      unsigned long long* acc) {
+                                                      uint32_t bin_base, unsigned long long* acc) {
   constexpr int KW = Rec<RB>::kKeyWords;
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(256) k_checksum_out(ShuffleBuffers b, uint32_t
       }
       uint32_t pid;
       uint32_t mybin = bin_of<RB>(w, bp, &pid);
-      if (mybin != bin) bad_part++;
+      if (mybin != bin + bin_base) bad_part++;
     }
   }
   a0 = warp_sum64(a0);
@@ -330,22 +341,26 @@ int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, cons
   k_gen_zipf32<<<stream_grid(n, 256, 8), 256, 0, s>>>((uint4*)dst, seed, start, n, d_table, V);
   return 1;
 }
-int launch_hist(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                uint32_t ordered, uint32_t ctr_shift, uint32_t* hist, cudaStream_t s) {
+int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* hist, cudaStream_t s) {
   if (!n) return 0;
-  BinParams bp{P, S, partitioner, ordered, ctr_shift};
   DISPATCH_RB(rb, (k_hist<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
   return 1;
 }
-int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t cap,
-                  uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift, cudaStream_t s) {
-  k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, cap, big_list, nbig, total, shift);
+int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t* out_dense,
+                  uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift,
+                  cudaStream_t s) {
+  k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
   return 1;
 }
-int launch_scatter(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                   uint32_t ordered, uint32_t ctr_shift, uint32_t* cursor, void* mid, cudaStream_t s) {
+int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
+                   uint32_t* tot, cudaStream_t s) {
   if (!n) return 0;
-  BinParams bp{P, S, partitioner, ordered, ctr_shift};
+  k_sum_src<<<(n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, 256, 0, s>>>(all, world, stride, base, n, tot);
+  return 1;
+}
+int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
+                   cudaStream_t s) {
+  if (!n) return 0;
   DISPATCH_RB(rb, (k_scatter<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
                                                                        (uint4*)mid)));
   return 1;
@@ -374,11 +389,10 @@ int launch_checksum_in(int rb, const void* recs, uint64_t n, uint64_t* acc4, cud
                                                                            (unsigned long long*)acc4)));
   return 1;
 }
-int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t P, uint32_t S,
-                        uint32_t partitioner, uint32_t ordered, uint64_t* acc6, cudaStream_t s) {
-  BinParams bp{P, S, partitioner, ordered, 0};
+int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, const BinParams& bp, uint32_t bin_base,
+                        uint64_t* acc6, cudaStream_t s) {
   int grid = g_sm_count * 8;
-  DISPATCH_RB(rb, (k_checksum_out<RB><<<grid, 256, 0, s>>>(b, B, bp, (unsigned long long*)acc6)));
+  DISPATCH_RB(rb, (k_checksum_out<RB><<<grid, 256, 0, s>>>(b, B, bp, bin_base, (unsigned long long*)acc6)));
   return 1;
 }
 

@@ -5,7 +5,29 @@
 
 namespace mrhbm {
 
-struct BinParams;
+#ifdef __CUDACC__
+#define MRHBM_HD __host__ __device__
+#else
+#define MRHBM_HD
+#endif
+
+struct BinParams {
+  uint32_t P;            // partitions
+  uint32_t S;            // sub-bins per partition
+  uint32_t partitioner;  // MRHBM_PART_*
+  uint32_t ordered;      // 1: sub-bin = top key bits (partition becomes one ascending run)
+                         // 0: sub-bin = further hash bits (partition = S ascending runs)
+  uint32_t ctr_shift;    // hist / cursor counters live at index bin << ctr_shift: the L2
+                         // atomic unit serialises per 32 B sector, so counters are spread out
+  // multi-GPU: partition p is owned by rank p % world and sits in slot pbase[p % world] + p / world,
+  // so that the bins of one destination rank are contiguous (its all-to-all send region)
+  uint32_t world;        // 1 = single GPU (slot == p)
+  uint32_t pbase[9];
+};
+
+MRHBM_HD inline uint32_t partition_slot(const BinParams& bp, uint32_t pid) {
+  return bp.world > 1 ? bp.pbase[pid % bp.world] + pid / bp.world : pid;
+}
 
 constexpr int kCapBytes = 32 * 1024;  // record bytes one CTA sorts in shared memory (2 CTAs per SM)
 inline uint32_t cap_records(int rb) { return (uint32_t)(kCapBytes / rb); }
@@ -22,6 +44,14 @@ struct ShuffleBuffers {
   void* mid;           // scattered records, N * RB
   void* out_keys;      // N * key_bytes (runs at bin_off)
   uint64_t* out_sums;  // N
+  // Where the records of bin b live: nseg segments, segment s holds
+  // seg_off[s][b+1]-seg_off[s][b] records at src + (seg_base[s] + seg_off[s][b]) records.
+  // Single GPU: one segment == the scattered buffer (seg_off[0] = bin_off).  After the
+  // all-to-all: one segment per source rank inside the receive buffer.
+  const void* src;
+  uint32_t nseg;
+  const uint32_t* seg_off[8];
+  uint64_t seg_base[8];
 };
 enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3 };
 enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2 };
@@ -30,21 +60,25 @@ enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2 };
 int launch_gen_u64(void* dst, uint64_t seed, uint64_t start, uint64_t n, cudaStream_t s);
 int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, const uint64_t* d_table,
                       uint64_t V, cudaStream_t s);
-int launch_hist(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                uint32_t ordered, uint32_t ctr_shift, uint32_t* hist, cudaStream_t s);
+int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* hist, cudaStream_t s);
+// exclusive scan of in[i << shift], i < n: out_excl[n+1]; optional copies: out_copy[i << shift] (scatter
+// cursors), out_dense[i] (the counts, densely packed), entries > cap appended to big_list
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy,
-                  uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift,
-                  cudaStream_t s);
-int launch_scatter(int rb, const void* recs, uint64_t n, uint32_t P, uint32_t S, uint32_t partitioner,
-                   uint32_t ordered, uint32_t ctr_shift, uint32_t* cursor, void* mid, cudaStream_t s);
+                  uint32_t* out_dense, uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total,
+                  uint32_t shift, cudaStream_t s);
+int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
+                   cudaStream_t s);
+// tot[b] = sum over s < world of all[s * stride + base + b], b < n
+int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
+                   uint32_t* tot, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);
 int launch_compact(int rb, const ShuffleBuffers& b, uint32_t B, void* dst_keys, uint64_t* dst_sums,
                    cudaStream_t s);
 int launch_checksum_in(int rb, const void* recs, uint64_t n, uint64_t* acc4, cudaStream_t s);
-int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t P, uint32_t S,
-                        uint32_t partitioner, uint32_t ordered, uint64_t* acc6, cudaStream_t s);
+int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, const BinParams& bp, uint32_t bin_base,
+                        uint64_t* acc6, cudaStream_t s);
 cudaError_t kernels_configure();  // opt-in shared memory sizes; call once per device
 
 }  // namespace mrhbm

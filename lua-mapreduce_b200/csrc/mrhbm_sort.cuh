@@ -254,17 +254,27 @@ __device__ uint32_t counting_path(const SortSmem& sm, uint32_t cnt, uint64_t pmi
 
 // Sorts cnt (<= cap) records of one bin by key, sums the values of equal keys and writes
 // the groups in ascending key order.  Returns the number of groups.
+template <int RB, int MODE>
+__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out);
+
 template <int RB, int MODE, bool NC>
 __device__ uint32_t process_chunk(const SortSmem& sm, const uint4* __restrict__ src, uint32_t cnt,
                                   const ChunkOut& out) {
   using R = Rec<RB>;
+  // coalesced load of the bin
+  for (uint32_t v = threadIdx.x; v < cnt * R::kVec; v += blockDim.x) sm.rec[v] = NC ? ldg_stream(src + v) : src[v];
+  __syncthreads();
+  return process_loaded<RB, MODE>(sm, cnt, out);
+}
+
+// the bin's cnt records are in sm.rec (all threads have passed a barrier after the load)
+template <int RB, int MODE>
+__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out) {
+  using R = Rec<RB>;
   constexpr uint32_t CAP = kCapBytes / RB;
   const uint32_t tid = threadIdx.x, T = blockDim.x;
   const uint32_t* recw = (const uint32_t*)sm.rec;
-  // 1. coalesced load of the bin
-  for (uint32_t v = tid; v < cnt * R::kVec; v += T) sm.rec[v] = NC ? ldg_stream(src + v) : src[v];
-  __syncthreads();
-  // 2. range of the 64-bit key prefix
+  // range of the 64-bit key prefix
   uint64_t pmin = ~0ull, pmax = 0;
   for (uint32_t i = tid; i < cnt; i += T) {
     uint64_t p = key_prefix64<RB>(recw + i * R::kWords);
@@ -376,7 +386,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
       continue;
     }
     ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
-    uint32_t g = process_chunk<RB, MODE_FINAL, true>(sm, (const uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec, cnt, out);
+    // gather the bin's segments (one per source rank after the all-to-all; one on a single GPU)
+    uint32_t filled = 0;
+    for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
+      uint32_t so = b.seg_off[sgm][bin], sc = b.seg_off[sgm][bin + 1] - so;
+      const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * Rec<RB>::kVec;
+      for (uint32_t v = threadIdx.x; v < sc * Rec<RB>::kVec; v += blockDim.x)
+        sm.rec[filled * Rec<RB>::kVec + v] = ldg_stream(src + v);
+      filled += sc;
+    }
+    __syncthreads();
+    uint32_t g = process_loaded<RB, MODE_FINAL>(sm, cnt, out);
     if (threadIdx.x == 0) b.ucount[bin] = g;
   }
 }
@@ -389,6 +409,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, 
   uint32_t bin = b.big_list[blockIdx.x];
   uint32_t off = b.bin_off[bin], n = b.bin_off[bin + 1] - off;
   uint4* base = (uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
+  if (b.src != b.mid) {  // after an exchange: make the bin contiguous inside the (free) send buffer
+    uint64_t filled = 0;
+    for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
+      uint32_t so = b.seg_off[sgm][bin], sc = b.seg_off[sgm][bin + 1] - so;
+      const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * Rec<RB>::kVec;
+      for (uint64_t v = threadIdx.x; v < (uint64_t)sc * Rec<RB>::kVec; v += blockDim.x)
+        base[filled * Rec<RB>::kVec + v] = src[v];
+      filled += sc;
+    }
+    __syncthreads();
+  }
   while (n > cap) {
     uint32_t w = 0;
     for (uint32_t c = 0; c < n; c += cap) {

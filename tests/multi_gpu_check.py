@@ -1,0 +1,126 @@
+"""Launched by torchrun (one rank per GPU) from tests/test_gpu_multi.py and profiles/*.sh:
+the sharded shuffle (count all-gather + NCCL all-to-all + per-rank sort/reduce) must give the
+oracle's result for the union of all ranks' pairs, with partition p living on rank p % world."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mrhbm_loader  # noqa: E402
+
+mrhbm_loader.load()
+from lua_mapreduce_b200 import mrhbm, parallel, synth  # noqa: E402
+
+
+def check(name, cond):
+    if not cond:
+        raise AssertionError("rank %d: %s" % (dist.get_rank(), name))
+
+
+def run_u64(rank, world, n_per, P, flags=0, dup=False):
+    import oracle as O
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, device=int(os.environ["LOCAL_RANK"]), flags=flags) as ctx:
+        parallel.init_comm(ctx, dist)
+        m = ctx.map_begin("r%d" % rank)
+        if dup:  # hot key + few distinct keys: big-bin path after the exchange
+            keys, vals = O.gen_u64(synth.SEED, rank * n_per, n_per)
+            keys = keys[np.arange(n_per) % 3000]
+            keys[::5] = np.uint64(42)
+            recs = np.zeros(n_per, dtype=mrhbm.record_dtype(mrhbm.KEY_U64))
+            recs["key"], recs["val"] = keys, vals
+            m.emit_batch(recs)
+        else:
+            m.gen_u64(synth.SEED, rank * n_per, n_per)
+        m.commit()
+        ctx.shuffle()
+        info = ctx.result_info()
+        gk, gs, gpo = ctx.result_copy()
+        cin, cout = ctx.checksum_input(), ctx.checksum_result()
+        st = ctx.stats()
+        pairs = parallel.gather_final_pairs(ctx, dist) if n_per <= 200_000 else None
+        box = [None] * world
+        payload = (gk, gs, gpo, cin, cout, info.sorted, ctx.partitions(), st,
+                   (keys, vals) if dup else None)
+        dist.gather_object(payload, box if rank == 0 else None, dst=0)
+        if rank != 0:
+            return
+        if dup:
+            keys = np.concatenate([b[8][0] for b in box])
+            vals = np.concatenate([b[8][1] for b in box])
+        else:
+            keys, vals = O.gen_u64(synth.SEED, 0, n_per * world)
+        ok, osum, po = O.groupby_u64(keys, vals, O.PART_MULHASH, P)
+        tot_in = [sum(b[3][i] for b in box) % 2**64 for i in range(3)]
+        tot_out = [sum(b[4][i] for b in box) % 2**64 for i in range(3)]
+        check("sum linearity across ranks", tot_in == tot_out)
+        check("pairs", sum(b[3][3] for b in box) == keys.size)
+        check("groups", sum(b[4][3] for b in box) == ok.size)
+        check("order / membership", all(b[4][4:] == [0, 0] for b in box))
+        for r, (gk, gs, gpo, _, _, srt, parts, st, _) in enumerate(box):
+            check("ownership", all(p % world == r for p in parts))
+            for p in range(P):
+                a, b = int(gpo[p]), int(gpo[p + 1])
+                if p % world != r:
+                    check("foreign partition empty", a == b)
+                    continue
+                wa, wb = int(po[p]), int(po[p + 1])
+                check("partition size", b - a == wb - wa)
+                k, s = gk[a:b], gs[a:b]
+                if not srt:
+                    o = np.argsort(k, kind="stable")
+                    k, s = k[o], s[o]
+                check("partition %d keys" % p, (k == ok[wa:wb]).all() and (s == osum[wa:wb]).all())
+        if pairs is not None:
+            want = [(int(np.searchsorted(po, i, side="right")) - 1, int(ok[i]).to_bytes(8, "big"), [int(osum[i])])
+                    for i in range(ok.size)]
+            check("finalfn order over all ranks", pairs == want)
+        print("u64 world=%d n/rank=%d P=%d dup=%s ok: groups=%d sorted=%s big_bins=%s exch=%.3f ms %.1f MB"
+              % (world, n_per, P, dup, ok.size, [b[5] for b in box], [b[7]["big_bins"] for b in box],
+                 box[0][7]["ms_exchange"], box[0][7]["bytes_exchanged"] / 1e6), flush=True)
+
+
+def run_zipf(rank, world, n_per, P):
+    import oracle as O
+    table = synth.zipf_table(1 << 14)
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, device=int(os.environ["LOCAL_RANK"])) as ctx:
+        parallel.init_comm(ctx, dist)
+        m = ctx.map_begin("r%d" % rank)
+        m.gen_zipf(synth.SEED, rank * n_per, n_per, table)
+        m.commit()
+        ctx.shuffle()
+        pairs = parallel.gather_final_pairs(ctx, dist)
+        st = ctx.stats()
+        if rank != 0:
+            return
+        recs = O.gen_zipf_rec32(synth.SEED, 0, n_per * world, table)
+        okeys, osum, po = O.groupby_rec(recs, O.PART_FNV_LUA, P)
+        want = [(int(np.searchsorted(po, i, side="right")) - 1, bytes(okeys[i]).rstrip(b"\0"), [int(osum[i])])
+                for i in range(osum.size)]
+        check("zipf word count over all ranks", pairs == want)
+        print("zipf world=%d n/rank=%d P=%d ok: groups=%d big_bins(rank0)=%d" % (world, n_per, P, osum.size, st["big_bins"]),
+              flush=True)
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    run_u64(rank, world, 100_000, 16)
+    run_u64(rank, world, 1_000_000, 1024)
+    run_u64(rank, world, 200_000, 7, dup=True)           # P not a multiple of world, hot key
+    run_u64(rank, world, 150_000, 3, flags=mrhbm.F_FORCE_RUNS)
+    run_zipf(rank, world, 200_000, 15)
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_CHECK_OK world=%d" % world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
