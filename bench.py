@@ -32,7 +32,7 @@ UNIT = "pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="u64", choices=["u64", "zipf32"])
@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -176,6 +176,10 @@ def run_reference(a):
 
 def main():
     a = parse()
+    # Libraries (NCCL prints its version) must not pollute stdout: the driver reads ONE JSON line.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if a.impl == "reference":
         return run_reference(a)
     import torch
@@ -189,7 +193,9 @@ def main():
     if a.gpus > 1 or world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     else:
         dist = None
     torch.cuda.set_device(local)
@@ -222,6 +228,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        for _ in range(3):  # let nvidia-smi attach before the timed region
+            ctx.shuffle()
     barrier()
     t0 = time.perf_counter()
     agg = {}
@@ -243,6 +251,12 @@ def main():
     st = ctx.stats()
     groups = ctx.result_info().groups
     cin, cout = ctx.checksum_input(), ctx.checksum_result()
+    if dist is not None:  # the sum is linear over the whole job: add the per-rank digests mod 2^64
+        box = [None] * world
+        dist.all_gather_object(box, (cin, cout))
+        cin = [sum(b[0][i] for b in box) % 2**64 for i in range(4)]
+        cout = [sum(b[1][i] for b in box) % 2**64 for i in range(6)]
+        groups = cout[3]
     parity_ok = cin[:3] == cout[:3] and cout[4:] == [0, 0]
     ms_step = 1e3 * dt / a.steps
     dev_ms = {k: v / a.steps for k, v in agg.items()}
@@ -251,18 +265,22 @@ def main():
     # ---- roofline (SURVEY 8d accounting: one read of its input + one write of its output per stage)
     peak, peak_src = peaks()
     R = rb
-    stage_bytes = {
-        "hash_partition(k_hist+k_scatter)": 2 * n * R,
-        "sort+segmented_reduce(k_sort_reduce)": 3 * n * R + groups * R,
+    g_local = ctx.result_info().groups
+    stage_bytes = {  # per GPU, SURVEY 8d: hash-partition = N R + N R, sort = N R + N R, reduce = N R + U R
+        "k_scatter": 2 * n * R,              # the hash-partition stage's read + write (k_hist is overhead)
+        "k_sort_reduce": 3 * n * R + g_local * R,
     }
     pipe_bytes = sum(stage_bytes.values())
-    k_ms = {"hash_partition(k_hist+k_scatter)": dev_ms["ms_hist"] + dev_ms["ms_plan"] + dev_ms["ms_scatter"],
-            "sort+segmented_reduce(k_sort_reduce)": dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"]}
+    k_ms = {"k_scatter": dev_ms["ms_scatter"], "k_sort_reduce": dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"]}
     dom = max(k_ms, key=k_ms.get)
     ach = stage_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp) and world == 1 and a.workload == "u64" and n == 100_000_000:
+        traffic = json.load(open(tp)).get(dom)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes": stage_bytes[dom],
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": stage_bytes[dom],
         "kernel_ms": k_ms[dom],
         "pipeline": {"algorithmic_bytes": pipe_bytes, "ms": dev_ms["ms_total"],
                      "achieved": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9,
@@ -284,8 +302,9 @@ def main():
             mm.commit()
             ctx.pool_read(0, n, host)
             ctx.reset()
-        out_keys = ctx.pinned_array(n, np.uint64 if kind == mrhbm.KEY_U64 else "S%d" % (rb - 4))
-        out_sums = ctx.pinned_array(n, np.uint64)
+        cap_out = n + n // 16 + 4096  # a rank may own slightly more than n groups after the exchange
+        out_keys = ctx.pinned_array(cap_out, np.uint64 if kind == mrhbm.KEY_U64 else "S%d" % (rb - 4))
+        out_sums = ctx.pinned_array(cap_out, np.uint64)
         chunk = 1 << 22
         e2e_dt = []
         for it in range(a.e2e_steps + 1):

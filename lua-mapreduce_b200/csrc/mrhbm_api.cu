@@ -585,6 +585,7 @@ BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered) {
   bp.ctr_shift = c->ctr_shift;
   bp.world = (uint32_t)c->world;
   for (int r = 0; r <= 8; r++) bp.pbase[r] = c->pbase[r];
+  if (const char* e = getenv("MRHBM_DEBUG_SCATTER")) bp.debug = (uint32_t)atoi(e);  // profiling hook, results invalid
   return bp;
 }
 

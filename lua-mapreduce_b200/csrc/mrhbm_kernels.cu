@@ -125,8 +125,20 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
     for (int k = 0; k < U; k++)
       if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
 #pragma unroll
-    for (int k = 0; k < U; k++)
-      if (base + k * stride < n) pos[k] = atomicAdd(cursor + ((size_t)bin_of<RB>(w[k], bp, nullptr) << bp.ctr_shift), 1u);
+    for (int k = 0; k < U; k++) {
+      if (base + k * stride < n) {
+        uint32_t bin = bin_of<RB>(w[k], bp, nullptr);
+        if (bp.debug == 0) {
+          pos[k] = atomicAdd(cursor + ((size_t)bin << bp.ctr_shift), 1u);
+        } else if (bp.debug == 1) {  // profiling only: stores without the claim (results invalid)
+          pos[k] = cursor[(size_t)bin << bp.ctr_shift] + (uint32_t)((base + k * stride) & 1023);
+          if (pos[k] >= n) pos[k] = (uint32_t)(n - 1);
+        } else {  // profiling only: claim without the scattered store
+          pos[k] = atomicAdd(cursor + ((size_t)bin << bp.ctr_shift), 1u);
+        }
+      }
+    }
+    if (bp.debug == 2) continue;
 #pragma unroll
     for (int k = 0; k < U; k++) {
       if (base + k * stride < n) {

@@ -23,6 +23,7 @@ struct BinParams {
   // so that the bins of one destination rank are contiguous (its all-to-all send region)
   uint32_t world;        // 1 = single GPU (slot == p)
   uint32_t pbase[9];
+  uint32_t debug;        // MRHBM_DEBUG_SCATTER profiling variants (0 = product path)
 };
 
 MRHBM_HD inline uint32_t partition_slot(const BinParams& bp, uint32_t pid) {

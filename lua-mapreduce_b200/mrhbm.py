@@ -279,6 +279,8 @@ class Ctx:
             keys = np.empty(max(g, 1), dtype=np.uint64 if self.key_kind == KEY_U64 else "S%d" % info.key_bytes)
         if sums is None:
             sums = np.empty(max(g, 1), dtype=np.uint64)
+        if keys.shape[0] < g or sums.shape[0] < g:
+            raise MrhbmError(-1, "result_copy: output arrays hold %d groups, %d needed" % (min(keys.shape[0], sums.shape[0]), g))
         po = np.empty(self.num_partitions + 1, dtype=np.uint64)
         self._chk(self.L.mrhbm_result_copy(self.h, keys.ctypes.data, sums.ctypes.data, po.ctypes.data))
         return keys[:g], sums[:g], po

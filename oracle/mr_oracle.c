@@ -257,6 +257,10 @@ struct mro {
   uint32_t nparts;
   ofile_t *files;
   size_t nfiles, capfiles;
+  uint32_t *findex; /* open-addressing name -> file index + 1 (listing stays a table scan
+                       only in spirit: GridFS answers name queries from an index too) */
+  size_t findex_cap;
+  size_t *part_first, *part_next; /* per-partition file chains built by mro_reduce_all */
   ofile_t *results;
   size_t nresults;
   pthread_mutex_t mu;
@@ -293,8 +297,41 @@ static void free_files(ofile_t *f, size_t n) {
   }
   free(f);
 }
+static uint64_t hash_bytes(const void *p, size_t n, uint64_t seed);
+static void findex_rebuild(mro_t *o, size_t cap) {
+  free(o->findex);
+  o->findex_cap = cap;
+  o->findex = (uint32_t *)calloc(cap, sizeof(uint32_t));
+  for (size_t i = 0; i < o->nfiles; i++) {
+    size_t h = hash_bytes(o->files[i].name, strlen(o->files[i].name), 7) & (cap - 1);
+    while (o->findex[h]) h = (h + 1) & (cap - 1);
+    o->findex[h] = (uint32_t)i + 1;
+  }
+}
+/* find-or-create in the global spill table (caller holds o->mu) */
+static ofile_t *global_file_get(mro_t *o, const char *name) {
+  if (!o->findex_cap || (o->nfiles + 1) * 2 > o->findex_cap) findex_rebuild(o, o->findex_cap ? o->findex_cap * 2 : 1024);
+  size_t cap = o->findex_cap, h = hash_bytes(name, strlen(name), 7) & (cap - 1);
+  while (o->findex[h]) {
+    ofile_t *f = &o->files[o->findex[h] - 1];
+    if (strcmp(f->name, name) == 0) return f;
+    h = (h + 1) & (cap - 1);
+  }
+  if (o->nfiles == o->capfiles) {
+    o->capfiles = o->capfiles ? o->capfiles * 2 : 64;
+    o->files = (ofile_t *)realloc(o->files, o->capfiles * sizeof(ofile_t));
+  }
+  ofile_t *f = &o->files[o->nfiles++];
+  memset(f, 0, sizeof *f);
+  f->name = strdup(name);
+  o->findex[h] = (uint32_t)o->nfiles;
+  return f;
+}
 void mro_free(mro_t *o) {
   if (!o) return;
+  free(o->findex);
+  free(o->part_first);
+  free(o->part_next);
   free_files(o->files, o->nfiles);
   free_files(o->results, o->nresults);
   pthread_mutex_destroy(&o->mu);
@@ -479,7 +516,7 @@ int mro_map_commit(mro_map_t *m) {
   /* job.lua:217-221: remove_file + build == replace by name */
   pthread_mutex_lock(&o->mu);
   for (size_t i = 0; i < nl; i++) {
-    ofile_t *g = file_get(&o->files, &o->nfiles, &o->capfiles, local[i].name);
+    ofile_t *g = global_file_get(o, local[i].name);
     free(g->data.p);
     g->data = local[i].data;
     g->part = local[i].part;
@@ -501,7 +538,7 @@ int mro_add_file(mro_t *o, const char *name, const void *data, size_t len) {
   /* server.lua:305 parses P<part>.M<mapper> from the name */
   const char *p = strstr(name, ".P");
   if (!p) return -1;
-  ofile_t *f = file_get(&o->files, &o->nfiles, &o->capfiles, name);
+  ofile_t *f = global_file_get(o, name);
   f->part = strtol(p + 2, NULL, 10);
   f->data.n = 0;
   sb_put(&f->data, data, len);
@@ -599,10 +636,10 @@ static int name_cmp(const void *a, const void *b) {
 /* job.lua:230-296 for one partition; appends result lines to out */
 static int reduce_partition(mro_t *o, long part, sbuf_t *out, char *err, size_t errn) {
   /* job.lua:255-260: files matching ^<path>/map_results.P<part>\..*  (listed sorted by name) */
-  size_t nf = 0;
-  ofile_t **fl = (ofile_t **)malloc((o->nfiles ? o->nfiles : 1) * sizeof *fl);
-  for (size_t i = 0; i < o->nfiles; i++)
-    if (o->files[i].part == part) fl[nf++] = &o->files[i];
+  size_t nf = 0, cnt = 0;
+  for (size_t i = o->part_first[part]; i != (size_t)-1; i = o->part_next[i]) cnt++;
+  ofile_t **fl = (ofile_t **)malloc((cnt ? cnt : 1) * sizeof *fl);
+  for (size_t i = o->part_first[part]; i != (size_t)-1; i = o->part_next[i]) fl[nf++] = &o->files[i];
   qsort(fl, nf, sizeof *fl, name_cmp);
   liter_t *its = (liter_t *)calloc(nf ? nf : 1, sizeof *its);
   heap_t h = {0};
@@ -712,6 +749,15 @@ int mro_reduce_all(mro_t *o, int nthreads) {
   for (size_t i = 0; i < u; i++)
     if (parts[i] > maxp) maxp = parts[i];
   int digits = mro_count_digits(maxp);
+  free(o->part_first);
+  free(o->part_next);
+  o->part_first = (size_t *)malloc((size_t)(maxp + 1) * sizeof(size_t));
+  o->part_next = (size_t *)malloc((o->nfiles ? o->nfiles : 1) * sizeof(size_t));
+  for (long q = 0; q <= maxp; q++) o->part_first[q] = (size_t)-1;
+  for (size_t i = o->nfiles; i-- > 0;) {
+    o->part_next[i] = o->part_first[o->files[i].part];
+    o->part_first[o->files[i].part] = i;
+  }
   o->results = (ofile_t *)calloc(u ? u : 1, sizeof(ofile_t));
   o->nresults = u;
   for (size_t i = 0; i < u; i++) {
@@ -735,6 +781,9 @@ int mro_reduce_all(mro_t *o, int nthreads) {
     free_files(o->files, o->nfiles);
     o->files = NULL;
     o->nfiles = o->capfiles = 0;
+    free(o->findex);
+    o->findex = NULL;
+    o->findex_cap = 0;
   }
   return c.rc ? -1 : (int)u;
 }

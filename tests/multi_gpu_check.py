@@ -109,7 +109,8 @@ def run_zipf(rank, world, n_per, P):
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     rank, world = dist.get_rank(), dist.get_world_size()
     run_u64(rank, world, 100_000, 16)
     run_u64(rank, world, 1_000_000, 1024)
