@@ -204,7 +204,8 @@ def main():
     table = synth.zipf_table() if a.workload == "zipf32" else None
     kind = mrhbm.KEY_U64 if a.workload == "u64" else mrhbm.KEY_STR
     part = mrhbm.PART_MULHASH if a.workload == "u64" else mrhbm.PART_FNV_LUA
-    ctx = mrhbm.Ctx(kind, P, part, max_key_bytes=27, device=local, reserve_pairs=n)
+    ctx = mrhbm.Ctx(kind, P, part, max_key_bytes=27, device=local, reserve_pairs=n,
+                    combiner=(a.workload == "zipf32"))  # the reference's headline run uses combiner = reducer
     if world > 1:
         uid = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

@@ -74,6 +74,7 @@ typedef struct mrhbm_config {
 } mrhbm_config;
 #define MRHBM_F_FORCE_RUNS 1u   /* always use hash sub-bins (skip the key-ordered attempt) */
 #define MRHBM_F_SMALL_BINS 2u   /* test hook: tiny smem bins to exercise the overflow paths */
+#define MRHBM_F_NO_OPTIMISTIC 4u /* always run the exact two-pass (histogram) partition layout */
 
 /* record layouts (little endian) moved by emit_batch / gen / result_copy:
  *   U64 : { uint64_t key; uint32_t value; uint32_t zero; }              16 B

@@ -25,7 +25,7 @@ struct Range {
   uint64_t owner;  // map handle serial
 };
 constexpr size_t kStageRecs = 1 << 16;
-enum { EV_START, EV_COMBINE, EV_HIST, EV_PLAN, EV_SCATTER, EV_EXCH, EV_SORT, EV_BIG, EV_END, EV_PROBE, EV_N };
+enum { EV_START, EV_CSTART, EV_COMBINE, EV_HIST, EV_PLAN, EV_SCATTER, EV_EXCH, EV_SORT, EV_BIG, EV_END, EV_PROBE, EV_N };
 }  // namespace
 
 struct mrhbm_ctx {
@@ -52,6 +52,10 @@ struct mrhbm_ctx {
   void *recvbuf = nullptr, *bigbuf = nullptr;
   uint64_t recv_cap = 0, big_cap = 0;
   uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
+  bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
+  bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
+  void* comb = nullptr;  // map-side combined pairs
+  uint64_t comb_cap = 0;
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
   std::vector<uint32_t> h_bin_off, h_uoff;
@@ -359,7 +363,7 @@ void mrhbm_destroy(mrhbm_ctx* c) {
   void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
-                   c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small};
+                   c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -656,6 +660,36 @@ int ensure_out(mrhbm_ctx* c, uint64_t need) {
   return 0;
 }
 
+struct Src {
+  const char* p;
+  uint64_t n;
+};
+// The pairs the shuffle partitions: the committed pool ranges, or -- with a combiner declared
+// (job.lua:92-96,198-202) -- their map-side combined image.  EV_START .. EV_COMBINE.
+int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_stats& st) {
+  srcs.clear();
+  uint64_t n = 0;
+  for (auto& r : live_ranges(c)) {
+    srcs.push_back(Src{(const char*)c->pool + r.first * c->rb, r.second});
+    n += r.second;
+  }
+  *N = n;
+  if (!c->cfg.combiner || n < (1u << 20)) return 0;
+  int rc = ensure_records(c, &c->comb, &c->comb_cap, n);
+  if (rc) return rc;
+  unsigned long long* cnt = (unsigned long long*)c->d_acc;
+  CU(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+  for (auto& sr : srcs) st.launches += launch_combine(c->rb, sr.p, sr.n, c->comb, cnt, c->sm_count, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->h_acc, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  uint64_t n2 = c->h_acc[0];
+  srcs.clear();
+  srcs.push_back(Src{(const char*)c->comb, n2});
+  *N = n2;
+  return 0;
+}
+
 uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
   // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill
   uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap));
@@ -665,7 +699,7 @@ uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
 
 void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
   st.ms_total = ev_ms(c, EV_START, EV_END);
-  st.ms_combine = 0;
+  st.ms_combine = ev_ms(c, EV_START, EV_CSTART);
   st.ms_hist = ev_ms(c, EV_COMBINE, EV_HIST);
   st.ms_plan = ev_ms(c, EV_HIST, EV_PLAN);
   st.ms_scatter = ev_ms(c, EV_PLAN, EV_SCATTER);
@@ -676,19 +710,81 @@ void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
 
 // ---- one GPU: hist -> scan -> scatter -> sort+reduce ---------------------------------------
 int shuffle_single(mrhbm_ctx* c) {
-  auto live = live_ranges(c);
-  uint64_t N = 0;
-  for (auto& r : live) N += r.second;
-  if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
+  uint64_t N_in = 0;
+  for (auto& r : live_ranges(c)) N_in += r.second;
+  if (N_in >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N_in);
   const uint32_t P = c->cfg.num_partitions;
-  uint32_t S = pick_sub_bins(c, N);
   int rc = 0;
   uint32_t nbig = 0, ordered = 1;
   mrhbm_stats st{};
-  st.pairs = N;
+  st.pairs = N_in;
   cudaStream_t s = c->stream;
-  uint64_t B = 0;
+  uint64_t B = 0, N = 0;
+  std::vector<Src> live;
   CU(c, cudaEventRecord(c->ev[EV_START], s));
+  rc = collect_sources(c, live, &N, st);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[EV_CSTART], s));
+  uint32_t S = pick_sub_bins(c, N);
+  bool skip_ordered = c->no_ordered;
+  // ---- optimistic single pass: no histogram.  Hash-balanced bins almost never exceed their
+  // capacity (mean = cap - 6 sigma); the cursor claim doubles as the count.  A full bin sets
+  // ERRF_CAPACITY and the exact two-pass layout below takes over (and stays, for this ctx).
+  if (!c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && N > 0 && (uint64_t)P * S < (1ull << 31)) {
+    B = (uint64_t)P * S;
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !skip_ordered) || S == 1);
+    rc = ensure_buffers(c, B, B * c->cap);
+    if (rc) return rc;
+    BinParams bp = make_bp(c, S, ordered);
+    st.attempts++;
+    CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+    CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
+    CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
+    CU(c, cudaEventRecord(c->ev[EV_HIST], s));
+    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+    for (auto& r : live)
+      st.launches += launch_scatter_fixed(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, c->cap, c->sb.counters + CNT_ERR, s);
+    CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
+    CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
+    c->sb.src = c->sb.mid;
+    c->sb.nseg = 1;
+    c->sb.stride = c->cap;
+    c->sb.ctr_shift = c->ctr_shift;
+    st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+    CU(c, cudaEventRecord(c->ev[EV_SORT], s));
+    CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+    st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
+                                 c->sb.counters + CNT_TOTAL, 0, s);
+    c->h_uoff.resize(B + 1);
+    CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->ev[EV_END], s));
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(s));
+    if (!(c->h_counters[CNT_ERR] & ERRF_CAPACITY)) {
+      c->rv = c->sb;
+      c->sb.stride = 0;
+      c->B = (uint32_t)B;
+      c->S = S;
+      c->ordered = ordered;
+      c->N = N_in;
+      c->N_recv = N;
+      c->bin_base = 0;
+      c->groups = c->h_uoff[B];
+      c->shuffled = true;
+      c->compacted = false;
+      st.bins = (uint32_t)B;
+      st.sub_bins = S;
+      st.big_bins = 0;
+      st.groups = c->groups;
+      st.ms_exchange = 0;
+      finish_stats(c, st);
+      return MRHBM_OK;
+    }
+    c->sb.stride = 0;
+    c->no_optimistic = true;
+    if (ordered && S > 1) skip_ordered = c->no_ordered = true;  // key-ordered sub-bins just overflowed
+  }
   // A bin that holds more distinct keys than one CTA sorts (ERRF_SKEW) is retried with
   // twice the sub-bins: distinct keys spread, hot keys keep collapsing in k_big_bins.
   for (int widen = 0;; widen++) {
@@ -696,22 +792,22 @@ int shuffle_single(mrhbm_ctx* c) {
     if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
     rc = ensure_buffers(c, B, N);
     if (rc) return rc;
-    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !skip_ordered) || S == 1);
+    c->sb.stride = 0;
     for (int attempt = 0;; attempt++) {
       st.attempts++;
       BinParams bp = make_bp(c, S, ordered);
       CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
                                    c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live)
-        st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.cursor, c->sb.mid, s);
+      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
       c->sb.src = c->sb.mid;
@@ -726,6 +822,7 @@ int shuffle_single(mrhbm_ctx* c) {
       if (nbig && ordered && S > 1) {
         // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
         ordered = 0;
+        c->no_ordered = true;
         continue;
       }
       break;
@@ -757,7 +854,7 @@ int shuffle_single(mrhbm_ctx* c) {
   c->B = (uint32_t)B;
   c->S = S;
   c->ordered = ordered;
-  c->N = N;
+  c->N = N_in;
   c->N_recv = N;
   c->bin_base = 0;
   c->groups = c->h_uoff[B];
@@ -776,25 +873,28 @@ int shuffle_single(mrhbm_ctx* c) {
 //      -> sort+reduce of the owned partitions, each bin gathered from one segment per source
 int shuffle_multi(mrhbm_ctx* c) {
   const int G = c->world, me = c->rank;
-  auto live = live_ranges(c);
-  uint64_t N = 0;
-  for (auto& r : live) N += r.second;
-  if (N >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N);
+  uint64_t N_in = 0, N = 0;
+  for (auto& r : live_ranges(c)) N_in += r.second;
+  if (N_in >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N_in);
   const uint32_t P = c->cfg.num_partitions;
   uint32_t all[8];
-  int rc = gather_u32(c, (uint32_t)N, all);
+  mrhbm_stats st{};
+  st.pairs = N_in;
+  std::vector<Src> live;
+  CU(c, cudaEventRecord(c->ev[EV_START], c->stream));
+  int rc = collect_sources(c, live, &N, st);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[EV_CSTART], c->stream));
+  rc = gather_u32(c, (uint32_t)N, all);
   if (rc) return rc;
   uint64_t Nglobal = 0;
   for (int r = 0; r < G; r++) Nglobal += all[r];
   uint32_t S = pick_sub_bins(c, Nglobal);
   uint32_t nbig = 0, ordered = 1;
-  mrhbm_stats st{};
-  st.pairs = N;
   cudaStream_t s = c->stream;
   uint64_t B = 0, Bl = 0, total_recv = 0;
   uint64_t send_off[9], send_cnt[8], recv_off[9], recv_cnt[8];
   ShuffleBuffers v{};
-  CU(c, cudaEventRecord(c->ev[EV_START], s));
   for (int widen = 0;; widen++) {
     B = (uint64_t)P * S;
     Bl = (uint64_t)c->Pl * S;
@@ -811,7 +911,7 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       // send layout (destination-major bins) + dense counts for the all-gather
       st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->d_hd, 0xffffffffu, nullptr,
@@ -830,8 +930,7 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live)
-        st.launches += launch_scatter(c->rb, (char*)c->pool + r.first * c->rb, r.second, bp, c->sb.cursor, c->sb.mid, s);
+      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaGetLastError());
       CU(c, cudaStreamSynchronize(s));
@@ -870,6 +969,7 @@ int shuffle_multi(mrhbm_ctx* c) {
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     v = c->sb;
+    v.stride = 0;
     v.bin_off = c->d_outoff;
     v.src = c->recvbuf;
     v.mid = nbig ? c->bigbuf : c->recvbuf;
@@ -911,7 +1011,7 @@ int shuffle_multi(mrhbm_ctx* c) {
   c->B = (uint32_t)Bl;
   c->S = S;
   c->ordered = ordered;
-  c->N = N;
+  c->N = N_in;
   c->N_recv = total_recv;
   c->bin_base = c->pbase[me] * S;
   c->groups = c->h_uoff[Bl];

@@ -151,6 +151,43 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
   }
 }
 
+// Optimistic single pass: no histogram.  Every bin owns `stride` slots; the claim on the bin
+// cursor is both the slot and, afterwards, the bin's count.
+template <int RB>
+__global__ void __launch_bounds__(256) k_scatter_fixed(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
+                                                       uint32_t* __restrict__ cursor, uint4* __restrict__ mid,
+                                                       uint32_t slots, uint32_t* __restrict__ err_flags) {
+  constexpr int U = Unroll<RB>::U;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
+    uint32_t w[U][Rec<RB>::kWords];
+    uint32_t pos[U], bin[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (base + k * stride < n) {
+        bin[k] = bin_of<RB>(w[k], bp, nullptr);
+        pos[k] = atomicAdd(cursor + ((size_t)bin[k] << bp.ctr_shift), 1u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (base + k * stride < n) {
+        if (pos[k] >= slots) {
+          atomicOr(err_flags, (uint32_t)ERRF_CAPACITY);
+          continue;
+        }
+        uint4* d = mid + ((uint64_t)bin[k] * slots + pos[k]) * Rec<RB>::kVec;
+#pragma unroll
+        for (int v = 0; v < Rec<RB>::kVec; v++)
+          stg_stream(d + v, make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]));
+      }
+    }
+  }
+}
+
 // single-CTA exclusive scan (B <= a few million): out_excl[0..n], optional copy into
 // out_copy (scatter cursors), optional list of entries larger than cap
 __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in, uint32_t n,
@@ -198,6 +235,95 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
   }
 }
 
+// ============================================================================
+// map-side combiner (mapreduce/job.lua:92-96,198-202 with the built-in sum)
+// ============================================================================
+// Each CTA keeps an open-addressing table of whole records in shared memory for its lifetime;
+// a pair whose key is resident adds its value there, everything else passes through.  Hot
+// keys (Zipf) collapse to at most one record per CTA before the partition pass.
+constexpr uint32_t kCombineLock = 0xffffffffu;
+constexpr int kCombineThreads = 1024;
+constexpr int kCombineSmem = 200 * 1024;
+
+template <int RB>
+__global__ void __launch_bounds__(kCombineThreads, 1)
+    k_combine(const uint4* __restrict__ recs, uint64_t n, uint4* __restrict__ out, unsigned long long* out_count,
+              uint32_t entries) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = Rec<RB>;
+  constexpr int W = R::kWords, KW = R::kKeyWords;
+  uint32_t* tab = (uint32_t*)smem_raw;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  for (uint32_t i = tid; i < entries * W; i += blockDim.x) tab[i] = 0;
+  __syncthreads();
+  auto append = [&](bool want, const uint32_t* w) {  // warp-aggregated append to the output
+    uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    unsigned long long basepos = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) basepos = atomicAdd(out_count, (unsigned long long)__popc(mask));
+    basepos = __shfl_sync(0xffffffffu, basepos, __ffs(mask) - 1);
+    if (want) {
+      uint4* d = out + (basepos + __popc(mask & ((1u << lane) - 1))) * R::kVec;
+#pragma unroll
+      for (int v = 0; v < R::kVec; v++) stg_stream(d + v, make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]));
+    }
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_round = (n + 31) / 32 * 32;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n_round; i += stride) {
+    uint32_t w[W];
+    bool valid = i < n, pass = valid;
+    if (valid) {
+      load_rec<RB>(recs + i * R::kVec, w);
+      uint32_t v = w[KW];
+      bool small = v != 0 && v <= 0xffffu && (!R::kU64 || w[3] == 0);
+      if (small) {
+        uint64_t h = word_hash<RB>(w);
+        uint32_t slot = (uint32_t)__umul64hi(h, (uint64_t)entries);
+#pragma unroll 1
+        for (int probe = 0; probe < 4; probe++) {
+          uint32_t* e = tab + (size_t)slot * W;
+          uint32_t st = *(volatile uint32_t*)(e + KW);
+          if (st == 0) {
+            if (atomicCAS(e + KW, 0u, kCombineLock) == 0u) {
+#pragma unroll
+              for (int k = 0; k < KW; k++) e[k] = w[k];
+              __threadfence_block();
+              atomicExch(e + KW, v);
+              pass = false;
+              break;
+            }
+          } else if (st != kCombineLock && st <= 0x7fffffffu) {
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < KW; k++) eq &= (((volatile uint32_t*)e)[k] == w[k]);
+            if (eq) {
+              atomicAdd(e + KW, v);  // <= 0x7fffffff + 0xffff: never wraps, never looks empty or locked
+              pass = false;
+              break;
+            }
+          }
+          slot = slot + 1 == entries ? 0 : slot + 1;
+        }
+      }
+    }
+    append(pass, w);
+  }
+  __syncthreads();
+  // flush the table
+  const uint32_t e_round = (entries + 31) / 32 * 32;
+  for (uint32_t e = tid; e < e_round; e += blockDim.x) {
+    uint32_t w[W];
+    bool want = false;
+    if (e < entries) {
+#pragma unroll
+      for (int k = 0; k < W; k++) w[k] = tab[(size_t)e * W + k];
+      want = w[KW] != 0;
+    }
+    append(want, w);
+  }
+}
+
 __global__ void k_sum_src(const uint32_t* __restrict__ all, uint32_t world, uint32_t stride, uint32_t base,
                           uint32_t n, uint32_t* __restrict__ tot) {
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
@@ -219,7 +345,7 @@ __global__ void __launch_bounds__(256) k_compact(ShuffleBuffers b, uint32_t B, u
   const uint32_t* skeys = (const uint32_t*)b.out_keys;
   for (uint32_t bin = warp; bin < B; bin += nwarps) {
     uint32_t len = b.ucount[bin];
-    uint64_t so = b.bin_off[bin], d0 = b.uoff[bin];
+    uint64_t so = bin_start(b, bin), d0 = b.uoff[bin];
     for (uint32_t i = lane; i < len * KW; i += 32) dkeys[d0 * KW + i] = skeys[so * KW + i];
     for (uint32_t i = lane; i < len; i += 32) dsums[d0 + i] = b.out_sums[so + i];
   }
@@ -268,7 +394,7 @@ __global__ void __launch_bounds__(256) k_checksum_out(ShuffleBuffers b, uint32_t
   uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, bad_order = 0, bad_part = 0;
   for (uint32_t bin = warp; bin < B; bin += nwarps) {
     uint32_t len = b.ucount[bin];
-    uint64_t so = b.bin_off[bin];
+    uint64_t so = bin_start(b, bin);
     for (uint32_t i = lane; i < len; i += 32) {
       uint32_t w[Rec<RB>::kWords], p[Rec<RB>::kWords];
 #pragma unroll
@@ -331,6 +457,11 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
+#define CFGC(RB)                                                                                       \
+  e = cudaFuncSetAttribute(k_combine<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
+  if (e != cudaSuccess) return e;
+  CFGC(16) CFGC(32) CFGC(64) CFGC(128)
+#undef CFGC
   return cudaSuccess;
 }
 
@@ -364,6 +495,14 @@ int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* 
   k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
   return 1;
 }
+int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned long long* out_count, int sm_count,
+                   cudaStream_t s) {
+  if (!n) return 0;
+  uint32_t entries = (uint32_t)(kCombineSmem / rb);
+  DISPATCH_RB(rb, (k_combine<RB><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, (uint4*)out,
+                                                                                out_count, entries)));
+  return 1;
+}
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                    uint32_t* tot, cudaStream_t s) {
   if (!n) return 0;
@@ -375,6 +514,13 @@ int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, ui
   if (!n) return 0;
   DISPATCH_RB(rb, (k_scatter<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
                                                                        (uint4*)mid)));
+  return 1;
+}
+int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
+                         uint32_t stride, uint32_t* err_flags, cudaStream_t s) {
+  if (!n) return 0;
+  DISPATCH_RB(rb, (k_scatter_fixed<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
+                                                                             (uint4*)mid, stride, err_flags)));
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,

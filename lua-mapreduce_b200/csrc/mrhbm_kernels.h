@@ -53,9 +53,23 @@ struct ShuffleBuffers {
   uint32_t nseg;
   const uint32_t* seg_off[8];
   uint64_t seg_base[8];
+  // Optimistic single-pass layout (no histogram pass): bin b owns the fixed slots
+  // [b*stride, (b+1)*stride) of mid / out and its fill level is its scatter cursor.
+  uint32_t stride;     // 0 = exact layout through bin_off
+  uint32_t ctr_shift;  // cursor[b << ctr_shift]
 };
+MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
+  return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[bin];
+}
+MRHBM_HD inline uint32_t bin_count(const ShuffleBuffers& b, uint32_t bin) {
+  if (b.stride) {
+    uint32_t c = b.cursor[(size_t)bin << b.ctr_shift];
+    return c < b.stride ? c : b.stride;
+  }
+  return b.bin_off[bin + 1] - b.bin_off[bin];
+}
 enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3 };
-enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2 };
+enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2, ERRF_CAPACITY = 4 };
 
 // every launcher returns the number of kernels it launched
 int launch_gen_u64(void* dst, uint64_t seed, uint64_t start, uint64_t n, cudaStream_t s);
@@ -68,6 +82,12 @@ int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* 
                   uint32_t* out_dense, uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total,
                   uint32_t shift, cudaStream_t s);
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
+                   cudaStream_t s);
+// optimistic variant: fixed `stride` slots per bin, cursors start at 0, a full bin sets ERRF_CAPACITY
+int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
+                         uint32_t stride, uint32_t* err_flags, cudaStream_t s);
+// map-side combine of one committed range into out (appends; *out_count is the running total)
+int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned long long* out_count, int sm_count,
                    cudaStream_t s);
 // tot[b] = sum over s < world of all[s * stride + base + b], b < n
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,

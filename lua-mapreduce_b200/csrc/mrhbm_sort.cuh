@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
     uint32_t bin = s_bin;
     __syncthreads();
     if (bin >= B) break;
-    uint32_t off = b.bin_off[bin], cnt = b.bin_off[bin + 1] - off;
+    uint64_t off = bin_start(b, bin);
+    uint32_t cnt = bin_count(b, bin);
     if (cnt > cap) continue;  // k_big_bins
     if (cnt == 0) {
       if (threadIdx.x == 0) b.ucount[bin] = 0;
@@ -388,12 +389,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
     ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
     // gather the bin's segments (one per source rank after the all-to-all; one on a single GPU)
     uint32_t filled = 0;
-    for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
-      uint32_t so = b.seg_off[sgm][bin], sc = b.seg_off[sgm][bin + 1] - so;
-      const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * Rec<RB>::kVec;
-      for (uint32_t v = threadIdx.x; v < sc * Rec<RB>::kVec; v += blockDim.x)
-        sm.rec[filled * Rec<RB>::kVec + v] = ldg_stream(src + v);
-      filled += sc;
+    if (b.stride) {
+      const uint4* src = (const uint4*)b.src + off * Rec<RB>::kVec;
+      for (uint32_t v = threadIdx.x; v < cnt * Rec<RB>::kVec; v += blockDim.x) sm.rec[v] = ldg_stream(src + v);
+    } else {
+      for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
+        uint32_t so = b.seg_off[sgm][bin], sc = b.seg_off[sgm][bin + 1] - so;
+        const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * Rec<RB>::kVec;
+        for (uint32_t v = threadIdx.x; v < sc * Rec<RB>::kVec; v += blockDim.x)
+          sm.rec[filled * Rec<RB>::kVec + v] = ldg_stream(src + v);
+        filled += sc;
+      }
     }
     __syncthreads();
     uint32_t g = process_loaded<RB, MODE_FINAL>(sm, cnt, out);

@@ -13,7 +13,7 @@ from . import build as _build
 KEY_U64, KEY_STR = 0, 1
 PART_FNV_LUA, PART_MULHASH, PART_WORDHASH = 0, 1, 2
 RED_SUM = 0
-F_FORCE_RUNS, F_SMALL_BINS = 1, 2
+F_FORCE_RUNS, F_SMALL_BINS, F_NO_OPTIMISTIC = 1, 2, 4
 E_NODEVICE = -8
 UNIQUE_ID_BYTES = 128
 

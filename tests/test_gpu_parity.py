@@ -48,10 +48,11 @@ def check_vs_oracle_u64(ctx, keys, vals, P, partitioner=O.PART_MULHASH):
     assert cin[:3] == cout[:3] and cin[3] == keys.size and cout[3] == ok.size and cout[4:] == [0, 0]
 
 
+@pytest.mark.parametrize("flags", [0, mrhbm.F_NO_OPTIMISTIC])  # single-pass and two-pass partition layouts
 @pytest.mark.parametrize("n,P", [(1, 1), (37, 4), (5000, 16), (200_000, 16), (1_000_000, 1024)])
-def test_u64_uniform_vs_oracle(n, P):
+def test_u64_uniform_vs_oracle(n, P, flags):
     keys, vals = O.gen_u64(SEED, 0, n)
-    with mrhbm.Ctx(mrhbm.KEY_U64, P) as ctx:
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, flags=flags) as ctx:
         m = ctx.map_begin("m1")
         m.emit_batch(u64_records(keys, vals))
         m.commit()
@@ -99,7 +100,7 @@ def test_u64_clustered_keys_fall_back_to_runs():
         m.emit_batch(u64_records(keys, vals))
         m.commit()
         ctx.shuffle()
-        assert ctx.stats()["attempts"] == 2 and ctx.result_info().sorted == 0
+        assert ctx.stats()["attempts"] >= 2 and ctx.result_info().sorted == 0
         check_vs_oracle_u64(ctx, keys, vals, P)
 
 
@@ -248,6 +249,20 @@ def test_commit_replaces_abort_discards_and_empty_shuffle():
         assert ctx.partitions() == []
 
 
+def test_second_shuffle_after_overflow_skips_the_optimistic_layout():
+    keys = np.arange(200_000, dtype=np.uint64)
+    vals = np.ones(keys.size, dtype=np.uint32)
+    with mrhbm.Ctx(mrhbm.KEY_U64, 4) as ctx:
+        for it in range(2):  # "loop" iterations of one task (server.lua:386-404)
+            ctx.reset()
+            m = ctx.map_begin("seq")
+            m.emit_batch(u64_records(keys, vals))
+            m.commit()
+            ctx.shuffle()
+            assert ctx.stats()["attempts"] == (2 if it == 0 else 1)
+            check_vs_oracle_u64(ctx, keys, vals, 4)
+
+
 def test_properties_at_10_pow_7():
     """size-independent parity: sum linearity, strict ascending order, partition membership"""
     n, P = 10_000_000, 1024
@@ -261,3 +276,34 @@ def test_properties_at_10_pow_7():
         keys, vals = O.gen_u64(SEED, 0, n)
         assert cout[3] == np.unique(keys).size and cin[2] == int(vals.astype(np.uint64).sum())
         assert ctx.result_info().sorted == 1
+
+
+@pytest.mark.parametrize("kind", ["zipf", "u64dup"])
+def test_map_side_combiner_keeps_the_result(kind):
+    """combinerfn == reducefn (job.lua:92-96,198-202): the map-side combine changes nothing"""
+    n, P = 1_500_000, 15
+    if kind == "zipf":
+        table = synth.zipf_table(1 << 16)
+        recs = O.gen_zipf_rec32(SEED, 0, n, table).view(mrhbm.record_dtype(mrhbm.KEY_STR, 27)).reshape(-1)
+        with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, combiner=True) as ctx:
+            m = ctx.map_begin(1)
+            m.gen_zipf(SEED, 0, n, table)
+            m.commit()
+            ctx.shuffle()
+            st = ctx.stats()
+            info = ctx.result_info()
+            assert info.pairs_in == n and info.pairs_recv < n // 2  # hot keys collapsed before partitioning
+            assert st["ms_combine"] > 0
+            check_vs_oracle_str(ctx, recs, P, O.PART_FNV_LUA)
+    else:
+        rng = np.random.default_rng(9)
+        keys = O.gen_u64(SEED, 0, 5000)[0][rng.integers(0, 5000, n)]
+        vals = rng.integers(0, 70000, n).astype(np.uint32)  # values > 0xffff and 0 bypass the table
+        vals[::11] = 0
+        with mrhbm.Ctx(mrhbm.KEY_U64, P, combiner=True) as ctx:
+            m = ctx.map_begin(1)
+            m.emit_batch(u64_records(keys, vals))
+            m.commit()
+            ctx.shuffle()
+            assert ctx.result_info().pairs_recv < n
+            check_vs_oracle_u64(ctx, keys, vals, P)
