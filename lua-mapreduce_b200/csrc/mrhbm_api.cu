@@ -580,6 +580,11 @@ int mrhbm_reset(mrhbm_ctx* c) {
 // ---------------------------------------------------------------------------
 namespace {
 
+void set_range_hint(ShuffleBuffers& b, uint32_t S, uint32_t ordered) {
+  b.hint_S = (ordered && S > 1) ? S : 0;
+  b.hint_q = S > 1 ? (uint64_t)(((unsigned __int128)1 << 64) / S) : 0;
+}
+
 BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered) {
   BinParams bp{};
   bp.P = c->cfg.num_partitions;
@@ -750,6 +755,7 @@ int shuffle_single(mrhbm_ctx* c) {
     c->sb.nseg = 1;
     c->sb.stride = c->cap;
     c->sb.ctr_shift = c->ctr_shift;
+    set_range_hint(c->sb, S, ordered);
     st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
@@ -814,6 +820,7 @@ int shuffle_single(mrhbm_ctx* c) {
       c->sb.nseg = 1;
       c->sb.seg_off[0] = c->sb.bin_off;
       c->sb.seg_base[0] = 0;
+      set_range_hint(c->sb, S, ordered);
       st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
       CU(c, cudaEventRecord(c->ev[EV_SORT], s));
       CU(c, cudaGetLastError());
@@ -974,6 +981,7 @@ int shuffle_multi(mrhbm_ctx* c) {
     v.src = c->recvbuf;
     v.mid = nbig ? c->bigbuf : c->recvbuf;
     v.nseg = (uint32_t)G;
+    set_range_hint(v, S, ordered);
     for (int r = 0; r < G; r++) {
       v.seg_off[r] = c->d_segoff + (uint64_t)r * (Bl + 1);
       v.seg_base[r] = recv_off[r] / c->rb;

@@ -57,6 +57,10 @@ struct ShuffleBuffers {
   // [b*stride, (b+1)*stride) of mid / out and its fill level is its scatter cursor.
   uint32_t stride;     // 0 = exact layout through bin_off
   uint32_t ctr_shift;  // cursor[b << ctr_shift]
+  // key-ordered sub-bins of u64 keys (sub = mulhi(key, S)): lets the sort kernel skip the
+  // min/max pass.  hint_S = 0: unknown.
+  uint32_t hint_S;
+  uint64_t hint_q;     // floor(2^64 / S)
 };
 MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
   return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[bin];

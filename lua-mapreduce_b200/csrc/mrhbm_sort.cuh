@@ -107,6 +107,22 @@ __device__ __forceinline__ uint32_t block_exscan(T_* a, uint32_t n, uint32_t* /*
   return total;
 }
 
+// coalesced copy of nvec uint4 from global to shared memory, four independent loads in
+// flight per thread (the load is latency bound otherwise)
+__device__ __forceinline__ void load_bin(uint4* dst, const uint4* __restrict__ src, uint32_t nvec) {
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  uint32_t v = tid;
+  for (; v + 3 * T < nvec; v += 4 * T) {
+    uint4 a = ldg_stream(src + v), b = ldg_stream(src + v + T), c = ldg_stream(src + v + 2 * T),
+          d = ldg_stream(src + v + 3 * T);
+    dst[v] = a;
+    dst[v + T] = b;
+    dst[v + 2 * T] = c;
+    dst[v + 3 * T] = d;
+  }
+  for (; v < nvec; v += T) dst[v] = ldg_stream(src + v);
+}
+
 enum { MODE_FINAL = 0, MODE_PARTIAL = 1 };
 struct ChunkOut {
   void* keys;      // FINAL: key slots; PARTIAL: AoS records
@@ -141,13 +157,12 @@ __device__ __forceinline__ void write_group(const ChunkOut& out, uint64_t o, con
   }
 }
 
-// Shared epilogue: the bin is in ascending key order (position j holds record at(j)).  When
-// !HAVE_FLAGS, mark the first record of every key; then number the groups, let each head sum
-// its run and write it out.  flags: CAP u16, slot: CAP u32 (slot[j] = flags[j] on entry when
-// HAVE_FLAGS).
+// Shared epilogue: the bin is in ascending key order (position j holds record at(j)).  hs holds
+// one u16 per position: on entry (HAVE_FLAGS) 1 for the first record of every key, else it is
+// computed here.  An in-place scan turns the flags into group numbers (a position is a head iff
+// the next number differs); each head sums its run and writes the group.
 template <int RB, int MODE, bool HAVE_FLAGS, typename At>
-__device__ __forceinline__ uint32_t reduce_sorted(At at, uint32_t cnt, uint16_t* flags, uint32_t* slot,
-                                                  uint32_t* scratch33, const ChunkOut& out) {
+__device__ __forceinline__ uint32_t reduce_sorted(At at, uint32_t cnt, uint16_t* hs, const ChunkOut& out) {
   constexpr int CAP = kCapBytes / RB;
   constexpr int PER = (CAP + kSortThreads - 1) / kSortThreads;
   const uint32_t tid = threadIdx.x, T = blockDim.x;
@@ -155,18 +170,22 @@ __device__ __forceinline__ uint32_t reduce_sorted(At at, uint32_t cnt, uint16_t*
     for (uint32_t j = tid; j < cnt; j += T) {
       uint32_t head = 1;
       if (j > 0) head = !key_eq<RB>(at(j), at(j - 1));
-      flags[j] = (uint16_t)head;
-      slot[j] = head;
+      hs[j] = (uint16_t)head;
     }
     __syncthreads();
   }
-  uint32_t groups = block_exscan<PER>(slot, cnt, scratch33);
+  const uint32_t groups = block_exscan<PER>(hs, cnt, nullptr);
   for (uint32_t j = tid; j < cnt; j += T) {
-    if (!flags[j]) continue;
+    uint32_t g = hs[j], gn = j + 1 < cnt ? hs[j + 1] : groups;
+    if (gn == g) continue;  // not a head
     const uint32_t* r = at(j);
     uint64_t s = rec_value<RB>(r);
-    for (uint32_t k = j + 1; k < cnt && !flags[k]; k++) s += rec_value<RB>(at(k));
-    write_group<RB, MODE>(out, out.base + slot[j], r, s);
+    for (uint32_t k = j + 1; k < cnt; k++) {  // the run: positions that do not start a group
+      uint32_t a = hs[k], an = k + 1 < cnt ? hs[k + 1] : groups;
+      if (an != a) break;
+      s += rec_value<RB>(at(k));
+    }
+    write_group<RB, MODE>(out, out.base + g, r, s);
   }
   __syncthreads();
   return groups;
@@ -233,29 +252,29 @@ __device__ uint32_t counting_path(const SortSmem& sm, uint32_t cnt, uint64_t pmi
     uint32_t b = bucket_of(r);
     uint32_t s = bcnt[b], e = (b + 1 < NB) ? bcnt[b + 1] : cnt;
     uint32_t rank = 0, head = 1;
-    for (uint32_t m = s; m < e; m++) {
-      if (m == j) continue;
-      int c = key_cmp<RB>(rec2w + m * R::kWords, r);
-      bool eq_before = (c == 0 && m < j);
-      rank += (c < 0) || eq_before;
-      if (eq_before) head = 0;  // an equal key sits earlier: not the first of its group
+    if (e - s > 1) {  // most buckets hold one record
+      for (uint32_t m = s; m < e; m++) {
+        if (m == j) continue;
+        int c = key_cmp<RB>(rec2w + m * R::kWords, r);
+        bool eq_before = (c == 0 && m < j);
+        rank += (c < 0) || eq_before;
+        if (eq_before) head = 0;  // an equal key sits earlier: not the first of its group
+      }
     }
 #pragma unroll
     for (int v = 0; v < R::kVec; v++) sm.rec[(s + rank) * R::kVec + v] = sm.rec2[j * R::kVec + v];
     heads[s + rank] = (uint16_t)head;
   }
   __syncthreads();
-  // bucket offsets are dead: reuse the words as group slots (slot[j] = head flag of position j)
-  for (uint32_t j = tid; j < CAP; j += T) bcnt[j] = j < cnt ? (uint32_t)heads[j] : 0u;
-  __syncthreads();
   auto at = [&](uint32_t j) -> const uint32_t* { return recw + j * R::kWords; };
-  return reduce_sorted<RB, MODE, true>(at, cnt, heads, bcnt, (uint32_t*)sm.red, out);
+  return reduce_sorted<RB, MODE, true>(at, cnt, heads, out);
 }
 
 // Sorts cnt (<= cap) records of one bin by key, sums the values of equal keys and writes
 // the groups in ascending key order.  Returns the number of groups.
 template <int RB, int MODE>
-__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out);
+__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out, bool have_range = false,
+                                   uint64_t lo = 0, uint64_t hi = 0);
 
 template <int RB, int MODE, bool NC>
 __device__ uint32_t process_chunk(const SortSmem& sm, const uint4* __restrict__ src, uint32_t cnt,
@@ -269,11 +288,16 @@ __device__ uint32_t process_chunk(const SortSmem& sm, const uint4* __restrict__ 
 
 // the bin's cnt records are in sm.rec (all threads have passed a barrier after the load)
 template <int RB, int MODE>
-__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out) {
+__device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const ChunkOut& out, bool have_range,
+                                   uint64_t lo, uint64_t hi) {
   using R = Rec<RB>;
   constexpr uint32_t CAP = kCapBytes / RB;
   const uint32_t tid = threadIdx.x, T = blockDim.x;
   const uint32_t* recw = (const uint32_t*)sm.rec;
+  if (have_range) {  // key-ordered sub-bin: the prefix range is known from the bin id
+    uint32_t g = counting_path<RB, MODE>(sm, cnt, lo, hi, out);
+    if (g != kNoFastPath) return g;
+  }
   // range of the 64-bit key prefix
   uint64_t pmin = ~0ull, pmax = 0;
   for (uint32_t i = tid; i < cnt; i += T) {
@@ -365,7 +389,7 @@ __device__ uint32_t process_loaded(const SortSmem& sm, uint32_t cnt, const Chunk
   }
   const uint16_t* pp = perm;
   auto at = [&](uint32_t j) -> const uint32_t* { return recw + (uint32_t)pp[j] * R::kWords; };
-  return reduce_sorted<RB, MODE, false>(at, cnt, other, (uint32_t*)comp, (uint32_t*)sm.red, out);
+  return reduce_sorted<RB, MODE, false>(at, cnt, other, out);
 }
 
 template <int RB>
@@ -391,18 +415,25 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
     uint32_t filled = 0;
     if (b.stride) {
       const uint4* src = (const uint4*)b.src + off * Rec<RB>::kVec;
-      for (uint32_t v = threadIdx.x; v < cnt * Rec<RB>::kVec; v += blockDim.x) sm.rec[v] = ldg_stream(src + v);
+      load_bin(sm.rec, src, cnt * Rec<RB>::kVec);
     } else {
       for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
         uint32_t so = b.seg_off[sgm][bin], sc = b.seg_off[sgm][bin + 1] - so;
         const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * Rec<RB>::kVec;
-        for (uint32_t v = threadIdx.x; v < sc * Rec<RB>::kVec; v += blockDim.x)
-          sm.rec[filled * Rec<RB>::kVec + v] = ldg_stream(src + v);
+        load_bin(sm.rec + filled * Rec<RB>::kVec, src, sc * Rec<RB>::kVec);
         filled += sc;
       }
     }
     __syncthreads();
-    uint32_t g = process_loaded<RB, MODE_FINAL>(sm, cnt, out);
+    bool have_range = false;
+    uint64_t lo = 0, hi = 0;
+    if (Rec<RB>::kU64 && b.hint_S > 1) {  // sub = mulhi(key, S): keys of sub-bin `sub` lie in [sub*q, (sub+1)*(q+1)]
+      uint32_t sub = bin % b.hint_S;
+      have_range = true;
+      lo = (uint64_t)sub * b.hint_q;
+      hi = sub + 1 == b.hint_S ? ~0ull : (uint64_t)(sub + 1) * (b.hint_q + 1);
+    }
+    uint32_t g = process_loaded<RB, MODE_FINAL>(sm, cnt, out, have_range, lo, hi);
     if (threadIdx.x == 0) b.ucount[bin] = g;
   }
 }
