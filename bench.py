@@ -229,8 +229,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        for _ in range(3):  # let nvidia-smi attach before the timed region
-            ctx.shuffle()
+    for _ in range(3):  # every rank (the shuffle is collective): lets nvidia-smi attach before the timed region
+        ctx.shuffle()
     barrier()
     t0 = time.perf_counter()
     agg = {}
@@ -330,7 +330,7 @@ def main():
             e2e_t = float(t.item())
         e2e = {"value": world * n / e2e_t, "unit": UNIT, "h2d_bytes_per_step": n * rb,
                "d2h_bytes_per_step": int(g2) * (rb - 4 + 8 if kind == mrhbm.KEY_STR else 16) + 8 * (P + 1),
-               "ms_per_step": 1e3 * e2e_t, "steps": a.e2e_steps, "groups_match": bool(g2 == groups)}
+               "ms_per_step": 1e3 * e2e_t, "steps": a.e2e_steps, "groups_match": bool(g2 == g_local)}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

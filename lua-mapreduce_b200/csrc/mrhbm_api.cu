@@ -926,12 +926,11 @@ int shuffle_multi(mrhbm_ctx* c) {
       rc = comm_allgather_u32(c->comm, c->d_hd, c->d_hall, B, s, &c->err);
       if (rc) return rc;
       // receive layout: per owned bin the total and the per-source offsets
-      st.launches += launch_sum_src(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_tot, s);
+      st.launches += launch_sum_src(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_tot, c->cap,
+                                    c->sb.counters + CNT_GBIG, s);
       st.launches += launch_exscan(c->d_tot, (uint32_t)Bl, c->d_outoff, nullptr, nullptr, c->cap, c->sb.big_list,
                                    c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, 0, s);
-      for (int r = 0; r < G; r++)
-        st.launches += launch_exscan(c->d_hall + (uint64_t)r * B + bin_base, (uint32_t)Bl, c->d_segoff + (uint64_t)r * (Bl + 1),
-                                     nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small + 32 + r, 0, s);
+      st.launches += launch_exscan_rows(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_segoff, c->d_small + 32, s);
       for (int d = 0; d <= G; d++)
         CU(c, cudaMemcpyAsync(c->h_small + 48 + d, c->sb.bin_off + (uint64_t)c->pbase[d] * S, 4, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
@@ -943,10 +942,9 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaStreamSynchronize(s));
       nbig = c->h_counters[CNT_NBIG];
       total_recv = c->h_counters[CNT_TOTAL];
-      rc = gather_u32(c, (nbig && ordered && S > 1) ? 1u : 0u, all);  // collective decision
-      if (rc) return rc;
-      bool redo = false;
-      for (int r = 0; r < G; r++) redo |= all[r] != 0;
+      // every rank counted the oversized bins of ALL ranks from the same all-gathered counts:
+      // the decision is identical everywhere without another collective
+      bool redo = c->h_counters[CNT_GBIG] && ordered && S > 1;
       if (redo) {
         ordered = 0;
         continue;

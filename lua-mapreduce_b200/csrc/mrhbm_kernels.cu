@@ -190,12 +190,11 @@ __global__ void __launch_bounds__(256) k_scatter_fixed(const uint4* __restrict__
 
 // single-CTA exclusive scan (B <= a few million): out_excl[0..n], optional copy into
 // out_copy (scatter cursors), optional list of entries larger than cap
-__global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in, uint32_t n,
-                                                 uint32_t* __restrict__ out_excl,
-                                                 uint32_t* __restrict__ out_copy,
-                                                 uint32_t* __restrict__ out_dense, uint32_t cap,
-                                                 uint32_t* __restrict__ big_list, uint32_t* nbig,
-                                                 uint32_t* total, uint32_t shift) {
+__device__ __forceinline__ void exscan_body(const uint32_t* __restrict__ in, uint32_t n,
+                                            uint32_t* __restrict__ out_excl, uint32_t* __restrict__ out_copy,
+                                            uint32_t* __restrict__ out_dense, uint32_t cap,
+                                            uint32_t* __restrict__ big_list, uint32_t* nbig, uint32_t* total,
+                                            uint32_t shift) {
   __shared__ uint32_t warp_sums[32];
   const uint32_t T = blockDim.x, tid = threadIdx.x;
   uint32_t per = (n + T - 1) / T;
@@ -233,6 +232,21 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
     out_excl[n] = run;
     if (total) *total = run;
   }
+}
+__global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in, uint32_t n,
+                                                 uint32_t* __restrict__ out_excl,
+                                                 uint32_t* __restrict__ out_copy,
+                                                 uint32_t* __restrict__ out_dense, uint32_t cap,
+                                                 uint32_t* __restrict__ big_list, uint32_t* nbig,
+                                                 uint32_t* total, uint32_t shift) {
+  exscan_body(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
+}
+// one CTA per source rank: exclusive scan of that rank's counts for this rank's bins
+__global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict__ all, uint32_t stride, uint32_t base,
+                                                      uint32_t n, uint32_t* __restrict__ out, uint32_t* __restrict__ totals) {
+  uint32_t r = blockIdx.x;
+  exscan_body(all + (size_t)r * stride + base, n, out + (size_t)r * (n + 1), nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
+              totals + r, 0);
 }
 
 // ============================================================================
@@ -324,12 +338,15 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   }
 }
 
+// global per-bin totals from the all-gathered counts: this rank's bins go to tot[], and every
+// rank counts the bins (of ALL ranks) above cap, so that all ranks take the same decision
 __global__ void k_sum_src(const uint32_t* __restrict__ all, uint32_t world, uint32_t stride, uint32_t base,
-                          uint32_t n, uint32_t* __restrict__ tot) {
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+                          uint32_t n, uint32_t* __restrict__ tot, uint32_t cap, uint32_t* __restrict__ nover) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < stride; b += gridDim.x * blockDim.x) {
     uint32_t t = 0;
-    for (uint32_t s = 0; s < world; s++) t += all[(size_t)s * stride + base + b];
-    tot[b] = t;
+    for (uint32_t s = 0; s < world; s++) t += all[(size_t)s * stride + b];
+    if (b >= base && b < base + n) tot[b - base] = t;
+    if (t > cap) atomicAdd(nover, 1u);
   }
 }
 
@@ -504,9 +521,15 @@ int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned lon
   return 1;
 }
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
-                   uint32_t* tot, cudaStream_t s) {
-  if (!n) return 0;
-  k_sum_src<<<(n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024, 256, 0, s>>>(all, world, stride, base, n, tot);
+                   uint32_t* tot, uint32_t cap, uint32_t* nover, cudaStream_t s) {
+  if (!stride) return 0;
+  k_sum_src<<<(stride + 255) / 256 < 1024 ? (stride + 255) / 256 : 1024, 256, 0, s>>>(all, world, stride, base, n, tot,
+                                                                                      cap, nover);
+  return 1;
+}
+int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n, uint32_t* out,
+                       uint32_t* totals, cudaStream_t s) {
+  k_exscan_rows<<<world, 1024, 0, s>>>(all, stride, base, n, out, totals);
   return 1;
 }
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,

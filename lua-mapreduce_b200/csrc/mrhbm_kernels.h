@@ -72,7 +72,7 @@ MRHBM_HD inline uint32_t bin_count(const ShuffleBuffers& b, uint32_t bin) {
   }
   return b.bin_off[bin + 1] - b.bin_off[bin];
 }
-enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3 };
+enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3, CNT_GBIG = 4 };
 enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2, ERRF_CAPACITY = 4 };
 
 // every launcher returns the number of kernels it launched
@@ -93,9 +93,13 @@ int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& 
 // map-side combine of one committed range into out (appends; *out_count is the running total)
 int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned long long* out_count, int sm_count,
                    cudaStream_t s);
-// tot[b] = sum over s < world of all[s * stride + base + b], b < n
+// tot[b] = sum over s < world of all[s * stride + base + b], b < n; *nover += bins (of all `stride`
+// bins) whose global total exceeds cap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
-                   uint32_t* tot, cudaStream_t s);
+                   uint32_t* tot, uint32_t cap, uint32_t* nover, cudaStream_t s);
+// row r < world: out[r*(n+1) ..] = exclusive scan of all[r*stride + base ..+n), totals[r] = its sum
+int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
+                       uint32_t* out, uint32_t* totals, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);
