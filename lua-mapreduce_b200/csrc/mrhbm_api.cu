@@ -55,6 +55,7 @@ struct mrhbm_ctx {
   bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
   void* comb = nullptr;  // map-side combined pairs
+  uint32_t *d_hll = nullptr, *h_hll = nullptr;  // HyperLogLog registers of the combined stream (8 ranks x kHllRegs on the host)
   uint64_t comb_cap = 0;
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
@@ -345,6 +346,8 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaHostAlloc((void**)&c->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
   c->Pl = cfg->num_partitions;
   for (int r = 1; r <= 8; r++) c->pbase[r] = cfg->num_partitions;
+  CU(c, cudaMalloc((void**)&c->d_hll, 8 * kHllRegs * sizeof(uint32_t)));
+  CU(c, cudaHostAlloc((void**)&c->h_hll, 8 * kHllRegs * sizeof(uint32_t), cudaHostAllocDefault));
   c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
   if (const char* e = getenv("MRHBM_CTR_SHIFT")) c->ctr_shift = (uint32_t)std::min(7, std::max(0, atoi(e)));  // tuning hook
   if (cfg->reserve_pairs) {
@@ -363,12 +366,14 @@ void mrhbm_destroy(mrhbm_ctx* c) {
   void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
-                   c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb};
+                   c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
+                   c->d_hll};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_acc) cudaFreeHost(c->h_acc);
   if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_hll) cudaFreeHost(c->h_hll);
   for (int i = 0; i < EV_N; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -585,8 +590,9 @@ void set_range_hint(ShuffleBuffers& b, uint32_t S, uint32_t ordered) {
   b.hint_q = S > 1 ? (uint64_t)(((unsigned __int128)1 << 64) / S) : 0;
 }
 
-BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered) {
+BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered, uint32_t rep_shift = 0) {
   BinParams bp{};
+  bp.rep_shift = rep_shift;
   bp.P = c->cfg.num_partitions;
   bp.S = S;
   bp.partitioner = c->cfg.partitioner;
@@ -668,10 +674,39 @@ int ensure_out(mrhbm_ctx* c, uint64_t need) {
 struct Src {
   const char* p;
   uint64_t n;
+  // segmented (combiner output): nseg regions of seg_stride records, fill levels in d_seg_counts
+  const uint32_t* d_seg_counts = nullptr;
+  uint64_t seg_stride = 0;
+  uint32_t nseg = 0;
 };
+inline BinParams with_src(BinParams bp, const Src& sr) {
+  bp.seg_counts = sr.d_seg_counts;
+  bp.seg_stride = sr.seg_stride;
+  bp.nseg = sr.nseg;
+  return bp;
+}
 // The pairs the shuffle partitions: the committed pool ranges, or -- with a combiner declared
 // (job.lua:92-96,198-202) -- their map-side combined image.  EV_START .. EV_COMBINE.
-int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_stats& st) {
+// HyperLogLog estimate from max-merged registers of `ranks` sketches
+double hll_estimate(const uint32_t* regs, int ranks) {
+  const double m = (double)kHllRegs;
+  double sum = 0;
+  uint32_t zeros = 0;
+  for (uint32_t i = 0; i < kHllRegs; i++) {
+    uint32_t r = 0;
+    for (int k = 0; k < ranks; k++) r = std::max(r, regs[(size_t)k * kHllRegs + i]);
+    sum += std::ldexp(1.0, -(int)r);
+    zeros += r == 0;
+  }
+  double e = 0.7213 / (1.0 + 1.079 / m) * m * m / sum;
+  if (e < 2.5 * m && zeros) e = m * std::log(m / zeros);  // small-range correction
+  return e;
+}
+
+// *distinct: < 0 when no combine ran, else the estimated number of distinct keys in the
+// combined stream of the whole job (all ranks)
+int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_stats& st, double* distinct) {
+  *distinct = -1.0;
   srcs.clear();
   uint64_t n = 0;
   for (auto& r : live_ranges(c)) {
@@ -679,20 +714,54 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
     n += r.second;
   }
   *N = n;
-  if (!c->cfg.combiner || n < (1u << 20)) return 0;
-  int rc = ensure_records(c, &c->comb, &c->comb_cap, n);
+  // collective in a multi-GPU job: every rank must take the same branch
+  uint32_t all[8];
+  int rc = gather_u32(c, (c->cfg.combiner && n >= (1u << 20)) ? 1u : 0u, all);
   if (rc) return rc;
-  unsigned long long* cnt = (unsigned long long*)c->d_acc;
-  CU(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-  for (auto& sr : srcs) st.launches += launch_combine(c->rb, sr.p, sr.n, c->comb, cnt, c->sm_count, c->stream);
+  bool any = false;
+  for (int r = 0; r < c->world; r++) any |= all[r] != 0;
+  if (!c->cfg.combiner || !any) return 0;
+  // every combiner CTA owns one output region (no global append counter): size it for the worst case
+  const uint32_t nseg = (uint32_t)c->sm_count;
+  uint64_t region = 0;
+  for (auto& sr : srcs) region += sr.n / nseg + combine_region_slack(c->rb);
+  if (region >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "combiner region too large");
+  rc = ensure_records(c, &c->comb, &c->comb_cap, region * nseg);
+  if (rc) return rc;
+  uint32_t* segc = c->d_hll + kHllRegs;  // [nseg] fill levels, after the sketch registers
+  CU(c, cudaMemsetAsync(c->d_hll, 0, (kHllRegs + nseg) * sizeof(uint32_t), c->stream));
+  for (auto& sr : srcs)
+    st.launches += launch_combine(c->rb, sr.p, sr.n, c->comb, (uint32_t)region, segc, c->d_hll, c->sm_count, c->stream);
   CU(c, cudaGetLastError());
-  CU(c, cudaMemcpyAsync(c->h_acc, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  int ranks = 1;
+  CU(c, cudaMemcpyAsync(c->h_hll, c->d_hll, (kHllRegs + nseg) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  uint64_t n2 = c->h_acc[0];
+  double est = hll_estimate(c->h_hll, ranks);
+  if (c->world > 1) {  // upper bound: sum of the per-rank estimates (exact merge would need an all-reduce max)
+    rc = gather_u32(c, (uint32_t)std::min(est, 4.0e9), all);
+    if (rc) return rc;
+    est = 0;
+    for (int r = 0; r < c->world; r++) est += all[r];
+  }
+  *distinct = est;
+  uint64_t n2 = 0;
+  for (uint32_t i = 0; i < nseg; i++) n2 += c->h_hll[kHllRegs + i];
   srcs.clear();
-  srcs.push_back(Src{(const char*)c->comb, n2});
+  Src out{(const char*)c->comb, n2};
+  out.d_seg_counts = segc;
+  out.seg_stride = region;
+  out.nseg = nseg;
+  srcs.push_back(out);
   *N = n2;
   return 0;
+}
+
+// sub-bins per partition when bins are sized by distinct keys (aggregation pass)
+uint32_t pick_sub_bins_agg(const mrhbm_ctx* c, double distinct) {
+  double keys_per_bin = std::min<double>(agg_table_entries(c->rb) * 0.4, c->cap * 0.5);
+  double bins = std::ceil(distinct * 1.15 / keys_per_bin);
+  double P = c->cfg.num_partitions;
+  return (uint32_t)std::max(1.0, std::ceil(bins / P));
 }
 
 uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
@@ -727,15 +796,17 @@ int shuffle_single(mrhbm_ctx* c) {
   uint64_t B = 0, N = 0;
   std::vector<Src> live;
   CU(c, cudaEventRecord(c->ev[EV_START], s));
-  rc = collect_sources(c, live, &N, st);
+  double distinct = -1;
+  rc = collect_sources(c, live, &N, st, &distinct);
   if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[EV_CSTART], s));
-  uint32_t S = pick_sub_bins(c, N);
-  bool skip_ordered = c->no_ordered;
+  const bool agg = distinct >= 0;  // duplicate-heavy: aggregate per bin, bins sized by distinct keys
+  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, N);
+  bool skip_ordered = c->no_ordered || agg;
   // ---- optimistic single pass: no histogram.  Hash-balanced bins almost never exceed their
   // capacity (mean = cap - 6 sigma); the cursor claim doubles as the count.  A full bin sets
   // ERRF_CAPACITY and the exact two-pass layout below takes over (and stays, for this ctx).
-  if (!c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && N > 0 && (uint64_t)P * S < (1ull << 31)) {
+  if (!agg && !c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && N > 0 && (uint64_t)P * S < (1ull << 31)) {
     B = (uint64_t)P * S;
     ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !skip_ordered) || S == 1);
     rc = ensure_buffers(c, B, B * c->cap);
@@ -754,6 +825,7 @@ int shuffle_single(mrhbm_ctx* c) {
     c->sb.src = c->sb.mid;
     c->sb.nseg = 1;
     c->sb.stride = c->cap;
+    c->sb.rep_shift = 0;
     c->sb.ctr_shift = c->ctr_shift;
     set_range_hint(c->sb, S, ordered);
     st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
@@ -796,36 +868,43 @@ int shuffle_single(mrhbm_ctx* c) {
   for (int widen = 0;; widen++) {
     B = (uint64_t)P * S;
     if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
-    rc = ensure_buffers(c, B, N);
+    // few, heavily hit bins (aggregation pass): spread every bin's counter over 2^rep copies
+    uint32_t rep = 0;
+    if (agg)
+      while (rep < 6 && (B << (rep + 1)) <= 65536) rep++;
+    const uint64_t Bv = B << rep;
+    rc = ensure_buffers(c, Bv, N);
     if (rc) return rc;
     ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !skip_ordered) || S == 1);
     c->sb.stride = 0;
     for (int attempt = 0;; attempt++) {
       st.attempts++;
-      BinParams bp = make_bp(c, S, ordered);
-      CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+      BinParams bp = make_bp(c, S, ordered, rep);
+      CU(c, cudaMemsetAsync(c->sb.hist, 0, (Bv << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, with_src(bp, r), c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
-      st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
+      st.launches += launch_exscan(c->sb.hist, (uint32_t)Bv, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
                                    c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
+      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
       c->sb.src = c->sb.mid;
       c->sb.nseg = 1;
       c->sb.seg_off[0] = c->sb.bin_off;
       c->sb.seg_base[0] = 0;
+      c->sb.rep_shift = rep;
       set_range_hint(c->sb, S, ordered);
-      st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+      st.launches += agg ? launch_agg_bins(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s)
+                         : launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
       CU(c, cudaEventRecord(c->ev[EV_SORT], s));
       CU(c, cudaGetLastError());
       CU(c, cudaEventSynchronize(c->ev[EV_PROBE]));  // overlaps with scatter / sort on the device
-      nbig = c->h_counters[CNT_NBIG];
+      nbig = agg ? 0 : c->h_counters[CNT_NBIG];
       if (nbig && ordered && S > 1) {
         // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
         ordered = 0;
@@ -889,14 +968,16 @@ int shuffle_multi(mrhbm_ctx* c) {
   st.pairs = N_in;
   std::vector<Src> live;
   CU(c, cudaEventRecord(c->ev[EV_START], c->stream));
-  int rc = collect_sources(c, live, &N, st);
+  double distinct = -1;
+  int rc = collect_sources(c, live, &N, st, &distinct);
   if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[EV_CSTART], c->stream));
   rc = gather_u32(c, (uint32_t)N, all);
   if (rc) return rc;
   uint64_t Nglobal = 0;
   for (int r = 0; r < G; r++) Nglobal += all[r];
-  uint32_t S = pick_sub_bins(c, Nglobal);
+  const bool agg = distinct >= 0;
+  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, Nglobal);
   uint32_t nbig = 0, ordered = 1;
   cudaStream_t s = c->stream;
   uint64_t B = 0, Bl = 0, total_recv = 0;
@@ -911,14 +992,14 @@ int shuffle_multi(mrhbm_ctx* c) {
     if (rc) return rc;
     rc = ensure_multi_buffers(c, B, Bl);
     if (rc) return rc;
-    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0) || S == 1);
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !agg) || S == 1);
     for (int attempt = 0;; attempt++) {
       st.attempts++;
       BinParams bp = make_bp(c, S, ordered);
       CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, with_src(bp, r), c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       // send layout (destination-major bins) + dense counts for the all-gather
       st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->d_hd, 0xffffffffu, nullptr,
@@ -936,15 +1017,15 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
+      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaGetLastError());
       CU(c, cudaStreamSynchronize(s));
-      nbig = c->h_counters[CNT_NBIG];
+      nbig = agg ? 0 : c->h_counters[CNT_NBIG];
       total_recv = c->h_counters[CNT_TOTAL];
       // every rank counted the oversized bins of ALL ranks from the same all-gathered counts:
       // the decision is identical everywhere without another collective
-      bool redo = c->h_counters[CNT_GBIG] && ordered && S > 1;
+      bool redo = !agg && c->h_counters[CNT_GBIG] && ordered && S > 1;
       if (redo) {
         ordered = 0;
         continue;
@@ -975,6 +1056,7 @@ int shuffle_multi(mrhbm_ctx* c) {
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     v = c->sb;
     v.stride = 0;
+    v.rep_shift = 0;
     v.bin_off = c->d_outoff;
     v.src = c->recvbuf;
     v.mid = nbig ? c->bigbuf : c->recvbuf;
@@ -984,7 +1066,8 @@ int shuffle_multi(mrhbm_ctx* c) {
       v.seg_off[r] = c->d_segoff + (uint64_t)r * (Bl + 1);
       v.seg_base[r] = recv_off[r] / c->rb;
     }
-    st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
+    st.launches += agg ? launch_agg_bins(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s)
+                       : launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     st.launches += launch_big_bins(c->rb, v, nbig, c->cap, s);
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));

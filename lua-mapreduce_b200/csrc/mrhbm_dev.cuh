@@ -89,20 +89,25 @@ __device__ __forceinline__ uint64_t rec_value(const uint32_t* r) {
 // examples/WordCount/partitionfn.lua:8-16 evaluated exactly as Lua 5.2 does, i.e. in IEEE
 // doubles: h*16777619 reaches ~2^56, so the product is rounded to 53 significant bits
 // (round-to-nearest-even) BEFORE "% 2^32".  Emulated with integers so no FP64 is issued.
+// Only (h * 16777619 rounded to 53 bits) mod 2^32 is needed, and the rounding only touches the
+// low `sh` bits, so everything is computed from the 32-bit halves of the product:
+// sh = bitlen(product) - 53 = bitlen(high word) - 21.
 __host__ __device__ __forceinline__ uint32_t fnv_lua_step(uint32_t h, uint32_t byte) {
-  uint64_t p = (uint64_t)h * 16777619ull;
-  if (p >> 53) {
+  uint32_t lo = h * 16777619u;
 #ifdef __CUDA_ARCH__
-    int sh = 64 - __clzll((long long)p) - 53;
+  uint32_t hi = __umulhi(h, 16777619u);
+  int sh = 11 - __clz((int)hi);  // (32 - clz) - 21
 #else
-    int sh = 64 - __builtin_clzll(p) - 53;
+  uint32_t hi = (uint32_t)(((uint64_t)h * 16777619ull) >> 32);
+  int sh = hi ? 11 - __builtin_clz(hi) : -21;
 #endif
-    uint64_t half = 1ull << (sh - 1), rem = p & ((1ull << sh) - 1);
-    p >>= sh;
-    if (rem > half || (rem == half && (p & 1))) p++;
-    p <<= sh;
+  if (sh > 0) {
+    uint32_t half = 1u << (sh - 1), rem = lo & ((1u << sh) - 1u);
+    uint32_t q = lo >> sh;  // bit 0 of q is bit sh of the product: the ties-to-even parity
+    if (rem > half || (rem == half && (q & 1u))) q++;
+    lo = q << sh;           // a carry out of bit 31 vanishes mod 2^32, as it must
   }
-  return (uint32_t)p ^ byte;
+  return lo ^ byte;
 }
 // h over the key bytes (u64 keys: the 8 big-endian bytes; strings: up to the first NUL)
 template <int RB>
@@ -115,23 +120,24 @@ __device__ __forceinline__ uint32_t fnv_lua_hash(const uint32_t* r) {
       h = fnv_lua_step(h, (w >> (24 - 8 * (i & 3))) & 0xff);
     }
   } else {
-    bool live = true;
 #pragma unroll
     for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
       uint32_t w = r[i];
+      if (w == 0) break;  // keys hold no NUL: a zero word is past the end (short keys leave early)
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         uint32_t b = (w >> (8 * j)) & 0xff;
-        live = live && (b != 0);
-        if (live) h = fnv_lua_step(h, b);
+        if (b == 0) break;
+        h = fnv_lua_step(h, b);
       }
+      if ((w >> 24) == 0) break;
     }
   }
   return h;
 }
 // 64-bit word hash over the little-endian u32 words of the key bytes while non-zero
 // (length-exact for NUL-free keys, independent of the slot width)
-template <int RB>
+template <int RB, bool EARLY = true>
 __device__ __forceinline__ uint64_t word_hash(const uint32_t* r) {
   uint64_t h = 0x9E3779B97F4A7C15ull;
   bool live = true;
@@ -142,11 +148,14 @@ __device__ __forceinline__ uint64_t word_hash(const uint32_t* r) {
       w = bswap32(i == 0 ? r[1] : r[0]);  // LE load of the 8 big-endian key bytes
     else
       w = r[i];
-    live = live && (w != 0);
-    if (live) {
-      h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
-      h ^= h >> 29;
+    if (EARLY) {
+      if (w == 0) break;  // short keys leave early
+    } else {
+      live = live && (w != 0);
+      if (!live) continue;
     }
+    h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
   }
   h ^= h >> 32;
   h *= 0x94D049BB133111EBull;
@@ -192,6 +201,39 @@ __device__ __forceinline__ void key_mix2(const uint32_t* r, uint64_t& f1, uint64
   }
   f1 = a;
   f2 = mix64(b);
+}
+
+// ---- shared-memory hash tables of whole records (k_combine, k_agg_bins) --------------------
+// 128-bit volatile shared loads: one or two per probe instead of a word-by-word compare (a
+// record-strided word access hits only 4 bank groups)
+__device__ __forceinline__ uint4 lds128_volatile(const uint4* p) {
+  uint4 v;
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// does table entry e hold the key of record w?  (the value/state word is ignored)
+template <int RB>
+__device__ __forceinline__ bool entry_key_eq_scalar(const uint32_t* e, const uint32_t* w) {
+  bool eq = true;
+#pragma unroll
+  for (int k = 0; k < Rec<RB>::kKeyWords; k++) eq &= (((volatile const uint32_t*)e)[k] == w[k]);
+  return eq;
+}
+template <int RB>
+__device__ __forceinline__ bool entry_key_eq(const uint32_t* e, const uint32_t* w) {
+  constexpr int KW = Rec<RB>::kKeyWords;
+  bool eq = true;
+#pragma unroll
+  for (int v = 0; v < Rec<RB>::kVec; v++) {
+    uint4 x = lds128_volatile((const uint4*)e + v);
+    uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (4 * v + k < KW) eq &= (xs[k] == w[4 * v + k]);
+    if (!eq) break;
+  }
+  return eq;
 }
 
 // ---- streaming global access ------------------------------------------------

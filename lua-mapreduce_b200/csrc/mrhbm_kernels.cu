@@ -10,6 +10,8 @@
 // HBM-bound integer work: no tensor cores.  Grids are multiples of the SM count.
 #include "mrhbm_kernels.h"
 
+#include <cstdlib>
+
 #include "mrhbm_dev.cuh"
 #include "mrhbm_sort.cuh"
 
@@ -101,6 +103,10 @@ template <int RB>
 __global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                               uint32_t* __restrict__ hist) {
   constexpr int U = Unroll<RB>::U;
+  if (bp.seg_counts) {
+    recs += (size_t)blockIdx.y * bp.seg_stride * Rec<RB>::kVec;
+    n = bp.seg_counts[blockIdx.y];
+  }
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
     uint32_t w[U][Rec<RB>::kWords];
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ recs, ui
       if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
 #pragma unroll
     for (int k = 0; k < U; k++)
-      if (base + k * stride < n) atomicAdd(hist + ((size_t)bin_of<RB>(w[k], bp, nullptr) << bp.ctr_shift), 1u);  // RED
+      if (base + k * stride < n) atomicAdd(hist + (((((size_t)bin_of<RB>(w[k], bp, nullptr)) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);  // RED
   }
 }
 
@@ -117,6 +123,10 @@ template <int RB>
 __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                                  uint32_t* __restrict__ cursor, uint4* __restrict__ mid) {
   constexpr int U = Unroll<RB>::U;
+  if (bp.seg_counts) {
+    recs += (size_t)blockIdx.y * bp.seg_stride * Rec<RB>::kVec;
+    n = bp.seg_counts[blockIdx.y];
+  }
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
     uint32_t w[U][Rec<RB>::kWords];
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
       if (base + k * stride < n) {
         uint32_t bin = bin_of<RB>(w[k], bp, nullptr);
         if (bp.debug == 0) {
-          pos[k] = atomicAdd(cursor + ((size_t)bin << bp.ctr_shift), 1u);
+          pos[k] = atomicAdd(cursor + (((((size_t)bin) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);
         } else if (bp.debug == 1) {  // profiling only: stores without the claim (results invalid)
           pos[k] = cursor[(size_t)bin << bp.ctr_shift] + (uint32_t)((base + k * stride) & 1023);
           if (pos[k] >= n) pos[k] = (uint32_t)(n - 1);
@@ -258,26 +268,52 @@ __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict
 constexpr uint32_t kCombineLock = 0xffffffffu;
 constexpr int kCombineThreads = 1024;
 constexpr int kCombineSmem = 200 * 1024;
+// HyperLogLog sketch of the keys the combiner lets through: sizes the bins of the aggregation
+// pass by DISTINCT keys (a duplicate-heavy stream must not be binned by record count)
+__device__ __forceinline__ void hll_update(uint32_t* regs, uint64_t h) {
+  uint32_t idx = (uint32_t)h & (kHllRegs - 1);
+  uint64_t x = h >> 11;  // 53 bits
+  uint32_t rho = x ? (uint32_t)__clzll((long long)x) - 10u : 54u;
+  atomicMax(regs + idx, rho);
+}
+
+// cheap 32-bit slot hash (one IMAD per key word): any hash works for the table, the 64-bit
+// word_hash is only needed for the HyperLogLog sketch of what passes through
+template <int RB>
+__device__ __forceinline__ uint32_t slot_hash(const uint32_t* w) {
+  uint32_t h = 0x9E3779B9u;
+#pragma unroll
+  for (int k = 0; k < Rec<RB>::kKeyWords; k++) h = (h ^ w[k]) * 0x85EBCA6Bu + (h >> 15);
+  h ^= h >> 16;
+  h *= 0xC2B2AE35u;
+  return h ^ (h >> 13);
+}
 
 template <int RB>
 __global__ void __launch_bounds__(kCombineThreads, 1)
-    k_combine(const uint4* __restrict__ recs, uint64_t n, uint4* __restrict__ out, unsigned long long* out_count,
-              uint32_t entries) {
+    k_combine(const uint4* __restrict__ recs, uint64_t n, uint4* __restrict__ out, uint32_t region_cap,
+              uint32_t* __restrict__ seg_counts, uint32_t entries, uint32_t* __restrict__ g_hll) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t hll[kHllRegs];
+  __shared__ uint32_t s_fill;  // fill level of this CTA's output region
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
-  uint32_t* tab = (uint32_t*)smem_raw;
+  uint32_t* tab = (uint32_t*)smem_raw;  // entries whole records; value word: 0 empty, lock, else the sum
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   for (uint32_t i = tid; i < entries * W; i += blockDim.x) tab[i] = 0;
+  for (uint32_t i = tid; i < kHllRegs; i += blockDim.x) hll[i] = 0;
+  if (tid == 0) s_fill = seg_counts[blockIdx.x];
   __syncthreads();
-  auto append = [&](bool want, const uint32_t* w) {  // warp-aggregated append to the output
+  uint4* region = out + (size_t)blockIdx.x * region_cap * R::kVec;
+  auto append = [&](bool want, const uint32_t* w) {  // warp-aggregated append to the CTA's region
     uint32_t mask = __ballot_sync(0xffffffffu, want);
     if (!mask) return;
-    unsigned long long basepos = 0;
-    if (lane == (uint32_t)(__ffs(mask) - 1)) basepos = atomicAdd(out_count, (unsigned long long)__popc(mask));
+    if (want) hll_update(hll, word_hash<RB>(w));
+    uint32_t basepos = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) basepos = atomicAdd(&s_fill, (uint32_t)__popc(mask));
     basepos = __shfl_sync(0xffffffffu, basepos, __ffs(mask) - 1);
     if (want) {
-      uint4* d = out + (basepos + __popc(mask & ((1u << lane) - 1))) * R::kVec;
+      uint4* d = region + (size_t)(basepos + __popc(mask & ((1u << lane) - 1))) * R::kVec;
 #pragma unroll
       for (int v = 0; v < R::kVec; v++) stg_stream(d + v, make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]));
     }
@@ -292,8 +328,9 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
       uint32_t v = w[KW];
       bool small = v != 0 && v <= 0xffffu && (!R::kU64 || w[3] == 0);
       if (small) {
-        uint64_t h = word_hash<RB>(w);
-        uint32_t slot = (uint32_t)__umul64hi(h, (uint64_t)entries);
+        uint32_t slot = __umulhi(slot_hash<RB>(w), entries);
+        // The kernel is bound by shared-memory load throughput: leave the probe loop as early as
+        // possible and stop comparing at the first zero word (keys are zero padded, no NUL inside).
 #pragma unroll 1
         for (int probe = 0; probe < 4; probe++) {
           uint32_t* e = tab + (size_t)slot * W;
@@ -310,7 +347,14 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
           } else if (st != kCombineLock && st <= 0x7fffffffu) {
             bool eq = true;
 #pragma unroll
-            for (int k = 0; k < KW; k++) eq &= (((volatile uint32_t*)e)[k] == w[k]);
+            for (int k = 0; k < KW; k++) {
+              uint32_t x = ((volatile uint32_t*)e)[k];
+              if (x != w[k]) {
+                eq = false;
+                break;
+              }
+              if (!R::kU64 && x == 0) break;  // both keys end here
+            }
             if (eq) {
               atomicAdd(e + KW, v);  // <= 0x7fffffff + 0xffff: never wraps, never looks empty or locked
               pass = false;
@@ -336,6 +380,10 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
     }
     append(want, w);
   }
+  __syncthreads();
+  if (tid == 0) seg_counts[blockIdx.x] = s_fill;
+  for (uint32_t i = tid; i < kHllRegs; i += blockDim.x)
+    if (hll[i]) atomicMax(g_hll + i, hll[i]);
 }
 
 // global per-bin totals from the all-gathered counts: this rank's bins go to tot[], and every
@@ -471,6 +519,9 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;                                                                 \
   e = cudaFuncSetAttribute(k_big_bins<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                            (int)sort_smem_bytes(RB));                                             \
+  if (e != cudaSuccess) return e;                                                                 \
+  e = cudaFuncSetAttribute(k_agg_bins<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                           (int)sort_smem_bytes(RB));                                             \
   if (e != cudaSuccess) return e;
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
@@ -501,9 +552,14 @@ int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, cons
   k_gen_zipf32<<<stream_grid(n, 256, 8), 256, 0, s>>>((uint4*)dst, seed, start, n, d_table, V);
   return 1;
 }
+static inline dim3 source_grid(uint64_t n, const BinParams& bp) {
+  if (!bp.seg_counts) return dim3(stream_grid(n, 256, 8));
+  int x = (g_sm_count * 8 + (int)bp.nseg - 1) / (int)bp.nseg;
+  return dim3(x < 1 ? 1 : x, bp.nseg);
+}
 int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* hist, cudaStream_t s) {
   if (!n) return 0;
-  DISPATCH_RB(rb, (k_hist<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
+  DISPATCH_RB(rb, (k_hist<RB><<<source_grid(n, bp), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
   return 1;
 }
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t* out_dense,
@@ -512,12 +568,19 @@ int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* 
   k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
   return 1;
 }
-int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned long long* out_count, int sm_count,
-                   cudaStream_t s) {
+uint32_t combine_region_slack(int rb) { return (uint32_t)(kCombineSmem / rb) + kCombineThreads + 64; }
+int launch_combine(int rb, const void* recs, uint64_t n, void* out, uint32_t region_cap, uint32_t* seg_counts,
+                   uint32_t* hll, int sm_count, cudaStream_t s) {
   if (!n) return 0;
   uint32_t entries = (uint32_t)(kCombineSmem / rb);
   DISPATCH_RB(rb, (k_combine<RB><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, (uint4*)out,
-                                                                                out_count, entries)));
+                                                                                region_cap, seg_counts, entries, hll)));
+  return 1;
+}
+int launch_agg_bins(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count, cudaStream_t s) {
+  int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
+  if (grid < 1) grid = 1;
+  DISPATCH_RB(rb, (k_agg_bins<RB><<<grid, kSortThreads, sort_smem_bytes(RB), s>>>(b, B, cap)));
   return 1;
 }
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
@@ -535,8 +598,7 @@ int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uin
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                    cudaStream_t s) {
   if (!n) return 0;
-  DISPATCH_RB(rb, (k_scatter<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
-                                                                       (uint4*)mid)));
+  DISPATCH_RB(rb, (k_scatter<RB><<<source_grid(n, bp), 256, 0, s>>>((const uint4*)recs, n, bp, cursor, (uint4*)mid)));
   return 1;
 }
 int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,

@@ -24,12 +24,20 @@ struct BinParams {
   uint32_t world;        // 1 = single GPU (slot == p)
   uint32_t pbase[9];
   uint32_t debug;        // MRHBM_DEBUG_SCATTER profiling variants (0 = product path)
+  // segmented source (the combiner's per-CTA output regions): blockIdx.y selects segment y =
+  // seg_counts[y] records at recs + y * seg_stride records.  seg_counts == nullptr: one range.
+  const uint32_t* seg_counts;
+  uint64_t seg_stride;
+  uint32_t nseg;
+  uint32_t rep_shift;    // few, heavily hit bins: 2^rep_shift counter copies per bin (copy = CTA id),
+                         // i.e. bin b owns the consecutive virtual bins [b << rep_shift, (b+1) << rep_shift)
 };
 
 MRHBM_HD inline uint32_t partition_slot(const BinParams& bp, uint32_t pid) {
   return bp.world > 1 ? bp.pbase[pid % bp.world] + pid / bp.world : pid;
 }
 
+constexpr uint32_t kHllRegs = 2048;
 constexpr int kCapBytes = 32 * 1024;  // record bytes one CTA sorts in shared memory (2 CTAs per SM)
 inline uint32_t cap_records(int rb) { return (uint32_t)(kCapBytes / rb); }
 
@@ -61,16 +69,17 @@ struct ShuffleBuffers {
   // min/max pass.  hint_S = 0: unknown.
   uint32_t hint_S;
   uint64_t hint_q;     // floor(2^64 / S)
+  uint32_t rep_shift;  // bin_off / seg_off are indexed by virtual bin = bin << rep_shift
 };
 MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
-  return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[bin];
+  return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[(size_t)bin << b.rep_shift];
 }
 MRHBM_HD inline uint32_t bin_count(const ShuffleBuffers& b, uint32_t bin) {
   if (b.stride) {
     uint32_t c = b.cursor[(size_t)bin << b.ctr_shift];
     return c < b.stride ? c : b.stride;
   }
-  return b.bin_off[bin + 1] - b.bin_off[bin];
+  return b.bin_off[(size_t)(bin + 1) << b.rep_shift] - b.bin_off[(size_t)bin << b.rep_shift];
 }
 enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3, CNT_GBIG = 4 };
 enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2, ERRF_CAPACITY = 4 };
@@ -91,8 +100,15 @@ int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, ui
 int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                          uint32_t stride, uint32_t* err_flags, cudaStream_t s);
 // map-side combine of one committed range into out (appends; *out_count is the running total)
-int launch_combine(int rb, const void* recs, uint64_t n, void* out, unsigned long long* out_count, int sm_count,
-                   cudaStream_t s);
+// map-side combine of one committed range: CTA y appends to its own region out + y * region_cap
+// (records), seg_counts[y] is its running fill level (no global atomics on the append path)
+int launch_combine(int rb, const void* recs, uint64_t n, void* out, uint32_t region_cap, uint32_t* seg_counts,
+                   uint32_t* hll, int sm_count, cudaStream_t s);
+uint32_t combine_region_slack(int rb);  // worst-case extra records one launch adds to a region
+// duplicate-heavy streams: per bin, aggregate through a shared-memory hash table, then sort the
+// distinct keys (bins are sized by distinct keys, not by records)
+int launch_agg_bins(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count, cudaStream_t s);
+inline uint32_t agg_table_entries(int rb) { return (uint32_t)((kCapBytes + (kCapBytes / rb) * 8) / rb); }
 // tot[b] = sum over s < world of all[s * stride + base + b], b < n; *nover += bins (of all `stride`
 // bins) whose global total exceeds cap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,

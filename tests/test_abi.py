@@ -75,3 +75,17 @@ def test_zipf_table_shape():
     assert (t[1:] >= t[:-1]).all()
     # top-1 mass of Zipf(1.1) over a small vocabulary
     assert 0.15 < int(t[0]) / 2**64 < 0.25
+
+
+def test_fnv_in_doubles_integer_emulation_matches_real_doubles(tmp_path):
+    """csrc/mrhbm_dev.cuh fnv_lua_step (32-bit integer emulation of the example partitionfn's
+    double arithmetic, examples/WordCount/partitionfn.lua:8-16) against real IEEE doubles on
+    3e7 random (h, byte) pairs + edge values: host-compiled from the same header."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "fnvcheck")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "lua-mapreduce_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "native", "fnv_emulation_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "bad=0" in out.stdout, out.stdout
