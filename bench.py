@@ -266,13 +266,21 @@ def main():
     # ---- roofline (SURVEY 8d accounting: one read of its input + one write of its output per stage)
     peak, peak_src = peaks()
     R = rb
-    g_local = ctx.result_info().groups
-    stage_bytes = {  # per GPU, SURVEY 8d: hash-partition = N R + N R, sort = N R + N R, reduce = N R + U R
-        "k_scatter": 2 * n * R,              # the hash-partition stage's read + write (k_hist is overhead)
-        "k_sort_reduce": 3 * n * R + g_local * R,
+    info = ctx.result_info()
+    g_local = info.groups
+    combined = a.workload == "zipf32"  # ctx runs the map-side combiner for this workload
+    n2 = info.pairs_recv if combined else n  # N' = pairs that survive the combiner
+    stage_bytes = {  # per GPU, SURVEY 8d: combine N R + N' R, hash-partition N' R + N' R, sort N' R + N' R, reduce N' R + U R
+        "k_scatter": 2 * n2 * R,          # the hash-partition stage's read + write (k_hist is overhead)
+        ("k_agg_bins" if combined else "k_sort_reduce"): 3 * n2 * R + g_local * R,
     }
+    if combined:
+        stage_bytes["k_combine"] = n * R + n2 * R
     pipe_bytes = sum(stage_bytes.values())
-    k_ms = {"k_scatter": dev_ms["ms_scatter"], "k_sort_reduce": dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"]}
+    k_ms = {"k_scatter": dev_ms["ms_scatter"],
+            ("k_agg_bins" if combined else "k_sort_reduce"): dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"]}
+    if combined:
+        k_ms["k_combine"] = dev_ms["ms_combine"]
     dom = max(k_ms, key=k_ms.get)
     ach = stage_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
     traffic = None
@@ -303,12 +311,14 @@ def main():
             mm.commit()
             ctx.pool_read(0, n, host)
             ctx.reset()
-        cap_out = n + n // 16 + 4096  # a rank may own slightly more than n groups after the exchange
+        # a rank may own slightly more groups than the resident run showed (multi-GPU ownership)
+        cap_out = min(n + n // 16, int(g_local) * 2) + 4096
         out_keys = ctx.pinned_array(cap_out, np.uint64 if kind == mrhbm.KEY_U64 else "S%d" % (rb - 4))
         out_sums = ctx.pinned_array(cap_out, np.uint64)
         chunk = 1 << 22
         e2e_dt = []
         for it in range(a.e2e_steps + 1):
+            ctx.reset()  # every step is a fresh task iteration (server.lua:386-404); frees the pool
             barrier()
             t1 = time.perf_counter()
             mm = ctx.map_begin("e2e")
@@ -343,7 +353,8 @@ def main():
             "config": {"workload": wp["name"], "pairs_per_gpu": n, "partitions": P, "record_bytes": rb,
                        "seed": hex(synth.SEED), "l2": "inputs (%.1f GB) >> 126 MB L2, no flush needed" % (n * rb / 1e9),
                        "bins": st["bins"], "sub_bins": st["sub_bins"], "big_bins": st["big_bins"],
-                       "groups": int(groups), "parity_properties_ok": bool(parity_ok)},
+                       "groups": int(groups), "pairs_after_combine": int(n2) if combined else None,
+                       "parity_properties_ok": bool(parity_ok)},
             "gpu_launches": int(launches), "device_ms_per_step": dev_ms["ms_total"],
             "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }))

@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ recs, ui
     for (int k = 0; k < U; k++)
       if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
 #pragma unroll
-    for (int k = 0; k < U; k++)
-      if (base + k * stride < n) atomicAdd(hist + (((((size_t)bin_of<RB>(w[k], bp, nullptr)) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);  // RED
+    for (int k = 0; k < U; k++) {
+      if (base + k * stride < n) {
+        uint32_t bin = bin_of<RB>(w[k], bp, nullptr);
+        atomicAdd(hist + (((((size_t)bin) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);  // RED
+      }
+    }
   }
 }
 
