@@ -54,6 +54,8 @@ struct mrhbm_ctx {
   uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
   bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
+  void* l1buf = nullptr;  // coarse regions of the two-level split
+  uint64_t l1_cap = 0;
   void* comb = nullptr;  // map-side combined pairs
   uint32_t *d_hll = nullptr, *h_hll = nullptr;  // HyperLogLog registers of the combined stream (8 ranks x kHllRegs on the host)
   uint64_t comb_cap = 0;
@@ -367,7 +369,7 @@ void mrhbm_destroy(mrhbm_ctx* c) {
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
                    c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
-                   c->d_hll};
+                   c->d_hll,       c->l1buf};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -817,9 +819,27 @@ int shuffle_single(mrhbm_ctx* c) {
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
-    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-    for (auto& r : live)
-      st.launches += launch_scatter_fixed(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, c->cap, c->sb.counters + CNT_ERR, s);
+    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));  // re-recorded after level 1 when the split runs
+    // many bins: two-level coalesced split (shared-memory claims, contiguous stores); few bins:
+    // direct scatter
+    uint32_t F = 1, C1 = 0;
+    while ((uint64_t)F * F < B) F <<= 1;  // power of two >= sqrt(B)
+    C1 = (uint32_t)((B + F - 1) / F);
+    const bool split = B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT");
+    if (split) {
+      rc = ensure_records(c, &c->l1buf, &c->l1_cap, (uint64_t)C1 * F * c->cap);
+      if (rc) return rc;
+      CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));  // coarse fill levels
+      for (auto& r : live)
+        st.launches += launch_split2(c->rb, r.p, r.n, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
+                                     c->sb.mid, c->sb.counters + CNT_ERR, false, s);
+      CU(c, cudaEventRecord(c->ev[EV_PLAN], s));  // ms_plan = level 1, ms_scatter = level 2
+      st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
+                                   c->sb.mid, c->sb.counters + CNT_ERR, true, s);
+    } else {
+      for (auto& r : live)
+        st.launches += launch_scatter_fixed(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, c->cap, c->sb.counters + CNT_ERR, s);
+    }
     CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     c->sb.src = c->sb.mid;

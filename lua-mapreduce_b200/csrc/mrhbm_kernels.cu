@@ -10,6 +10,7 @@
 // HBM-bound integer work: no tensor cores.  Grids are multiples of the SM count.
 #include "mrhbm_kernels.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "mrhbm_dev.cuh"
@@ -199,6 +200,138 @@ __global__ void __launch_bounds__(256) k_scatter_fixed(const uint4* __restrict__
           stg_stream(d + v, make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]));
       }
     }
+  }
+}
+
+// ============================================================================
+// two-level coalesced split (optimistic layout, many bins)
+// ============================================================================
+// k_scatter_fixed pays one L2 round trip (cursor claim) and one 16-byte scattered store per pair.
+// k_split instead partitions a TILE of records inside shared memory (one shared-memory atomic per
+// pair), claims global space once per (tile, bin) and copies the tile out bin by bin, so stores
+// are contiguous runs.  With F fine bins per coarse bin it runs twice:
+//   level 1: source -> coarse regions (coarse = fine / F), level 2: coarse region c -> fine bins.
+constexpr int kSplitThreads = 512;
+constexpr int kSplitTileBytes = 64 * 1024;
+constexpr int kSplitMaxBins = 1024;
+
+struct SplitArgs {
+  const uint4* src;       // level 1: records; level 2: the coarse regions (segment y = coarse bin)
+  uint64_t n;             // level 1: number of records
+  const uint32_t* seg_counts;  // level 2: fill level of coarse region y at seg_counts[y << ctr_shift]
+  uint64_t seg_stride;    // level 2: records per coarse region
+  uint4* dst;
+  uint64_t dst_stride;    // records per destination bin region
+  uint32_t* cursor;       // destination bin fill levels (index << ctr_shift)
+  uint32_t capacity;      // records a destination bin can take
+  uint32_t F;             // fine bins per coarse bin (a power of two)
+  uint32_t logF;
+  uint32_t nbins;         // bins this level distinguishes inside one tile (<= kSplitMaxBins)
+  uint32_t level;         // 1 or 2
+  uint32_t ctr_shift;
+  uint32_t* err_flags;
+};
+
+template <int RB>
+__global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinParams bp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = Rec<RB>;
+  constexpr int T = kSplitTileBytes / RB;            // records per tile
+  constexpr int U = T / kSplitThreads;               // records per thread
+  static_assert(T % kSplitThreads == 0, "tile");
+  uint4* stage = (uint4*)smem_raw;                   // T records in bin order
+  uint16_t* pos_sub = (uint16_t*)(smem_raw + kSplitTileBytes);  // bin of staged position
+  __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins + 1], sgb[kSplitMaxBins];
+  const uint32_t tid = threadIdx.x;
+  const uint4* src = a.src;
+  uint64_t n = a.n;
+  uint32_t coarse = 0;
+  if (a.level == 2) {
+    coarse = blockIdx.y;
+    src += (size_t)coarse * a.seg_stride * R::kVec;
+    uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
+    n = c < a.seg_stride ? c : a.seg_stride;
+  }
+  const uint64_t ntiles = (n + T - 1) / T;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t t0 = tile * T;
+    const uint32_t tn = (uint32_t)((n - t0) < (uint64_t)T ? (n - t0) : (uint64_t)T);
+    for (uint32_t b = tid; b < a.nbins; b += kSplitThreads) scnt[b] = 0;
+    __syncthreads();
+    uint32_t w[U][R::kWords];
+    uint32_t sub[U], rk[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      if (tid + k * kSplitThreads < tn) load_rec<RB>(src + (t0 + tid + k * kSplitThreads) * R::kVec, w[k]);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (tid + k * kSplitThreads < tn) {
+        uint32_t fine = bin_of<RB>(w[k], bp, nullptr);
+        sub[k] = a.level == 1 ? fine >> a.logF : fine & (a.F - 1u);
+        rk[k] = atomicAdd(scnt + sub[k], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the per-bin counts (nbins <= 1024: two items per thread) + global claims
+    {
+      uint32_t v0 = 2 * tid < a.nbins ? scnt[2 * tid] : 0u, v1 = 2 * tid + 1 < a.nbins ? scnt[2 * tid + 1] : 0u;
+      uint32_t s = v0 + v1, incl = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((tid & 31) >= (uint32_t)d) incl += t;
+      }
+      __shared__ uint32_t wsum[kSplitThreads / 32];
+      if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+      __syncthreads();
+      if (tid < 32) {  // exclusive scan of the 16 warp sums
+        uint32_t ws = tid < kSplitThreads / 32 ? wsum[tid] : 0u, wi = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+          if (tid >= (uint32_t)d) wi += t;
+        }
+        if (tid < kSplitThreads / 32) wsum[tid] = wi - ws;
+      }
+      __syncthreads();
+      uint32_t ex = wsum[tid >> 5] + incl - s;
+      if (2 * tid < a.nbins) soff[2 * tid] = ex;
+      if (2 * tid + 1 < a.nbins) soff[2 * tid + 1] = ex + v0;
+      for (uint32_t b = tid; b < a.nbins; b += kSplitThreads) {
+        uint32_t c = scnt[b];
+        uint32_t g = 0;
+        if (c) {
+          uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+          g = atomicAdd(a.cursor + ((size_t)dbin << a.ctr_shift), c);
+          if (g + c > a.capacity) atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
+        }
+        sgb[b] = g;
+      }
+    }
+    __syncthreads();
+    // records into bin order inside the tile
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (tid + k * kSplitThreads < tn) {
+        uint32_t p = soff[sub[k]] + rk[k];
+        pos_sub[p] = (uint16_t)sub[k];
+#pragma unroll
+        for (int v = 0; v < R::kVec; v++)
+          stage[p * R::kVec + v] = make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]);
+      }
+    }
+    __syncthreads();
+    // copy out: consecutive staged positions of one bin are consecutive in global memory
+    for (uint32_t p = tid; p < tn; p += kSplitThreads) {
+      uint32_t b = pos_sub[p];
+      uint32_t slot = sgb[b] + (p - soff[b]);
+      if (slot >= a.capacity) continue;  // flagged above
+      uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+      uint4* d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
+#pragma unroll
+      for (int v = 0; v < R::kVec; v++) stg_stream(d + v, stage[p * R::kVec + v]);
+    }
+    __syncthreads();
   }
 }
 
@@ -534,6 +667,12 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
 #undef CFGC
+#define CFGS(RB)                                                                                         \
+  e = cudaFuncSetAttribute(k_split<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                           kSplitTileBytes + (kSplitTileBytes / RB) * (int)sizeof(uint16_t));              \
+  if (e != cudaSuccess) return e;
+  CFGS(16) CFGS(32) CFGS(64) CFGS(128)
+#undef CFGS
   return cudaSuccess;
 }
 
@@ -610,6 +749,44 @@ int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& 
   if (!n) return 0;
   DISPATCH_RB(rb, (k_scatter_fixed<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
                                                                              (uint4*)mid, stride, err_flags)));
+  return 1;
+}
+// both levels of the coalesced split; cursor1 / l1 are the coarse fill levels and regions
+int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
+                  uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
+                  bool level2, cudaStream_t s) {
+  SplitArgs a{};
+  a.F = F;
+  a.logF = 0;
+  while ((1u << a.logF) < F) a.logF++;
+  a.ctr_shift = bp.ctr_shift;
+  a.err_flags = err_flags;
+  size_t smem = kSplitTileBytes + (kSplitTileBytes / rb) * sizeof(uint16_t);
+  if (!level2) {
+    if (!n) return 0;
+    a.src = (const uint4*)recs;
+    a.n = n;
+    a.dst = (uint4*)l1;
+    a.dst_stride = (uint64_t)F * cap;
+    a.cursor = cursor1;
+    a.capacity = (uint32_t)std::min<uint64_t>((uint64_t)F * cap, 0xffffffffull);
+    a.nbins = C1;
+    a.level = 1;
+    DISPATCH_RB(rb, (k_split<RB><<<2 * g_sm_count, kSplitThreads, smem, s>>>(a, bp)));
+  } else {
+    a.src = (const uint4*)l1;
+    a.seg_counts = cursor1;
+    a.seg_stride = (uint64_t)F * cap;
+    a.dst = (uint4*)mid;
+    a.dst_stride = cap;
+    a.cursor = cursor;
+    a.capacity = cap;
+    a.nbins = F;
+    a.level = 2;
+    int x = (2 * g_sm_count + (int)C1 - 1) / (int)C1;
+    DISPATCH_RB(rb, (k_split<RB><<<dim3(x < 1 ? 1 : x, C1), kSplitThreads, smem, s>>>(a, bp)));
+  }
+  (void)B;
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,

@@ -116,6 +116,11 @@ int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_
 // row r < world: out[r*(n+1) ..] = exclusive scan of all[r*stride + base ..+n), totals[r] = its sum
 int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                        uint32_t* out, uint32_t* totals, cudaStream_t s);
+// two-level coalesced split into the fixed-stride layout: level 1 (level2 = false) source ->
+// C1 coarse regions of F*cap records in l1, level 2 coarse regions -> fine bins of cap records in mid
+int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
+                  uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
+                  bool level2, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);
