@@ -832,10 +832,10 @@ int shuffle_single(mrhbm_ctx* c) {
       CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));  // coarse fill levels
       for (auto& r : live)
         st.launches += launch_split2(c->rb, r.p, r.n, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                     c->sb.mid, c->sb.counters + CNT_ERR, false, s);
+                                     c->sb.mid, c->sb.counters + CNT_ERR, false, nullptr, s);
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));  // ms_plan = level 1, ms_scatter = level 2
       st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                   c->sb.mid, c->sb.counters + CNT_ERR, true, s);
+                                   c->sb.mid, c->sb.counters + CNT_ERR, true, nullptr, s);
     } else {
       for (auto& r : live)
         st.launches += launch_scatter_fixed(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, c->cap, c->sb.counters + CNT_ERR, s);
@@ -910,7 +910,30 @@ int shuffle_single(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+      {
+        // exact layout through the two-level coalesced split when there are enough bins (claims relative
+        // to bin_off); else the direct scatter
+        uint32_t F = 1;
+        while ((uint64_t)F * F < B) F <<= 1;
+        uint32_t C1 = (uint32_t)((B + F - 1) / F);
+        // (not for the aggregation pass: its few, very unevenly filled bins make the tile-local
+        // shared-memory claims collide; measured slower than the direct scatter there)
+        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
+          rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
+          if (rc) return rc;
+          // relative fill levels: coarse levels live in hist (dead after the scan), fine levels in cursor
+          CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
+          CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+          BinParams bq = bp;
+          for (auto& r : live)
+            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bq, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
+                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
+          st.launches += launch_split2(c->rb, nullptr, 0, bq, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
+                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s);
+        } else {
+          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+        }
+      }
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
       c->sb.src = c->sb.mid;

@@ -230,6 +230,11 @@ struct SplitArgs {
   uint32_t level;         // 1 or 2
   uint32_t ctr_shift;
   uint32_t* err_flags;
+  // exact layout (after k_hist + k_exscan): bin f starts at base_off[f << rep_shift]; nullptr = the
+  // optimistic fixed-stride layout
+  const uint32_t* base_off;
+  uint32_t rep_shift;
+  uint32_t B;
 };
 
 template <int RB>
@@ -246,11 +251,22 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
   const uint4* src = a.src;
   uint64_t n = a.n;
   uint32_t coarse = 0;
+  if (a.level == 1 && bp.seg_counts) {  // segmented source (the combiner's per-CTA regions)
+    src += (size_t)blockIdx.y * bp.seg_stride * R::kVec;
+    n = bp.seg_counts[blockIdx.y];
+  }
   if (a.level == 2) {
     coarse = blockIdx.y;
-    src += (size_t)coarse * a.seg_stride * R::kVec;
-    uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
-    n = c < a.seg_stride ? c : a.seg_stride;
+    if (a.base_off) {  // exact: the coarse region is the union of its fine bins
+      uint32_t f0 = coarse * a.F, f1 = f0 + a.F < a.B ? f0 + a.F : a.B;
+      uint32_t o0 = a.base_off[(size_t)f0 << a.rep_shift], o1 = a.base_off[(size_t)f1 << a.rep_shift];
+      src += (size_t)o0 * R::kVec;
+      n = o1 - o0;
+    } else {
+      src += (size_t)coarse * a.seg_stride * R::kVec;
+      uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
+      n = c < a.seg_stride ? c : a.seg_stride;
+    }
   }
   const uint64_t ntiles = (n + T - 1) / T;
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -303,7 +319,12 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
         if (c) {
           uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
           g = atomicAdd(a.cursor + ((size_t)dbin << a.ctr_shift), c);
-          if (g + c > a.capacity) atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
+          if (a.base_off) {  // exact layout: absolute start of the destination region, always large enough
+            uint32_t f = a.level == 1 ? b * a.F : dbin;
+            g += a.base_off[(size_t)f << a.rep_shift];
+          } else if (g + c > a.capacity) {
+            atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
+          }
         }
         sgb[b] = g;
       }
@@ -325,9 +346,14 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
     for (uint32_t p = tid; p < tn; p += kSplitThreads) {
       uint32_t b = pos_sub[p];
       uint32_t slot = sgb[b] + (p - soff[b]);
-      if (slot >= a.capacity) continue;  // flagged above
-      uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-      uint4* d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
+      uint4* d;
+      if (a.base_off) {
+        d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
+      } else {
+        if (slot >= a.capacity) continue;  // flagged above
+        uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+        d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
+      }
 #pragma unroll
       for (int v = 0; v < R::kVec; v++) stg_stream(d + v, stage[p * R::kVec + v]);
     }
@@ -754,8 +780,11 @@ int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& 
 // both levels of the coalesced split; cursor1 / l1 are the coarse fill levels and regions
 int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
                   uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, cudaStream_t s) {
+                  bool level2, const uint32_t* base_off, cudaStream_t s) {
   SplitArgs a{};
+  a.base_off = base_off;
+  a.rep_shift = bp.rep_shift;
+  a.B = B;
   a.F = F;
   a.logF = 0;
   while ((1u << a.logF) < F) a.logF++;
@@ -772,7 +801,9 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
     a.capacity = (uint32_t)std::min<uint64_t>((uint64_t)F * cap, 0xffffffffull);
     a.nbins = C1;
     a.level = 1;
-    DISPATCH_RB(rb, (k_split<RB><<<2 * g_sm_count, kSplitThreads, smem, s>>>(a, bp)));
+    dim3 grid(2 * g_sm_count);
+    if (bp.seg_counts) grid = dim3((2 * g_sm_count + bp.nseg - 1) / bp.nseg, bp.nseg);
+    DISPATCH_RB(rb, (k_split<RB><<<grid, kSplitThreads, smem, s>>>(a, bp)));
   } else {
     a.src = (const uint4*)l1;
     a.seg_counts = cursor1;
@@ -786,7 +817,6 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
     int x = (2 * g_sm_count + (int)C1 - 1) / (int)C1;
     DISPATCH_RB(rb, (k_split<RB><<<dim3(x < 1 ? 1 : x, C1), kSplitThreads, smem, s>>>(a, bp)));
   }
-  (void)B;
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,

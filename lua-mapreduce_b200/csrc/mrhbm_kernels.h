@@ -120,7 +120,7 @@ int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uin
 // C1 coarse regions of F*cap records in l1, level 2 coarse regions -> fine bins of cap records in mid
 int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
                   uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, cudaStream_t s);
+                  bool level2, const uint32_t* base_off, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);

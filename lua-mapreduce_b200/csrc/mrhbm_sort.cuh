@@ -246,28 +246,56 @@ __device__ uint32_t counting_path(const SortSmem& sm, uint32_t cnt, uint64_t pmi
     }
   }
   __syncthreads();
-  // rank among the bucket mates -> final sorted slot (equal keys keep their bucket order)
-  for (uint32_t j = tid; j < cnt; j += T) {
-    const uint32_t* r = rec2w + j * R::kWords;
-    uint32_t b = bucket_of(r);
-    uint32_t s = bcnt[b], e = (b + 1 < NB) ? bcnt[b + 1] : cnt;
-    uint32_t rank = 0, head = 1;
-    if (e - s > 1) {  // most buckets hold one record
-      for (uint32_t m = s; m < e; m++) {
-        if (m == j) continue;
-        int c = key_cmp<RB>(rec2w + m * R::kWords, r);
-        bool eq_before = (c == 0 && m < j);
-        rank += (c < 0) || eq_before;
-        if (eq_before) head = 0;  // an equal key sits earlier: not the first of its group
-      }
-    }
+  // Every record ranks itself among its bucket mates: final sorted slot f = bucket start + rank,
+  // "head" = first of its key (bucket order breaks ties), and a head sums its equals (equal keys
+  // share a prefix, hence a bucket).  Only the head flags go back to shared memory, in sorted
+  // order; the records are written to global memory straight from the bucket-ordered buffer.
+  uint32_t fpos[ITEMS];
+  uint64_t hsum[ITEMS];
 #pragma unroll
-    for (int v = 0; v < R::kVec; v++) sm.rec[(s + rank) * R::kVec + v] = sm.rec2[j * R::kVec + v];
-    heads[s + rank] = (uint16_t)head;
+  for (int k = 0; k < ITEMS; k++) {
+    uint32_t j = tid + k * T;
+    fpos[k] = 0xffffffffu;
+    hsum[k] = 0;
+    if (j < cnt) {
+      const uint32_t* r = rec2w + j * R::kWords;
+      uint32_t b = bucket_of(r);
+      uint32_t s = bcnt[b], e = (b + 1 < NB) ? bcnt[b + 1] : cnt;
+      uint32_t rank = 0, head = 1;
+      uint64_t sum = rec_value<RB>(r);
+      if (e - s > 1) {  // most buckets hold one record
+        for (uint32_t m = s; m < e; m++) {
+          if (m == j) continue;
+          const uint32_t* q = rec2w + m * R::kWords;
+          int c = key_cmp<RB>(q, r);
+          if (c < 0) {
+            rank++;
+          } else if (c == 0) {
+            if (m < j) {
+              rank++;
+              head = 0;  // an equal key sits earlier: not the first of its group
+            } else {
+              sum += rec_value<RB>(q);
+            }
+          }
+        }
+      }
+      heads[s + rank] = (uint16_t)head;
+      fpos[k] = head ? s + rank : 0xffffffffu;
+      hsum[k] = sum;
+    }
   }
   __syncthreads();
-  auto at = [&](uint32_t j) -> const uint32_t* { return recw + j * R::kWords; };
-  return reduce_sorted<RB, MODE, true>(at, cnt, heads, out);
+  constexpr int PER = (CAP + kSortThreads - 1) / kSortThreads;
+  const uint32_t groups = block_exscan<PER>(heads, cnt, nullptr);  // heads[f] = groups before sorted slot f
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    uint32_t j = tid + k * T;
+    if (j < cnt && fpos[k] != 0xffffffffu)
+      write_group<RB, MODE>(out, out.base + heads[fpos[k]], rec2w + j * R::kWords, hsum[k]);
+  }
+  __syncthreads();
+  return groups;
 }
 
 // Sorts cnt (<= cap) records of one bin by key, sums the values of equal keys and writes

@@ -49,7 +49,7 @@ def check_vs_oracle_u64(ctx, keys, vals, P, partitioner=O.PART_MULHASH):
 
 
 @pytest.mark.parametrize("flags", [0, mrhbm.F_NO_OPTIMISTIC])  # single-pass and two-pass partition layouts
-@pytest.mark.parametrize("n,P", [(1, 1), (37, 4), (5000, 16), (200_000, 16), (1_000_000, 1024)])
+@pytest.mark.parametrize("n,P", [(1, 1), (37, 4), (5000, 16), (200_000, 16), (1_000_000, 1024), (6_000_000, 1024)])
 def test_u64_uniform_vs_oracle(n, P, flags):
     keys, vals = O.gen_u64(SEED, 0, n)
     with mrhbm.Ctx(mrhbm.KEY_U64, P, flags=flags) as ctx:
