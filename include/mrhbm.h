@@ -52,7 +52,16 @@ enum {
 };
 /* built-in reducefn/combinerfn (examples/WordCount/reducefn.lua:1-15: integer sum,
  * associative + commutative + idempotent flags set) */
-enum { MRHBM_RED_SUM = 0 };
+enum {
+  MRHBM_RED_SUM = 0,
+  /* general (non-built-in) Lua reducefn, job.lua:264-284: the device only partitions, sorts and
+   * groups; mrhbm_groups_next hands out every value of a key (order unspecified, like the
+   * reference's heap-pop order among equal keys) and the host calls reducefn per group.
+   * Needs combiner = 0.  mrhbm_result_copy then returns one row per pair (keys repeat).  On several
+   * GPUs a key may carry at most one shared-memory bin of values (2048 for u64 keys, 1024 / 512 /
+   * 256 for 32 / 64 / 128-byte records), else MRHBM_E_SKEW; on one GPU there is no limit. */
+  MRHBM_RED_NONE = 1
+};
 
 typedef struct mrhbm_ctx mrhbm_ctx;
 typedef struct mrhbm_map mrhbm_map;
@@ -128,7 +137,8 @@ int mrhbm_partitions(mrhbm_ctx *, uint32_t *ids, size_t cap, size_t *n);
 int mrhbm_groups_open(mrhbm_ctx *, uint32_t partition, mrhbm_iter **out);
 /* 1 = one group, 0 = end, <0 = error.  Ascending key order (C-locale bytewise; u64
  * numeric).  *key points at klen key bytes (u64 keys: 8 bytes big endian);
- * values/nvalues is the reduced list (built-in sum: one value).  Pointers stay valid
+ * values/nvalues is the reduced list (built-in sum: one value; MRHBM_RED_NONE: all values of the
+ * key).  Pointers stay valid
  * until the next call on this iterator. */
 int mrhbm_groups_next(mrhbm_iter *, const void **key, size_t *klen, const uint64_t **values,
                       size_t *nvalues);

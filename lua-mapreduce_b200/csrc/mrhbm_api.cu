@@ -62,6 +62,7 @@ struct mrhbm_ctx {
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
   std::vector<uint32_t> h_bin_off, h_uoff;
+  std::vector<uint32_t> h_big;  // group-only mode: oversized bins, each holding runs of `cap` rows
   void* ckeys = nullptr;
   uint64_t* csums = nullptr;
   uint64_t c_cap = 0;
@@ -95,6 +96,7 @@ struct RunCursor {
 };
 struct mrhbm_iter {
   mrhbm_ctx* ctx;
+  std::vector<uint64_t> valbuf;  // group-only mode: the values of the current key
   std::vector<unsigned char> keys;
   std::vector<uint64_t> sums;
   std::vector<RunCursor> runs;
@@ -337,7 +339,9 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
       return fail(c, MRHBM_E_INVAL, "string keys need partitioner FNV_LUA or WORDHASH");
   } else
     return fail(c, MRHBM_E_INVAL, "unknown key_kind %u", cfg->key_kind);
-  if (cfg->reducer != MRHBM_RED_SUM) return fail(c, MRHBM_E_INVAL, "unknown reducer %u", cfg->reducer);
+  if (cfg->reducer != MRHBM_RED_SUM && cfg->reducer != MRHBM_RED_NONE) return fail(c, MRHBM_E_INVAL, "unknown reducer %u", cfg->reducer);
+  if (cfg->reducer == MRHBM_RED_NONE && cfg->combiner) return fail(c, MRHBM_E_INVAL, "a general reducer cannot be combined on the device (combiner must be 0)");
+  c->sb.no_reduce = cfg->reducer == MRHBM_RED_NONE;
   CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < EV_N; i++) CU(c, cudaEventCreate(&c->ev[i]));
   CU(c, kernels_configure());
@@ -860,6 +864,7 @@ int shuffle_single(mrhbm_ctx* c) {
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
     if (!(c->h_counters[CNT_ERR] & ERRF_CAPACITY)) {
+      c->h_big.clear();
       c->rv = c->sb;
       c->sb.stride = 0;
       c->B = (uint32_t)B;
@@ -958,6 +963,11 @@ int shuffle_single(mrhbm_ctx* c) {
     }
     st.launches += launch_big_bins(c->rb, c->sb, nbig, c->cap, s);
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+    c->h_big.clear();
+    if (c->sb.no_reduce && nbig) {
+      c->h_big.resize(nbig);
+      CU(c, cudaMemcpyAsync(c->h_big.data(), c->sb.big_list, nbig * 4, cudaMemcpyDeviceToHost, s));
+    }
     st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
                                  c->sb.counters + CNT_TOTAL, 0, s);
     c->h_bin_off.resize(B + 1);
@@ -1286,13 +1296,19 @@ int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
       return fail(c, MRHBM_E_CUDA, "groups_open: %s", cudaGetErrorString(e));
     }
   }
-  it->sorted = c->ordered || c->S == 1;
+  it->sorted = (c->ordered || c->S == 1) && c->h_big.empty();
   if (it->sorted) {
     it->runs.push_back(RunCursor{0, hi - lo});
   } else {
     for (uint32_t r = 0; r < c->S; r++) {
       uint64_t a = c->h_uoff[b0 + r] - lo, b = c->h_uoff[b0 + r + 1] - lo;
-      if (b > a) it->runs.push_back(RunCursor{a, b});
+      if (b <= a) continue;
+      bool big = std::find(c->h_big.begin(), c->h_big.end(), (uint32_t)(b0 + r)) != c->h_big.end();
+      if (!big) {
+        it->runs.push_back(RunCursor{a, b});
+      } else {  // group-only mode: an oversized bin is a sequence of ascending runs of cap rows
+        for (uint64_t q = a; q < b; q += c->cap) it->runs.push_back(RunCursor{q, std::min<uint64_t>(q + c->cap, b)});
+      }
     }
   }
   *out = it;
@@ -1311,6 +1327,20 @@ int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint
   if (best < 0) return 0;
   uint64_t i = it->runs[best].pos++;
   const unsigned char* k = &it->keys[i * c->kb];
+  size_t nv = 1;
+  bool gathered = false;
+  if (c->cfg.reducer == MRHBM_RED_NONE) {
+    // every row of this key: adjacent in its run, and -- for an oversized bin -- at the head of
+    // sibling runs too
+    it->valbuf.clear();
+    it->valbuf.push_back(it->sums[i]);
+    for (size_t r = 0; r < it->runs.size(); r++) {
+      RunCursor& rc = it->runs[r];
+      while (rc.pos < rc.end && slot_cmp(c, &it->keys[rc.pos * c->kb], k) == 0) it->valbuf.push_back(it->sums[rc.pos++]);
+    }
+    nv = it->valbuf.size();
+    gathered = true;
+  }
   if (c->rb == 16) {
     for (int b = 0; b < 8; b++) it->keybuf[b] = k[7 - b];  // 8-byte big-endian string
     *key = it->keybuf;
@@ -1319,8 +1349,8 @@ int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint
     *key = k;
     *klen = strnlen((const char*)k, c->kb);
   }
-  *values = &it->sums[i];
-  *nvalues = 1;
+  *values = gathered ? it->valbuf.data() : &it->sums[i];
+  *nvalues = nv;
   return 1;
 }
 

@@ -636,7 +636,8 @@ __global__ void __launch_bounds__(256) k_checksum_out(ShuffleBuffers b, uint32_t
       if (i > 0) {
 #pragma unroll
         for (int k = 0; k < KW; k++) p[k] = keys[(so + i - 1) * KW + k];
-        if (key_cmp<RB>(p, w) >= 0) bad_order++;
+        int oc = key_cmp<RB>(p, w);
+        if (oc > 0 || (oc == 0 && !b.no_reduce)) bad_order++;
       }
       uint32_t pid;
       uint32_t mybin = bin_of<RB>(w, bp, &pid);

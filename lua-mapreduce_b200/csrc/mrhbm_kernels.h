@@ -70,6 +70,7 @@ struct ShuffleBuffers {
   uint32_t hint_S;
   uint64_t hint_q;     // floor(2^64 / S)
   uint32_t rep_shift;  // bin_off / seg_off are indexed by virtual bin = bin << rep_shift
+  uint32_t no_reduce;  // MRHBM_RED_NONE: every pair is its own output row (sorted, grouped on the host)
 };
 MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
   return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[(size_t)bin << b.rep_shift];

@@ -129,6 +129,7 @@ struct ChunkOut {
   uint64_t* sums;  // FINAL only
   uint64_t base;   // element offset into the destination
   uint32_t* err_flags;
+  uint32_t no_reduce = 0;  // group-only mode: equal keys stay separate rows
 };
 
 template <int RB, int MODE>
@@ -169,7 +170,7 @@ __device__ __forceinline__ uint32_t reduce_sorted(At at, uint32_t cnt, uint16_t*
   if (!HAVE_FLAGS) {
     for (uint32_t j = tid; j < cnt; j += T) {
       uint32_t head = 1;
-      if (j > 0) head = !key_eq<RB>(at(j), at(j - 1));
+      if (j > 0 && !out.no_reduce) head = !key_eq<RB>(at(j), at(j - 1));
       hs[j] = (uint16_t)head;
     }
     __syncthreads();
@@ -273,8 +274,8 @@ __device__ uint32_t counting_path(const SortSmem& sm, uint32_t cnt, uint64_t pmi
           } else if (c == 0) {
             if (m < j) {
               rank++;
-              head = 0;  // an equal key sits earlier: not the first of its group
-            } else {
+              if (!out.no_reduce) head = 0;  // an equal key sits earlier: not the first of its group
+            } else if (!out.no_reduce) {
               sum += rec_value<RB>(q);
             }
           }
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
       if (threadIdx.x == 0) b.ucount[bin] = 0;
       continue;
     }
-    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
+    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
     // gather the bin's segments (one per source rank after the all-to-all; one on a single GPU)
     uint32_t filled = 0;
     if (b.stride) {
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_agg_bins(ShuffleBuffers b, 
       }
       continue;
     }
-    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
+    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
     uint32_t g = process_loaded<RB, MODE_FINAL>(sm, n, out);
     if (tid == 0) b.ucount[bin] = g;
   }
@@ -590,6 +591,26 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, 
   SortSmem sm = carve(smem_raw, RB);
   uint32_t bin = b.big_list[blockIdx.x];
   uint32_t off = (uint32_t)bin_start(b, bin), n = bin_count(b, bin);
+  if (b.no_reduce) {
+    // group-only mode cannot shrink a bin (a key with more values than one CTA sorts): sort it
+    // chunk by chunk; the bin becomes ceil(n / cap) ascending runs of cap rows, which the host
+    // iterator merges (it knows the oversized bins from big_list).  Contiguous bins only.
+    if (b.src != b.mid || b.nseg != 1) {
+      if (threadIdx.x == 0) {
+        atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_SKEW);
+        b.ucount[bin] = 0;
+      }
+      return;
+    }
+    const uint4* src = (const uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
+    for (uint32_t c = 0; c < n; c += cap) {
+      uint32_t m = n - c < cap ? n - c : cap;
+      ChunkOut out{b.out_keys, b.out_sums, (uint64_t)off + c, b.counters + CNT_ERR, 1u};
+      process_chunk<RB, MODE_FINAL, false>(sm, src + (uint64_t)c * Rec<RB>::kVec, m, out);
+    }
+    if (threadIdx.x == 0) b.ucount[bin] = n;
+    return;
+  }
   uint4* base = (uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
   if (b.src != b.mid) {  // after an exchange: make the bin contiguous inside the (free) send buffer
     uint64_t filled = 0;
@@ -620,7 +641,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, 
     }
     n = w;
   }
-  ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR};
+  ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
   uint32_t g = process_chunk<RB, MODE_FINAL, false>(sm, base, n, out);
   if (threadIdx.x == 0) b.ucount[bin] = g;
 }

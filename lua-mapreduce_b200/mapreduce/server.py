@@ -52,12 +52,12 @@ class server:
         # associative/commutative/idempotent flags, examples/WordCount/reducefn.lua:10-14)
         red, part = mods["reducefn"], mods["partitionfn"]
         builtin_red = getattr(red, "hbm_reducefn", None)
-        if builtin_red != "sum":
-            raise NotImplementedError(
-                "storage 'hbm' needs a reducefn module declaring hbm_reducefn = 'sum' "
-                "(general reducers: SURVEY 8f rank 4, not built yet)")
-        if "combinerfn" in mods and getattr(mods["combinerfn"], "hbm_reducefn", None) != "sum":
-            raise NotImplementedError("combinerfn must declare hbm_reducefn = 'sum'")
+        if builtin_red not in (None, "sum"):
+            raise NotImplementedError("unknown hbm_reducefn %r (built-ins: 'sum')" % (builtin_red,))
+        # no declaration = general reducer: the device partitions, sorts and groups, reducefn runs
+        # on the host per group (job.lua:264-284); values are unsigned integers < 2^32
+        if "combinerfn" in mods and (builtin_red != "sum" or getattr(mods["combinerfn"], "hbm_reducefn", None) != "sum"):
+            raise NotImplementedError("a combinerfn runs on the device: it (and the reducefn) must declare hbm_reducefn = 'sum'")
         pname = getattr(part, "hbm_partitionfn", None)
         if pname not in _BUILTIN_PART:
             raise NotImplementedError("partitionfn module must declare hbm_partitionfn in %s" % sorted(_BUILTIN_PART))
@@ -65,7 +65,8 @@ class server:
         assert isinstance(nparts, int) and nparts >= 1, "partitionfn module must expose NUM_REDUCERS"
         hbm = dict(key_kind="str", max_key_bytes=123, device=-1)
         hbm.update(params.get("hbm") or {})
-        hbm.update(partitioner=_BUILTIN_PART[pname], num_partitions=nparts, combiner="combinerfn" in mods)
+        hbm.update(partitioner=_BUILTIN_PART[pname], num_partitions=nparts, combiner="combinerfn" in mods,
+                   reducer=0 if builtin_red == "sum" else 1)
         self.config = dict(mapfn=params["mapfn"], reducefn=params["reducefn"], partitionfn=params["partitionfn"],
                            combinerfn=params.get("combinerfn"), init_args=self.init_args,
                            storage=params["storage"], hbm=hbm)
@@ -78,7 +79,7 @@ class server:
         from .. import mrhbm
         kind = mrhbm.KEY_U64 if h["key_kind"] == "u64" else mrhbm.KEY_STR
         return mrhbm.Ctx(kind, h["num_partitions"], h["partitioner"], max_key_bytes=h["max_key_bytes"],
-                         combiner=h["combiner"], device=h["device"])
+                         combiner=h["combiner"], device=h["device"], reducer=h["reducer"])
 
     # ---- polling (server.lua:186-234) with inline execution when no worker is attached
     def _wait(self, ns):
@@ -112,7 +113,7 @@ class server:
             it += 1
             t0 = time.time()
             with b.cv:
-                if b.ctx is None:
+                if b.ctx is None or getattr(b.ctx, "h", True) is None:  # none yet, or closed by its owner
                     b.ctx = self._make_ctx()
                 else:
                     b.ctx.reset()

@@ -12,7 +12,7 @@ from . import build as _build
 
 KEY_U64, KEY_STR = 0, 1
 PART_FNV_LUA, PART_MULHASH, PART_WORDHASH = 0, 1, 2
-RED_SUM = 0
+RED_SUM, RED_NONE = 0, 1
 F_FORCE_RUNS, F_SMALL_BINS, F_NO_OPTIMISTIC = 1, 2, 4
 E_NODEVICE = -8
 UNIQUE_ID_BYTES = 128
@@ -171,12 +171,12 @@ class Ctx:
     """One GPU's shuffle context (storage = "hbm")."""
 
     def __init__(self, key_kind=KEY_STR, num_partitions=15, partitioner=None, max_key_bytes=27,
-                 combiner=False, device=-1, reserve_pairs=0, flags=0):
+                 combiner=False, device=-1, reserve_pairs=0, flags=0, reducer=RED_SUM):
         self.L = load()
         if partitioner is None:
             partitioner = PART_MULHASH if key_kind == KEY_U64 else PART_FNV_LUA
         self.cfg = Config(C.sizeof(Config), device, key_kind, max_key_bytes, num_partitions, partitioner,
-                          RED_SUM, int(bool(combiner)), reserve_pairs, flags, 0)
+                          reducer, int(bool(combiner)), reserve_pairs, flags, 0)
         self.h = C.c_void_p()
         rc = self.L.mrhbm_init(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:

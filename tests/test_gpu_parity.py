@@ -307,3 +307,43 @@ def test_map_side_combiner_keeps_the_result(kind):
             ctx.shuffle()
             assert ctx.result_info().pairs_recv < n
             check_vs_oracle_u64(ctx, keys, vals, P)
+
+
+def test_group_only_mode_for_general_reducers():
+    """MRHBM_RED_NONE (job.lua:264-284 with an arbitrary reducefn): the device sorts and groups, the
+    caller sees every value of a key.  Checked against the oracle's identity reducer."""
+    rng = np.random.default_rng(21)
+    n, P = 120_000, 7
+    words = [O.rank_to_key(int(r)) for r in rng.integers(1, 40_000, n)]
+    vals = rng.integers(0, 1 << 31, n).astype(np.uint32)
+    e = O.Engine(O.PART_FNV_LUA, P, combiner=-1, reducer=O.RED_IDENTITY, aci=False)
+    for j in range(3):
+        e.map_job(j, pairs=[(w, int(v)) for w, v in zip(words[j::3], vals[j::3])])
+    e.reduce_all()
+    want = {(p, k): sorted(int(x) for x in v) for p, k, v in e.final_pairs()}
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, reducer=mrhbm.RED_NONE) as ctx:
+        for j in range(3):
+            m = ctx.map_begin(j)
+            m.emit_batch(str_records(words[j::3], vals[j::3], 27))
+            m.commit()
+        ctx.shuffle()
+        got = {}
+        for p in ctx.partitions():
+            ks = []
+            for k, v in ctx.groups(p):
+                got[(p, k)] = sorted(v)
+                ks.append(k)
+            assert ks == sorted(ks) and len(set(ks)) == len(ks)
+        assert got == want
+        cin, cout = ctx.checksum_input(), ctx.checksum_result()
+        assert cin[:3] == cout[:3] and cout[3] == n and cout[4:] == [0, 0]
+    with pytest.raises(mrhbm.MrhbmError):  # a general reducer cannot be combined on the device
+        mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, reducer=mrhbm.RED_NONE, combiner=True)
+    with mrhbm.Ctx(mrhbm.KEY_U64, 2, reducer=mrhbm.RED_NONE) as ctx:  # more values for one key than a bin holds
+        keys = np.concatenate([np.full(5000, 7, dtype=np.uint64), np.arange(100, 400, dtype=np.uint64)])
+        m = ctx.map_begin(1)
+        m.emit_batch(u64_records(keys, np.arange(keys.size, dtype=np.uint32)))
+        m.commit()
+        ctx.shuffle()
+        got = {int.from_bytes(k, "big"): sorted(v) for p in ctx.partitions() for k, v in ctx.groups(p)}
+        assert got[7] == list(range(5000)) and len(got) == 301 and got[100] == [5000]

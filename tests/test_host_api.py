@@ -174,3 +174,30 @@ def test_wordcount_configs_on_gpu(name, corpus, golden_wordcount):
     assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
     assert s.stats["reduce_count"] == 15 and s.stats["shuffle"]["pairs"] == 4989
     s.board.ctx.close()
+
+
+def _general_reducer_module():
+    import sys
+    import types
+    mod = types.ModuleType("max_reducefn")
+
+    def reducefn(key, values, emit):  # not a sum: needs every value
+        emit(max(values))
+        emit(len(values))
+    mod.reducefn, mod.init = reducefn, lambda a=None: None
+    sys.modules["max_reducefn"] = mod
+    return "max_reducefn"
+
+
+@pytest.mark.gpu
+def test_general_reducer_runs_on_the_host_over_device_groups(corpus, golden_wordcount):
+    """a reducefn without hbm_reducefn: device groups, host reduces (job.lua:275-284)"""
+    s = server.new("hbm://local", "gpu-max-reducer")
+    s.configure(dict(taskfn=WC + ".taskfn", mapfn=WC + ".mapfn", partitionfn=WC + ".partitionfn",
+                     reducefn=_general_reducer_module(), finalfn=WC + ".finalfn", storage="hbm"))
+    assert s.config["hbm"]["reducer"] == 1
+    got = {}
+    s.finalfn = type("F", (), {"finalfn": staticmethod(lambda it: got.update({k: v for k, v in it}) or True)})
+    s.loop()
+    assert got == {k: [1, sum(c)] for k, _, c in golden_wordcount}
+    s.board.ctx.close()
