@@ -17,9 +17,11 @@ local hbm = { _VERSION = "0.1", _NAME = "mapreduce.hbm" }
 local ctx -- one context per worker process (job.lua keeps `funcs`/`initialized` per process too)
 
 function hbm.configure(partition_mod, reduce_mod, combiner_mod, opts)
-  assert(reduce_mod.hbm_reducefn == "sum",
-         "storage 'hbm' needs a reducefn module declaring hbm_reducefn = 'sum'")
-  assert(not combiner_mod or combiner_mod.hbm_reducefn == "sum")
+  -- hbm_reducefn = "sum": reduced on the device.  No declaration: general reducer -- the device
+  -- partitions, sorts and groups, job.lua:264-284 calls reducefn per group on the host.
+  local builtin = reduce_mod.hbm_reducefn == "sum"
+  assert(not combiner_mod or (builtin and combiner_mod.hbm_reducefn == "sum"),
+         "a combinerfn runs on the device: it (and the reducefn) must declare hbm_reducefn = 'sum'")
   opts = opts or {}
   local c, err = mrhbm.new{
     key_kind = opts.key_kind or "str",
@@ -27,6 +29,7 @@ function hbm.configure(partition_mod, reduce_mod, combiner_mod, opts)
     num_partitions = assert(partition_mod.NUM_REDUCERS, "partitionfn module must expose NUM_REDUCERS"),
     partitioner = assert(partition_mod.hbm_partitionfn, "partitionfn module must declare hbm_partitionfn"),
     combiner = combiner_mod ~= nil,
+    reducer = builtin and "sum" or "none",
     device = opts.device,
   }
   ctx = assert(c, err)

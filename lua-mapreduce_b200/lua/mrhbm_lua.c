@@ -32,7 +32,7 @@ static int fail(lua_State *L, mrhbm_ctx *c) { /* luamongo style: nil, msg */
 }
 
 /* mrhbm.new{ key_kind="str"|"u64", max_key_bytes=, num_partitions=, partitioner="fnv_lua"|"mulhash"|
- *            "wordhash", combiner=bool, device= } */
+ *            "wordhash", combiner=bool, reducer="sum"|"none", device= } */
 static int l_new(lua_State *L) {
   mrhbm_config cfg;
   const char *s;
@@ -54,8 +54,10 @@ static int l_new(lua_State *L) {
   cfg.combiner = lua_toboolean(L, -1);
   lua_getfield(L, 1, "device");
   cfg.device = (int32_t)luaL_optinteger(L, -1, -1);
-  lua_pop(L, 6);
-  cfg.reducer = MRHBM_RED_SUM;
+  lua_getfield(L, 1, "reducer"); /* "sum" (built-in) | "none" (general reducefn on the host) */
+  s = luaL_optstring(L, -1, "sum");
+  cfg.reducer = strcmp(s, "none") == 0 ? MRHBM_RED_NONE : MRHBM_RED_SUM;
+  lua_pop(L, 7);
   lctx *u = (lctx *)lua_newuserdata(L, sizeof *u);
   u->h = NULL;
   luaL_setmetatable(L, CTX_MT);
