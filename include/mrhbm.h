@@ -117,6 +117,11 @@ int mrhbm_emit_device(mrhbm_map *, const void *dev_records, size_t n);
 int mrhbm_map_gen_u64(mrhbm_map *, uint64_t seed, uint64_t start, uint64_t n);
 int mrhbm_map_gen_zipf(mrhbm_map *, uint64_t seed, uint64_t start, uint64_t n,
                        const uint64_t *table, uint64_t V);
+/* device-side WordCount mapfn (examples/WordCount/mapfn.lua:3-9, misc/naive.lua:2-5): emits
+ * (word, 1) for every maximal run of non-space bytes of `text`; the space class is C-locale
+ * isspace (' ' \t \n \v \f \r), i.e. Lua's "[^%s]+".  A word that does not fit the ctx record
+ * class fails with MRHBM_E_KEY and emits nothing.  *words (optional) receives the token count. */
+int mrhbm_map_wordcount(mrhbm_map *, const void *text, size_t len, uint64_t *words);
 /* copies n committed pairs starting at pair index `first` (commit order) back to host
  * memory in the record layout (bench + tests: checks the device generators) */
 int mrhbm_pool_read(mrhbm_ctx *, uint64_t first, uint64_t n, void *host_out);

@@ -520,6 +520,65 @@ int mrhbm_map_gen_zipf(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n, 
   return MRHBM_OK;
 }
 
+int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* words) {
+  if (!m || (!text && len)) return MRHBM_E_INVAL;
+  mrhbm_ctx* c = m->ctx;
+  if (words) *words = 0;
+  if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "wordcount needs a string-key ctx");
+  if (!len) return MRHBM_OK;
+  if (len >= (1ull << 38)) return fail(c, MRHBM_E_INVAL, "text too large for one call");
+  int rc = stage_flush(m);
+  if (rc) return rc;
+  const uint64_t nb = tok_blocks(len);
+  unsigned char* d_text = nullptr;
+  uint32_t *d_cnt = nullptr, *d_off = nullptr;
+  CU(c, cudaMalloc((void**)&d_text, len));
+  cudaError_t e = cudaMalloc((void**)&d_cnt, nb * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, (nb + 1) * 4);
+  auto cleanup = [&]() {
+    cudaFree(d_text);
+    cudaFree(d_cnt);
+    cudaFree(d_off);
+  };
+  if (e != cudaSuccess) {
+    cleanup();
+    cudaGetLastError();
+    return fail(c, MRHBM_E_NOMEM, "wordcount: %s", cudaGetErrorString(e));
+  }
+  uint64_t total = 0, off = 0;
+  do {
+    if ((e = cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(c->sb.counters ? c->sb.counters : c->d_small, 0, 4, c->stream)) != cudaSuccess) break;
+    launch_tok_count(d_text, len, d_cnt, c->stream);
+    // exclusive scan of the block counts (chunks of at most 2^30 blocks is far beyond any text here)
+    launch_exscan(d_cnt, (uint32_t)nb, d_off, nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small, 0, c->stream);
+    if ((e = cudaMemcpyAsync(c->h_small, c->d_small, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
+    total = c->h_small[0];
+    if (!total) break;
+    rc = pool_reserve(c, total, &off);
+    if (rc) break;
+    if ((e = cudaMemsetAsync(c->d_small + 1, 0, 4, c->stream)) != cudaSuccess) break;
+    launch_tok_emit(c->rb, d_text, len, d_off, (char*)c->pool + off * c->rb, c->d_small + 1, c->stream);
+    if ((e = cudaMemcpyAsync(c->h_small + 1, c->d_small + 1, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
+    if (c->h_small[1] & ERRF_KEYLEN) {
+      c->pool_used = off;  // nothing emitted
+      rc = fail(c, MRHBM_E_KEY, "a word is longer than the %d-byte key slot of this record class", c->kb - 1);
+      break;
+    }
+    add_range(m, off, total);
+  } while (0);
+  cleanup();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, MRHBM_E_CUDA, "wordcount: %s", cudaGetErrorString(e));
+  }
+  if (rc) return rc;
+  if (words) *words = total;
+  return MRHBM_OK;
+}
+
 int mrhbm_pool_read(mrhbm_ctx* c, uint64_t first, uint64_t n, void* host_out) {
   if (!c || (!host_out && n)) return MRHBM_E_INVAL;
   uint64_t skip = first, done = 0;

@@ -78,6 +78,68 @@ __global__ void k_gen_zipf32(uint4* dst, uint64_t seed, uint64_t start, uint64_t
 }
 
 // ============================================================================
+// device-side WordCount mapfn: text -> (word, 1) records
+// ============================================================================
+// Lua's %s in the C locale == isspace: ' ', \t \n \v \f \r (examples/WordCount/mapfn.lua:5)
+__device__ __forceinline__ bool tok_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+__device__ __forceinline__ bool tok_start(const unsigned char* t, uint64_t i) {
+  return !tok_space(t[i]) && (i == 0 || tok_space(t[i - 1]));
+}
+// one thread per byte, one count per 256-byte block
+__global__ void __launch_bounds__(256) k_tok_count(const unsigned char* __restrict__ t, uint64_t len,
+                                                   uint32_t* __restrict__ block_counts) {
+  uint64_t nb = (len + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    uint64_t i = blk * 256 + threadIdx.x;
+    int st = i < len && tok_start(t, i);
+    int c = __syncthreads_count(st);
+    if (threadIdx.x == 0) block_counts[blk] = (uint32_t)c;
+  }
+}
+template <int RB>
+__global__ void __launch_bounds__(256) k_tok_emit(const unsigned char* __restrict__ t, uint64_t len,
+                                                  const uint32_t* __restrict__ block_off, uint4* __restrict__ recs,
+                                                  uint32_t* __restrict__ flags) {
+  constexpr int KB = Rec<RB>::kKeyBytes;
+  __shared__ uint32_t wcount[8];
+  uint64_t nb = (len + 255) / 256;
+  for (uint64_t blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    uint64_t i = blk * 256 + threadIdx.x;
+    bool st = i < len && tok_start(t, i);
+    // rank of this word start inside the block: ballot prefix within the warp + warp totals
+    uint32_t m = __ballot_sync(0xffffffffu, st);
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = __popc(m & ((1u << lane) - 1u));
+    for (uint32_t w = 0; w < warp; w++) before += wcount[w];
+    __syncthreads();
+    if (!st) continue;
+    union {
+      unsigned char b[RB];
+      uint4 v[RB / 16];
+    } rec;
+#pragma unroll
+    for (int v = 0; v < RB / 16; v++) rec.v[v] = make_uint4(0, 0, 0, 0);
+    int l = 0;
+    while (i + l < len && !tok_space(t[i + l]) && l < KB) {
+      rec.b[l] = t[i + l];
+      l++;
+    }
+    if (l >= KB || (i + l < len && !tok_space(t[i + l]))) {  // does not fit (one zero byte must remain)
+      atomicOr(flags, (uint32_t)ERRF_KEYLEN);
+      l = KB - 1;
+      rec.b[KB - 1] = 0;
+    }
+    uint32_t one = 1u;
+    rec.b[KB] = (unsigned char)one;  // little-endian u32 value 1 (remaining value bytes are zero)
+    uint4* d = recs + ((uint64_t)block_off[blk] + before) * (RB / 16);
+#pragma unroll
+    for (int v = 0; v < RB / 16; v++) d[v] = rec.v[v];
+  }
+}
+
+// ============================================================================
 // histogram + scatter
 // ============================================================================
 template <int RB>
@@ -736,6 +798,24 @@ int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* 
                   uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift,
                   cudaStream_t s) {
   k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
+  return 1;
+}
+int launch_tok_count(const unsigned char* text, uint64_t len, uint32_t* block_counts, cudaStream_t s) {
+  if (!len) return 0;
+  uint64_t nb = (len + 255) / 256;
+  k_tok_count<<<(int)std::min<uint64_t>(nb, (uint64_t)g_sm_count * 16), 256, 0, s>>>(text, len, block_counts);
+  return 1;
+}
+int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint32_t* block_off, void* recs,
+                    uint32_t* flags, cudaStream_t s) {
+  if (!len || rb == 16) return 0;
+  uint64_t nb = (len + 255) / 256;
+  int grid = (int)std::min<uint64_t>(nb, (uint64_t)g_sm_count * 16);
+  switch (rb) {
+    case 32: k_tok_emit<32><<<grid, 256, 0, s>>>(text, len, block_off, (uint4*)recs, flags); break;
+    case 64: k_tok_emit<64><<<grid, 256, 0, s>>>(text, len, block_off, (uint4*)recs, flags); break;
+    default: k_tok_emit<128><<<grid, 256, 0, s>>>(text, len, block_off, (uint4*)recs, flags); break;
+  }
   return 1;
 }
 uint32_t combine_region_slack(int rb) { return (uint32_t)(kCombineSmem / rb) + kCombineThreads + 64; }

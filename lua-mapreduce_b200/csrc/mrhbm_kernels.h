@@ -83,7 +83,7 @@ MRHBM_HD inline uint32_t bin_count(const ShuffleBuffers& b, uint32_t bin) {
   return b.bin_off[(size_t)(bin + 1) << b.rep_shift] - b.bin_off[(size_t)bin << b.rep_shift];
 }
 enum { CNT_NBIG = 0, CNT_TICKET = 1, CNT_ERR = 2, CNT_TOTAL = 3, CNT_GBIG = 4 };
-enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2, ERRF_CAPACITY = 4 };
+enum { ERRF_SKEW = 1, ERRF_OVERFLOW = 2, ERRF_CAPACITY = 4, ERRF_KEYLEN = 8 };
 
 // every launcher returns the number of kernels it launched
 int launch_gen_u64(void* dst, uint64_t seed, uint64_t start, uint64_t n, cudaStream_t s);
@@ -101,6 +101,12 @@ int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, ui
 int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                          uint32_t stride, uint32_t* err_flags, cudaStream_t s);
 // map-side combine of one committed range into out (appends; *out_count is the running total)
+// device-side tokeniser: word starts per 256-byte block, then (after an exclusive scan of the
+// block counts) one record per word; *flags gets ERRF_KEYLEN when a word exceeds the key slot
+int launch_tok_count(const unsigned char* text, uint64_t len, uint32_t* block_counts, cudaStream_t s);
+int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint32_t* block_off, void* recs,
+                    uint32_t* flags, cudaStream_t s);
+inline uint64_t tok_blocks(uint64_t len) { return (len + 255) / 256; }
 // map-side combine of one committed range: CTA y appends to its own region out + y * region_cap
 // (records), seg_counts[y] is its running fill level (no global atomics on the append path)
 int launch_combine(int rb, const void* recs, uint64_t n, void* out, uint32_t region_cap, uint32_t* seg_counts,

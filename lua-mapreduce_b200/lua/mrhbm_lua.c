@@ -111,6 +111,17 @@ static int map_emit(lua_State *L) {
   lua_pushboolean(L, 1);
   return 1;
 }
+/* map:wordcount(text) -> number of words: the WordCount mapfn on the device
+ * (examples/WordCount/mapfn.lua:3-9), text is one Lua string (e.g. a whole file) */
+static int map_wordcount(lua_State *L) {
+  lmap *m = (lmap *)luaL_checkudata(L, 1, MAP_MT);
+  size_t len;
+  const char *t = luaL_checklstring(L, 2, &len);
+  uint64_t n = 0;
+  if (!m->h || mrhbm_map_wordcount(m->h, t, len, &n) != MRHBM_OK) return fail(L, m->ctx);
+  lua_pushnumber(L, (lua_Number)n);
+  return 1;
+}
 static int map_commit(lua_State *L) { /* job.lua:217-221: remove_file + build */
   lmap *m = (lmap *)luaL_checkudata(L, 1, MAP_MT);
   mrhbm_map *h = m->h;
@@ -191,7 +202,7 @@ static int ctx_groups(lua_State *L) {
 static const luaL_Reg ctx_methods[] = {{"map_begin", ctx_map_begin}, {"shuffle", ctx_shuffle},
                                        {"partitions", ctx_partitions}, {"groups", ctx_groups},
                                        {"reset", ctx_reset}, {"__gc", ctx_gc}, {NULL, NULL}};
-static const luaL_Reg map_methods[] = {{"emit", map_emit}, {"commit", map_commit},
+static const luaL_Reg map_methods[] = {{"emit", map_emit}, {"wordcount", map_wordcount}, {"commit", map_commit},
                                        {"abort", map_abort}, {"__gc", map_abort}, {NULL, NULL}};
 static const luaL_Reg mod_funcs[] = {{"new", l_new}, {NULL, NULL}};
 

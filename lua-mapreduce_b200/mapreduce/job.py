@@ -52,16 +52,24 @@ class Job:
     # ---- job.lua:166-227
     def _map(self):
         cfg, ctx = self.cfg, self.board.ctx
-        mapfn = get_func(cfg["mapfn"], "mapfn", None).mapfn  # init(nil): the job.lua:369 quirk
+        mod = get_func(cfg["mapfn"], "mapfn", None)  # init(nil): the job.lua:369 quirk
+        mapfn = mod.mapfn
         m = ctx.map_begin(self.get_id())
         try:
+            if getattr(mod, "hbm_mapfn", None) == "wordcount_file" and hasattr(m, "wordcount"):
+                # declared built-in (same opt-in pattern as hbm_reducefn): the job value is a file
+                # path, the device tokenises its bytes exactly like examples/WordCount/mapfn.lua:3-9
+                with open(self.doc["value"], "rb") as fh:
+                    m.wordcount(fh.read())
+                mapfn = None
             if cfg["hbm"]["key_kind"] == "u64":
                 def emit(key, value=1):
                     m.emit(int(key), int(value))
             else:
                 def emit(key, value=1):
                     m.emit(_key_bytes(key), int(value))
-            mapfn(self.get_id(), self.doc["value"], emit)  # job.lua:182
+            if mapfn is not None:
+                mapfn(self.get_id(), self.doc["value"], emit)  # job.lua:182
             self.board.mark(self.doc, STATUS.FINISHED, finished_time=time.time())
             m.commit()  # atomic publish; replaces an earlier attempt (job.lua:217-221)
         except BaseException:

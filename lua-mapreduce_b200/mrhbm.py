@@ -52,7 +52,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "mrhbm_abi_version", "mrhbm_init", "mrhbm_destroy", "mrhbm_last_error", "mrhbm_record_bytes",
     "mrhbm_host_alloc", "mrhbm_host_free", "mrhbm_map_begin", "mrhbm_emit_str", "mrhbm_emit_u64",
-    "mrhbm_emit_batch", "mrhbm_emit_device", "mrhbm_map_gen_u64", "mrhbm_map_gen_zipf", "mrhbm_pool_read", "mrhbm_map_commit",
+    "mrhbm_emit_batch", "mrhbm_emit_device", "mrhbm_map_gen_u64", "mrhbm_map_gen_zipf", "mrhbm_map_wordcount", "mrhbm_pool_read", "mrhbm_map_commit",
     "mrhbm_map_abort", "mrhbm_shuffle", "mrhbm_partitions", "mrhbm_groups_open", "mrhbm_groups_next",
     "mrhbm_groups_close", "mrhbm_result_info_get", "mrhbm_result_copy", "mrhbm_checksum_input",
     "mrhbm_checksum_result", "mrhbm_stats_get", "mrhbm_reset", "mrhbm_comm_unique_id", "mrhbm_comm_init",
@@ -97,6 +97,7 @@ def load(build_if_missing=True):
     sig("mrhbm_emit_device", i, vp, vp, sz)
     sig("mrhbm_map_gen_u64", i, vp, u64, u64, u64)
     sig("mrhbm_map_gen_zipf", i, vp, u64, u64, u64, vp, u64)
+    sig("mrhbm_map_wordcount", i, vp, C.c_char_p, sz, C.POINTER(u64))
     sig("mrhbm_pool_read", i, vp, u64, u64, vp)
     sig("mrhbm_map_commit", i, vp)
     sig("mrhbm_map_abort", None, vp)
@@ -156,6 +157,12 @@ class Map:
     def gen_zipf(self, seed, start, n, table):
         t = np.ascontiguousarray(table, dtype=np.uint64)
         self.ctx._chk(self.ctx.L.mrhbm_map_gen_zipf(self.h, seed, start, n, t.ctypes.data, t.size))
+
+    def wordcount(self, text: bytes):
+        """device-side WordCount mapfn over a text buffer; returns the number of words emitted"""
+        n = C.c_uint64()
+        self.ctx._chk(self.ctx.L.mrhbm_map_wordcount(self.h, text, len(text), C.byref(n)))
+        return n.value
 
     def commit(self):
         h, self.h = self.h, None

@@ -347,3 +347,42 @@ def test_group_only_mode_for_general_reducers():
         ctx.shuffle()
         got = {int.from_bytes(k, "big"): sorted(v) for p in ctx.partitions() for k, v in ctx.groups(p)}
         assert got[7] == list(range(5000)) and len(got) == 301 and got[100] == [5000]
+
+
+def test_device_tokeniser_wordcount_golden(golden_vectors, golden_wordcount):
+    """device-side mapfn (examples/WordCount/mapfn.lua:3-9): text -> (word, 1) with C-locale isspace"""
+    seps = [b" ", b"\n", b"\t", b"  \n", b"\r\n", b"\v", b"\f "]
+    with mrhbm.Ctx(mrhbm.KEY_STR, 15, mrhbm.PART_FNV_LUA, max_key_bytes=golden_vectors["max_key_len"]) as ctx:
+        total = 0
+        for job in range(4):
+            toks = expand_tokens(golden_wordcount, job)
+            text = b"\n \t" + b"".join(t + seps[i % len(seps)] for i, t in enumerate(toks[:-1])) + toks[-1]
+            m = ctx.map_begin(job + 1)
+            total += m.wordcount(text)
+            m.wordcount(b"")
+            m.wordcount(b" \n\t ")
+            m.commit()
+        assert total == golden_vectors["tokens"]
+        ctx.shuffle()
+        got = {k: (p, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p)}
+        assert got == {k: (p, sum(c)) for k, p, c in golden_wordcount}
+    # a longer stream against the oracle's tokeniser + naive count
+    table = synth.zipf_table(1 << 12)
+    recs = O.gen_zipf_rec32(SEED, 0, 300_000, table)
+    words = [bytes(r[:28]).rstrip(b"\0") for r in recs]
+    text = b"".join(w + (b"\n" if i % 25 == 24 else b" ") for i, w in enumerate(words))
+    ntok, wc = O.naive_wordcount([text])
+    with mrhbm.Ctx(mrhbm.KEY_STR, 15, mrhbm.PART_FNV_LUA) as ctx:
+        m = ctx.map_begin("t")
+        assert m.wordcount(text) == ntok == 300_000
+        m.commit()
+        ctx.shuffle()
+        assert sorted((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p)) == wc
+        m = ctx.map_begin("long")
+        m.emit(b"ok", 1)
+        with pytest.raises(mrhbm.MrhbmError) as err:
+            m.wordcount(b"fits " + b"x" * 28 + b" tail")
+        assert err.value.code == -4
+        m.commit()
+        ctx.shuffle()
+        assert dict((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p))[b"ok"] == 1

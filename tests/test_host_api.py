@@ -168,6 +168,19 @@ def test_broken_map_job_is_retried_then_failed(corpus):
 
 
 @pytest.mark.gpu
+def test_declared_device_mapfn(corpus, golden_wordcount):
+    """mapfn module declaring hbm_mapfn = "wordcount_file": the device tokenises the files"""
+    CONFIGS["device-mapfn"] = dict(mapfn=WC + ".mapfn_device", reducefn=WC + ".reducefn")
+    try:
+        s = run_config("device-mapfn", "gpu-device-mapfn")
+    finally:
+        del CONFIGS["device-mapfn"]
+    assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
+    assert s.stats["shuffle"]["pairs"] == 4989
+    s.board.ctx.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_wordcount_configs_on_gpu(name, corpus, golden_wordcount):
     s = run_config(name, "gpu-" + name)
