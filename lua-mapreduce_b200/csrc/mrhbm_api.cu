@@ -1129,7 +1129,25 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+      {
+        // send buffer (destination-major exact layout) through the two-level coalesced split
+        uint32_t F = 1;
+        while ((uint64_t)F * F < B) F <<= 1;
+        uint32_t C1 = (uint32_t)((B + F - 1) / F);
+        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
+          rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
+          if (rc) return rc;
+          CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
+          CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+          for (auto& r : live)
+            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bp, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
+                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
+          st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
+                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s);
+        } else {
+          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+        }
+      }
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaGetLastError());
       CU(c, cudaStreamSynchronize(s));
