@@ -270,18 +270,26 @@ def main():
     g_local = info.groups
     combined = a.workload == "zipf32"  # ctx runs the map-side combiner for this workload
     n2 = info.pairs_recv if combined else n  # N' = pairs that survive the combiner
-    stage_bytes = {  # per GPU, SURVEY 8d: combine N R + N' R, hash-partition N' R + N' R, sort N' R + N' R, reduce N' R + U R
-        "k_scatter": 2 * n2 * R,          # the hash-partition stage's read + write (k_hist is overhead)
-        ("k_agg_bins" if combined else "k_sort_reduce"): 3 * n2 * R + g_local * R,
-    }
+    # per GPU, SURVEY 8d: combine N R + N' R, hash-partition N' R + N' R, sort N' R + N' R, reduce N' R + U R.
+    # The hash-partition stage is one kernel (k_scatter) or, in the default single-GPU layout, the two
+    # levels of k_split, each charged half of the stage.
+    sort_name = "k_agg_bins" if combined else "k_sort_reduce"
+    split = world == 1 and not combined and dev_ms["ms_plan"] > 0.2
+    kernels = {}
     if combined:
-        stage_bytes["k_combine"] = n * R + n2 * R
+        kernels["k_combine"] = (n * R + n2 * R, dev_ms["ms_combine"])
+    if split:
+        kernels["k_split_level1"] = (n2 * R, dev_ms["ms_plan"])
+        kernels["k_split_level2"] = (n2 * R, dev_ms["ms_scatter"])
+    else:
+        kernels["k_scatter"] = (2 * n2 * R, dev_ms["ms_scatter"])
+        if dev_ms["ms_hist"] > 0.05:
+            kernels["k_hist(overhead)"] = (0, dev_ms["ms_hist"])
+    kernels[sort_name] = (3 * n2 * R + g_local * R, dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"])
+    stage_bytes = {k: v[0] for k, v in kernels.items()}
+    k_ms = {k: v[1] for k, v in kernels.items()}
     pipe_bytes = sum(stage_bytes.values())
-    k_ms = {"k_scatter": dev_ms["ms_scatter"],
-            ("k_agg_bins" if combined else "k_sort_reduce"): dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"]}
-    if combined:
-        k_ms["k_combine"] = dev_ms["ms_combine"]
-    dom = max(k_ms, key=k_ms.get)
+    dom = max((k for k in k_ms if stage_bytes[k]), key=k_ms.get)
     ach = stage_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
@@ -295,6 +303,10 @@ def main():
                      "achieved": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9,
                      "frac": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9 / peak},
         "stages_ms": dev_ms,
+        "kernels": {k: {"algorithmic_bytes": stage_bytes[k], "ms": k_ms[k],
+                        "achieved": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9) if k_ms[k] > 0 else None,
+                        "frac": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak) if k_ms[k] > 0 else None}
+                    for k in kernels},
     }
 
     # ---- e2e through the public API from pinned host buffers
