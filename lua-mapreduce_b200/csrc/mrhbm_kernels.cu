@@ -299,15 +299,15 @@ struct SplitArgs {
   uint32_t B;
 };
 
-template <int RB>
-__global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinParams bp) {
+template <int RB, int THREADS, int TILE_BYTES>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_split(SplitArgs a, BinParams bp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = Rec<RB>;
-  constexpr int T = kSplitTileBytes / RB;            // records per tile
-  constexpr int U = T / kSplitThreads;               // records per thread
-  static_assert(T % kSplitThreads == 0, "tile");
+  constexpr int T = TILE_BYTES / RB;            // records per tile
+  constexpr int U = T / THREADS;               // records per thread
+  static_assert(T % THREADS == 0, "tile");
   uint4* stage = (uint4*)smem_raw;                   // T records in bin order
-  uint16_t* pos_sub = (uint16_t*)(smem_raw + kSplitTileBytes);  // bin of staged position
+  uint16_t* pos_sub = (uint16_t*)(smem_raw + TILE_BYTES);  // bin of staged position
   __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins + 1], sgb[kSplitMaxBins];
   const uint32_t tid = threadIdx.x;
   const uint4* src = a.src;
@@ -334,16 +334,16 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint64_t t0 = tile * T;
     const uint32_t tn = (uint32_t)((n - t0) < (uint64_t)T ? (n - t0) : (uint64_t)T);
-    for (uint32_t b = tid; b < a.nbins; b += kSplitThreads) scnt[b] = 0;
+    for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
     __syncthreads();
     uint32_t w[U][R::kWords];
     uint32_t sub[U], rk[U];
 #pragma unroll
     for (int k = 0; k < U; k++)
-      if (tid + k * kSplitThreads < tn) load_rec<RB>(src + (t0 + tid + k * kSplitThreads) * R::kVec, w[k]);
+      if (tid + k * THREADS < tn) load_rec<RB>(src + (t0 + tid + k * THREADS) * R::kVec, w[k]);
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      if (tid + k * kSplitThreads < tn) {
+      if (tid + k * THREADS < tn) {
         uint32_t fine = bin_of<RB>(w[k], bp, nullptr);
         sub[k] = a.level == 1 ? fine >> a.logF : fine & (a.F - 1u);
         rk[k] = atomicAdd(scnt + sub[k], 1u);
@@ -352,30 +352,39 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
     __syncthreads();
     // exclusive scan of the per-bin counts (nbins <= 1024: two items per thread) + global claims
     {
-      uint32_t v0 = 2 * tid < a.nbins ? scnt[2 * tid] : 0u, v1 = 2 * tid + 1 < a.nbins ? scnt[2 * tid + 1] : 0u;
-      uint32_t s = v0 + v1, incl = s;
+      constexpr int IPT = kSplitMaxBins / THREADS;  // bins per thread in the scan
+      uint32_t v[IPT], s = 0;
+#pragma unroll
+      for (int i = 0; i < IPT; i++) {
+        v[i] = IPT * tid + i < a.nbins ? scnt[IPT * tid + i] : 0u;
+        s += v[i];
+      }
+      uint32_t incl = s;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if ((tid & 31) >= (uint32_t)d) incl += t;
       }
-      __shared__ uint32_t wsum[kSplitThreads / 32];
+      __shared__ uint32_t wsum[THREADS / 32];
       if ((tid & 31) == 31) wsum[tid >> 5] = incl;
       __syncthreads();
-      if (tid < 32) {  // exclusive scan of the 16 warp sums
-        uint32_t ws = tid < kSplitThreads / 32 ? wsum[tid] : 0u, wi = ws;
+      if (tid < 32) {  // exclusive scan of the warp sums
+        uint32_t ws = tid < THREADS / 32 ? wsum[tid] : 0u, wi = ws;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
           if (tid >= (uint32_t)d) wi += t;
         }
-        if (tid < kSplitThreads / 32) wsum[tid] = wi - ws;
+        if (tid < THREADS / 32) wsum[tid] = wi - ws;
       }
       __syncthreads();
       uint32_t ex = wsum[tid >> 5] + incl - s;
-      if (2 * tid < a.nbins) soff[2 * tid] = ex;
-      if (2 * tid + 1 < a.nbins) soff[2 * tid + 1] = ex + v0;
-      for (uint32_t b = tid; b < a.nbins; b += kSplitThreads) {
+#pragma unroll
+      for (int i = 0; i < IPT; i++) {
+        if (IPT * tid + i < a.nbins) soff[IPT * tid + i] = ex;
+        ex += v[i];
+      }
+      for (uint32_t b = tid; b < a.nbins; b += THREADS) {
         uint32_t c = scnt[b];
         uint32_t g = 0;
         if (c) {
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
     // records into bin order inside the tile
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      if (tid + k * kSplitThreads < tn) {
+      if (tid + k * THREADS < tn) {
         uint32_t p = soff[sub[k]] + rk[k];
         pos_sub[p] = (uint16_t)sub[k];
 #pragma unroll
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split(SplitArgs a, BinPara
     }
     __syncthreads();
     // copy out: consecutive staged positions of one bin are consecutive in global memory
-    for (uint32_t p = tid; p < tn; p += kSplitThreads) {
+    for (uint32_t p = tid; p < tn; p += THREADS) {
       uint32_t b = pos_sub[p];
       uint32_t slot = sgb[b] + (p - soff[b]);
       uint4* d;
@@ -751,13 +760,15 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
+  e = cudaFuncSetAttribute(k_sort_reduce_u64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
+  if (e != cudaSuccess) return e;
 #define CFGC(RB)                                                                                       \
   e = cudaFuncSetAttribute(k_combine<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
   if (e != cudaSuccess) return e;
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
 #undef CFGC
 #define CFGS(RB)                                                                                         \
-  e = cudaFuncSetAttribute(k_split<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+  e = cudaFuncSetAttribute(k_split<RB, 512, kSplitTileBytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            kSplitTileBytes + (kSplitTileBytes / RB) * (int)sizeof(uint16_t));              \
   if (e != cudaSuccess) return e;
   CFGS(16) CFGS(32) CFGS(64) CFGS(128)
@@ -871,7 +882,9 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
   while ((1u << a.logF) < F) a.logF++;
   a.ctr_shift = bp.ctr_shift;
   a.err_flags = err_flags;
+  const int ctas = 2 * g_sm_count;
   size_t smem = kSplitTileBytes + (kSplitTileBytes / rb) * sizeof(uint16_t);
+#define SPLIT_LAUNCH(GRID) DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));
   if (!level2) {
     if (!n) return 0;
     a.src = (const uint4*)recs;
@@ -882,9 +895,9 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
     a.capacity = (uint32_t)std::min<uint64_t>((uint64_t)F * cap, 0xffffffffull);
     a.nbins = C1;
     a.level = 1;
-    dim3 grid(2 * g_sm_count);
-    if (bp.seg_counts) grid = dim3((2 * g_sm_count + bp.nseg - 1) / bp.nseg, bp.nseg);
-    DISPATCH_RB(rb, (k_split<RB><<<grid, kSplitThreads, smem, s>>>(a, bp)));
+    dim3 grid(ctas);
+    if (bp.seg_counts) grid = dim3((ctas + bp.nseg - 1) / bp.nseg, bp.nseg);
+    SPLIT_LAUNCH(grid)
   } else {
     a.src = (const uint4*)l1;
     a.seg_counts = cursor1;
@@ -895,15 +908,33 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
     a.capacity = cap;
     a.nbins = F;
     a.level = 2;
-    int x = (2 * g_sm_count + (int)C1 - 1) / (int)C1;
-    DISPATCH_RB(rb, (k_split<RB><<<dim3(x < 1 ? 1 : x, C1), kSplitThreads, smem, s>>>(a, bp)));
+    // x CTAs per coarse region, chosen so that x*C1 CTAs fill whole waves of `ctas` resident CTAs
+    // (C1 = 220, x = 2 ran 440 CTAs = 1.49 waves on 296 slots: 26 % of the second wave idle)
+    int x = 1;
+    double best = 0;
+    const uint64_t tiles_per_region = ((uint64_t)F * cap * rb + kSplitTileBytes - 1) / kSplitTileBytes;
+    for (int cand = 1; cand <= 16 && (uint64_t)cand <= std::max<uint64_t>(1, tiles_per_region / 4); cand++) {
+      uint64_t total = (uint64_t)cand * C1, waves = (total + ctas - 1) / ctas;
+      double eff = (double)total / (double)(waves * ctas);
+      if (eff > best + 0.02) {
+        best = eff;
+        x = cand;
+      }
+    }
+    SPLIT_LAUNCH(dim3(x, C1))
   }
+#undef SPLIT_LAUNCH
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s) {
   int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
   if (grid < 1) grid = 1;
+  // u64 keys in key-ordered sub-bins read from one segment: the register-pipelined variant
+  if (rb == 16 && b.hint_S > 1 && (b.stride || b.nseg == 1) && !getenv("MRHBM_NO_PIPELINED_SORT")) {
+    k_sort_reduce_u64<<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+    return 1;
+  }
   DISPATCH_RB(rb, (k_sort_reduce<RB><<<grid, kSortThreads, sort_smem_bytes(RB), s>>>(b, B, cap)));
   return 1;
 }

@@ -467,6 +467,244 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
   }
 }
 
+// ---- u64 keys, key-ordered sub-bins, one source segment: the software-pipelined variant ----
+//
+// Same algorithm as counting_path, restructured around the two things the profile of
+// k_sort_reduce<16> showed (ncu source view: 36 % of the stall samples wait at barriers, 15 % on
+// the bin load): the records of a bin go from global memory into REGISTERS (4 x 16 B per thread),
+// are counted from there and land directly in bucket order, and the loads of the CTA's next bin are
+// issued right after that, so they fly while the current bin is ranked, scanned and written.
+// Bins are assigned round-robin (no ticket, no descriptor barrier); 7 barriers per bin instead of 14.
+
+// exclusive scan of a[0 .. 8*blockDim.x) in place, 8 consecutive words per thread; returns the total
+__device__ __forceinline__ uint32_t block_exscan_u32x8(uint32_t* a) {
+  __shared__ uint32_t scratch[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint4 x = ((const uint4*)a)[2 * tid], y = ((const uint4*)a)[2 * tid + 1];
+  const uint32_t s = x.x + x.y + x.z + x.w + y.x + y.y + y.z + y.w;
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  // every warp scans the (<= 32) warp totals itself: no second barrier
+  uint32_t w = lane < nwarps ? scratch[lane] : 0u, wi = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= (uint32_t)d) wi += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+  uint32_t run = __shfl_sync(0xffffffffu, wi - w, warp) + incl - s;
+  uint4 ox, oy;
+  ox.x = run; run += x.x;
+  ox.y = run; run += x.y;
+  ox.z = run; run += x.z;
+  ox.w = run; run += x.w;
+  oy.x = run; run += y.x;
+  oy.y = run; run += y.y;
+  oy.z = run; run += y.z;
+  oy.w = run;
+  ((uint4*)a)[2 * tid] = ox;
+  ((uint4*)a)[2 * tid + 1] = oy;
+  __syncthreads();
+  return total;
+}
+// exclusive scan of the u16 flags a[0 .. 4*blockDim.x) in place (entries at index >= n count as 0)
+__device__ __forceinline__ uint32_t block_exscan_u16x4(uint16_t* a, uint32_t n) {
+  __shared__ uint32_t scratch[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint2 x = ((const uint2*)a)[tid];
+  uint32_t v0 = x.x & 0xffffu, v1 = x.x >> 16, v2 = x.y & 0xffffu, v3 = x.y >> 16;
+  const uint32_t i0 = 4 * tid;
+  v0 = i0 < n ? v0 : 0u;
+  v1 = i0 + 1 < n ? v1 : 0u;
+  v2 = i0 + 2 < n ? v2 : 0u;
+  v3 = i0 + 3 < n ? v3 : 0u;
+  const uint32_t s = v0 + v1 + v2 + v3;
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  uint32_t w = lane < nwarps ? scratch[lane] : 0u, wi = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= (uint32_t)d) wi += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+  const uint32_t e0 = __shfl_sync(0xffffffffu, wi - w, warp) + incl - s;
+  const uint32_t e1 = e0 + v0, e2 = e1 + v1, e3 = e2 + v2;
+  ((uint2*)a)[tid] = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuffers b, uint32_t B, uint32_t cap) {
+  constexpr int RB = 16;
+  constexpr uint32_t CAP = kCapBytes / RB, NB = 2 * CAP, T = kSortThreads;
+  constexpr int ITEMS = CAP / T;
+  static_assert(ITEMS * T == CAP && NB == 8 * T && CAP == 4 * T, "tile shape");
+  constexpr int kLogNB = 31 - __builtin_clz(NB);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortSmem sm = carve(smem_raw, RB);
+  const uint32_t tid = threadIdx.x;
+  uint32_t* bcnt = sm.cnt;
+  uint16_t* heads = (uint16_t*)sm.red + 4 * 80;
+  const uint4* src = (const uint4*)b.src;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  ((uint4*)bcnt)[2 * tid] = zero4;
+  ((uint4*)bcnt)[2 * tid + 1] = zero4;
+
+  uint32_t bin = blockIdx.x;
+  uint64_t off = 0;
+  uint32_t cnt = 0;
+  if (bin < B) {
+    off = bin_start(b, bin);
+    cnt = bin_count(b, bin);
+  }
+  uint4 rg[ITEMS];
+  if (cnt <= cap) {
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+      if (tid + k * T < cnt) rg[k] = ldg_stream(src + off + tid + k * T);
+  }
+  __syncthreads();
+  while (bin < B) {
+    // descriptor of the CTA's next bin: the loads are in flight until after the move
+    const uint32_t nbin = bin + gridDim.x;
+    uint64_t noff = 0;
+    uint32_t ncnt = 0;
+    if (nbin < B) {
+      noff = bin_start(b, nbin);
+      ncnt = bin_count(b, nbin);
+    }
+    if (cnt == 0 || cnt > cap) {  // empty, or oversized (k_big_bins): nothing was loaded
+      if (cnt == 0 && tid == 0) b.ucount[bin] = 0;
+    } else {
+      ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
+      // sub = mulhi(key, S): keys of sub-bin `sub` lie in [sub*q, (sub+1)*(q+1)]
+      const uint32_t sub = bin % b.hint_S;
+      const uint64_t pmin = (uint64_t)sub * b.hint_q;
+      const uint64_t pmax = sub + 1 == b.hint_S ? ~0ull : (uint64_t)(sub + 1) * (b.hint_q + 1);
+      const uint64_t range = pmax - pmin;
+      const int bits = range ? 64 - __clzll((long long)range) : 0;
+      const int sh = bits > kLogNB ? bits - kLogNB : 0;
+      uint32_t br[ITEMS];
+      int over = 0;
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++) {
+        br[k] = 0;
+        if (tid + k * T < cnt) {
+          uint64_t key = (uint64_t)rg[k].x | ((uint64_t)rg[k].y << 32);
+          uint32_t bk = (uint32_t)((key - pmin) >> sh) & (NB - 1);
+          uint32_t r = atomicAdd(bcnt + bk, 1u);
+          br[k] = (bk << 4) | (r & 15u);
+          if (r >= kFixMax) over = 1;
+        }
+      }
+      if (__syncthreads_or(over)) {
+        // a bucket with more than kFixMax records (heavy duplicates / clustered keys): the general
+        // kernel body on the same records
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++)
+          if (tid + k * T < cnt) sm.rec[tid + k * T] = rg[k];
+        __syncthreads();
+        uint32_t g = process_loaded<RB, MODE_FINAL>(sm, cnt, out, false);
+        if (tid == 0) b.ucount[bin] = g;
+        __syncthreads();
+        ((uint4*)bcnt)[2 * tid] = zero4;
+        ((uint4*)bcnt)[2 * tid + 1] = zero4;
+      } else {
+        block_exscan_u32x8(bcnt);  // bcnt[bk] = first position of bucket bk
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++)
+          if (tid + k * T < cnt) sm.rec2[bcnt[br[k] >> 4] + (br[k] & 15u)] = rg[k];
+        __syncthreads();
+        // the registers are free: start loading the next bin
+        if (ncnt <= cap) {
+#pragma unroll
+          for (int k = 0; k < ITEMS; k++)
+            if (tid + k * T < ncnt) rg[k] = ldg_stream(src + noff + tid + k * T);
+        }
+        // every position of the bucket-ordered buffer ranks itself among its bucket mates
+        uint32_t fpos[ITEMS];
+        uint64_t hsum[ITEMS], hkey[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+          const uint32_t j = tid + k * T;
+          fpos[k] = 0xffffffffu;
+          hsum[k] = 0;
+          hkey[k] = 0;
+          if (j < cnt) {
+            const uint4 me = sm.rec2[j];
+            const uint64_t key = (uint64_t)me.x | ((uint64_t)me.y << 32);
+            const uint32_t bk = (uint32_t)((key - pmin) >> sh) & (NB - 1);
+            const uint32_t s0 = bcnt[bk], e0 = (bk + 1 < NB) ? bcnt[bk + 1] : cnt;
+            uint32_t rank = 0, head = 1;
+            uint64_t sum = (uint64_t)me.z | ((uint64_t)me.w << 32);
+            for (uint32_t m = s0; m < e0; m++) {
+              if (m == j) continue;
+              const uint2 qk = *(const uint2*)(sm.rec2 + m);
+              const uint64_t q = (uint64_t)qk.x | ((uint64_t)qk.y << 32);
+              if (q < key) {
+                rank++;
+              } else if (q == key) {
+                if (m < j) {
+                  rank++;
+                  if (!out.no_reduce) head = 0;
+                } else if (!out.no_reduce) {
+                  const uint2 qv = *((const uint2*)(sm.rec2 + m) + 1);
+                  sum += (uint64_t)qv.x | ((uint64_t)qv.y << 32);
+                }
+              }
+            }
+            heads[s0 + rank] = (uint16_t)head;
+            fpos[k] = head ? s0 + rank : 0xffffffffu;
+            hsum[k] = sum;
+            hkey[k] = key;
+          }
+        }
+        __syncthreads();
+        const uint32_t groups = block_exscan_u16x4(heads, cnt);  // heads[f] = groups before sorted slot f
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+          if (fpos[k] != 0xffffffffu) {
+            const uint64_t o = out.base + heads[fpos[k]];
+            ((uint64_t*)out.keys)[o] = hkey[k];
+            out.sums[o] = hsum[k];
+          }
+        }
+        ((uint4*)bcnt)[2 * tid] = zero4;
+        ((uint4*)bcnt)[2 * tid + 1] = zero4;
+        if (tid == 0) b.ucount[bin] = groups;
+        bin = nbin;
+        off = noff;
+        cnt = ncnt;
+        __syncthreads();
+        continue;
+      }
+    }
+    // no prefetch happened on this path
+    bin = nbin;
+    off = noff;
+    cnt = ncnt;
+    if (cnt <= cap) {
+#pragma unroll
+      for (int k = 0; k < ITEMS; k++)
+        if (tid + k * T < cnt) rg[k] = ldg_stream(src + off + tid + k * T);
+    }
+    __syncthreads();
+  }
+}
+
 // Duplicate-heavy input (a combiner is declared): a bin holds many records but few distinct keys.
 // Stream the bin through an open-addressing table in shared memory (one slot per distinct key,
 // value word = 1 + running sum), then sort the distinct keys and write the run.  The table

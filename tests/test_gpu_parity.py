@@ -90,6 +90,30 @@ def test_u64_duplicates_and_hot_key():
         check_vs_oracle_u64(ctx, keys, vals, P)
 
 
+def test_u64_sparse_duplicates_inside_key_ordered_bins():
+    """mostly unique keys plus a few keys repeated 9..40 times: the bins stay balanced (one pass, key-ordered
+    sub-bins, pipelined sort kernel) but some buckets exceed the rank-among-mates limit, so those bins take
+    the general sort inside the same kernel"""
+    rng = np.random.default_rng(11)
+    n0, P = 500_000, 16
+    keys, vals = O.gen_u64(SEED, 4242, n0)
+    reps = rng.integers(9, 41, 300)
+    dup = np.repeat(keys[rng.integers(0, n0, 300)], reps)
+    keys = np.concatenate([keys, dup])
+    vals = np.concatenate([vals, rng.integers(0, 1 << 16, dup.size).astype(np.uint32)])
+    perm = rng.permutation(keys.size)
+    keys, vals = keys[perm], vals[perm]
+    for flags in (0, mrhbm.F_NO_OPTIMISTIC):
+        with mrhbm.Ctx(mrhbm.KEY_U64, P, flags=flags) as ctx:
+            m = ctx.map_begin("sparse-dups")
+            m.emit_batch(u64_records(keys, vals))
+            m.commit()
+            ctx.shuffle()
+            st = ctx.stats()
+            assert st["attempts"] == 1 and st["sub_bins"] > 1 and ctx.result_info().sorted == 1
+            check_vs_oracle_u64(ctx, keys, vals, P)
+
+
 def test_u64_clustered_keys_fall_back_to_runs():
     """sequential integers: top key bits are constant, so key-ordered sub-bins cannot balance"""
     n, P = 300_000, 4
