@@ -432,6 +432,205 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_split(SplitArgs a, 
   }
 }
 
+// ---- k_split_tma: the same tile split, fed by the bulk-copy engine ------------------------------
+// ncu source view of k_split: ~40 % of the stall samples wait on the tile's global loads (each
+// thread loads 8 records into registers and needs them at once) and the staging pass moves every
+// record through shared memory a second time.  Here one thread issues ONE cp.async.bulk per tile
+// (global -> shared, completion on an mbarrier), double-buffered, so tile t+1 lands while tile t
+// is split; the tile is not re-staged: a u16 permutation says which raw record goes to which
+// output position, and the copy-out reads the raw tile through it.
+constexpr int kTmaSplitThreads = 512;
+constexpr int kTmaTileBytes = 40 * 1024;
+__host__ __device__ constexpr size_t tma_split_smem(int rb) {
+  return 2 * (size_t)kTmaTileBytes + 2 * (size_t)(kTmaTileBytes / rb) * sizeof(uint16_t);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one thread: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of dst are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kTmaSplitThreads, 2) k_split_tma(SplitArgs a, BinParams bp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using R = Rec<RB>;
+  constexpr int THREADS = kTmaSplitThreads;
+  constexpr int T = kTmaTileBytes / RB;              // records per tile
+  constexpr int U = (T + THREADS - 1) / THREADS;     // records per thread
+  constexpr int IPT = kSplitMaxBins / THREADS;       // bins per thread in the scan
+  uint4* raw0 = (uint4*)smem_raw;
+  uint4* raw1 = (uint4*)(smem_raw + kTmaTileBytes);
+  uint16_t* perm = (uint16_t*)(smem_raw + 2 * kTmaTileBytes);  // output position -> raw index
+  uint16_t* pos_sub = perm + T;                                 // output position -> bin
+  __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins], sgb[kSplitMaxBins];
+  __shared__ uint32_t wsum[THREADS / 32];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint4* src = a.src;
+  uint64_t n = a.n;
+  uint32_t coarse = 0;
+  if (a.level == 1 && bp.seg_counts) {  // segmented source (the combiner's per-CTA regions)
+    src += (size_t)blockIdx.y * bp.seg_stride * R::kVec;
+    n = bp.seg_counts[blockIdx.y];
+  }
+  if (a.level == 2) {
+    coarse = blockIdx.y;
+    if (a.base_off) {  // exact: the coarse region is the union of its fine bins
+      uint32_t f0 = coarse * a.F, f1 = f0 + a.F < a.B ? f0 + a.F : a.B;
+      uint32_t o0 = a.base_off[(size_t)f0 << a.rep_shift], o1 = a.base_off[(size_t)f1 << a.rep_shift];
+      src += (size_t)o0 * R::kVec;
+      n = o1 - o0;
+    } else {
+      src += (size_t)coarse * a.seg_stride * R::kVec;
+      uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
+      n = c < a.seg_stride ? c : a.seg_stride;
+    }
+  }
+  const uint64_t ntiles = (n + T - 1) / T;
+  auto tile_len = [&](uint64_t tile) -> uint32_t {
+    uint64_t t0 = tile * T;
+    return (uint32_t)((n - t0) < (uint64_t)T ? (n - t0) : (uint64_t)T);
+  };
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t b = tid; b < kSplitMaxBins; b += THREADS) scnt[b] = 0;
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < ntiles)
+    bulk_load(raw0, src + (uint64_t)blockIdx.x * T * R::kVec, tile_len(blockIdx.x) * RB, &mbar[0]);
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const uint32_t tn = tile_len(tile);
+    const uint4* raw = (it & 1) ? raw1 : raw0;
+    // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
+    const uint64_t next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles)
+      bulk_load((it & 1) ? raw0 : raw1, src + next * T * R::kVec, tile_len(next) * RB, &mbar[(it & 1) ^ 1]);
+    mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+    uint32_t sub[U], rk[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tn) {
+        uint32_t fine = bin_of<RB>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr);
+        sub[k] = a.level == 1 ? fine >> a.logF : fine & (a.F - 1u);
+        rk[k] = atomicAdd(scnt + sub[k], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the per-bin counts; the thread that owns a bin also claims its global space
+    uint32_t v[IPT], ex[IPT], g[IPT], s = 0;
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      v[i] = IPT * tid + i < a.nbins ? scnt[IPT * tid + i] : 0u;
+      s += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      g[i] = 0;
+      const uint32_t b = IPT * tid + i;
+      if (v[i]) {
+        const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+        g[i] = atomicAdd(a.cursor + ((size_t)dbin << a.ctr_shift), v[i]);  // result needed only after the placement
+      }
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    {
+      uint32_t ws = lane < THREADS / 32 ? wsum[lane] : 0u, wi = ws;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= (uint32_t)d) wi += t;
+      }
+      uint32_t e = __shfl_sync(0xffffffffu, wi - ws, warp) + incl - s;
+#pragma unroll
+      for (int i = 0; i < IPT; i++) {
+        ex[i] = e;
+        if (IPT * tid + i < a.nbins) soff[IPT * tid + i] = e;
+        e += v[i];
+      }
+    }
+    __syncthreads();
+    // which raw record goes to which output position
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tn) {
+        uint32_t p = soff[sub[k]] + rk[k];
+        perm[p] = (uint16_t)i;
+        pos_sub[p] = (uint16_t)sub[k];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t b = IPT * tid + i;
+      if (b < a.nbins) {
+        uint32_t gg = g[i];
+        if (v[i]) {
+          if (a.base_off) {  // exact layout: absolute start of the destination region, always large enough
+            const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+            const uint32_t f = a.level == 1 ? b * a.F : dbin;
+            gg += a.base_off[(size_t)f << a.rep_shift];
+          } else if (gg + v[i] > a.capacity) {
+            atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
+          }
+        }
+        sgb[b] = gg - ex[i];  // slot of output position p in bin b = sgb[b] + p
+      }
+    }
+    __syncthreads();
+    // copy out: consecutive output positions of one bin are consecutive in global memory
+    for (uint32_t p = tid; p < tn; p += THREADS) {
+      const uint32_t b = pos_sub[p];
+      const uint32_t slot = sgb[b] + p;
+      const uint4* r = raw + (size_t)perm[p] * R::kVec;
+      uint4* d;
+      if (a.base_off) {
+        d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
+      } else {
+        if (slot >= a.capacity) continue;  // flagged above
+        const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+        d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
+      }
+#pragma unroll
+      for (int vv = 0; vv < R::kVec; vv++) stg_stream(d + vv, r[vv]);
+    }
+    for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
+    __syncthreads();
+  }
+}
+
 // single-CTA exclusive scan (B <= a few million): out_excl[0..n], optional copy into
 // out_copy (scatter cursors), optional list of entries larger than cap
 __device__ __forceinline__ void exscan_body(const uint32_t* __restrict__ in, uint32_t n,
@@ -773,6 +972,11 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFGS(16) CFGS(32) CFGS(64) CFGS(128)
 #undef CFGS
+#define CFGT(RB)                                                                                         \
+  e = cudaFuncSetAttribute(k_split_tma<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(RB)); \
+  if (e != cudaSuccess) return e;
+  CFGT(16) CFGT(32) CFGT(64) CFGT(128)
+#undef CFGT
   return cudaSuccess;
 }
 
@@ -884,7 +1088,14 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
   a.err_flags = err_flags;
   const int ctas = 2 * g_sm_count;
   size_t smem = kSplitTileBytes + (kSplitTileBytes / rb) * sizeof(uint16_t);
-#define SPLIT_LAUNCH(GRID) DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));
+  static const bool use_tma = !getenv("MRHBM_NO_TMA_SPLIT");
+  const int tile_bytes = use_tma ? kTmaTileBytes : kSplitTileBytes;
+#define SPLIT_LAUNCH(GRID)                                                                              \
+  if (use_tma) {                                                                                        \
+    DISPATCH_RB(rb, (k_split_tma<RB><<<GRID, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));       \
+  } else {                                                                                              \
+    DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));                \
+  }
   if (!level2) {
     if (!n) return 0;
     a.src = (const uint4*)recs;
@@ -912,7 +1123,7 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
     // (C1 = 220, x = 2 ran 440 CTAs = 1.49 waves on 296 slots: 26 % of the second wave idle)
     int x = 1;
     double best = 0;
-    const uint64_t tiles_per_region = ((uint64_t)F * cap * rb + kSplitTileBytes - 1) / kSplitTileBytes;
+    const uint64_t tiles_per_region = ((uint64_t)F * cap * rb + tile_bytes - 1) / tile_bytes;
     for (int cand = 1; cand <= 16 && (uint64_t)cand <= std::max<uint64_t>(1, tiles_per_region / 4); cand++) {
       uint64_t total = (uint64_t)cand * C1, waves = (total + ctas - 1) / ctas;
       double eff = (double)total / (double)(waves * ctas);

@@ -230,6 +230,26 @@ def test_shared_prefix_keys_take_the_full_key_path(mkb):
         check_vs_oracle_str(ctx, recs, P, O.PART_FNV64)
 
 
+@pytest.mark.parametrize("mkb", [27, 59, 123])
+@pytest.mark.parametrize("flags", [0, mrhbm.F_NO_OPTIMISTIC])
+def test_string_keys_many_partitions_use_the_tile_split(mkb, flags):
+    """>= 2048 bins: the partition stage is the two-level tile split for every record class (32/64/128 B),
+    in the fixed-stride and in the exact layout"""
+    rng = np.random.default_rng(mkb)
+    n, P, V = 150_000, 2048, 40_000
+    vocab = [(b"k%d-" % i + b"abcdefghij" * 12)[: 3 + (i * 7) % (mkb - 2)] for i in range(V)]
+    words = [vocab[i] for i in rng.integers(0, V, n)]
+    vals = rng.integers(1, 1000, n).astype(np.uint32)
+    recs = str_records(words, vals, mkb)
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_WORDHASH, max_key_bytes=mkb, flags=flags) as ctx:
+        m = ctx.map_begin("many-partitions")
+        m.emit_batch(recs)
+        m.commit()
+        ctx.shuffle()
+        assert ctx.stats()["bins"] >= 2048
+        check_vs_oracle_str(ctx, recs, P, O.PART_FNV64)
+
+
 def test_small_bins_flag_exercises_overflow_paths():
     keys, vals = O.gen_u64(SEED, 0, 50_000)
     keys[::7] = keys[0]
