@@ -959,7 +959,9 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
-  e = cudaFuncSetAttribute(k_sort_reduce_u64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
+  e = cudaFuncSetAttribute(k_sort_reduce_u64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_sort_reduce_u64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
   if (e != cudaSuccess) return e;
 #define CFGC(RB)                                                                                       \
   e = cudaFuncSetAttribute(k_combine<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
@@ -1142,8 +1144,11 @@ int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap
   int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
   if (grid < 1) grid = 1;
   // u64 keys in key-ordered sub-bins read from one segment: the register-pipelined variant
-  if (rb == 16 && b.hint_S > 1 && (b.stride || b.nseg == 1) && !getenv("MRHBM_NO_PIPELINED_SORT")) {
-    k_sort_reduce_u64<<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+  if (rb == 16 && b.hint_S > 1 && !getenv("MRHBM_NO_PIPELINED_SORT")) {
+    if (b.stride || b.nseg == 1)
+      k_sort_reduce_u64<false><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+    else
+      k_sort_reduce_u64<true><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
     return 1;
   }
   DISPATCH_RB(rb, (k_sort_reduce<RB><<<grid, kSortThreads, sort_smem_bytes(RB), s>>>(b, B, cap)));

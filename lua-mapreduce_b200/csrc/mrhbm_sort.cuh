@@ -547,6 +547,9 @@ __device__ __forceinline__ uint32_t block_exscan_u16x4(uint16_t* a, uint32_t n) 
   return total;
 }
 
+// MULTI: a bin is gathered from one segment per source rank (after the all-to-all); a small
+// descriptor (cumulative counts + rebased segment addresses) is built by warp 0 one bin ahead.
+template <bool MULTI>
 __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuffers b, uint32_t B, uint32_t cap) {
   constexpr int RB = 16;
   constexpr uint32_t CAP = kCapBytes / RB, NB = 2 * CAP, T = kSortThreads;
@@ -562,6 +565,35 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   ((uint4*)bcnt)[2 * tid] = zero4;
   ((uint4*)bcnt)[2 * tid + 1] = zero4;
+  __shared__ uint32_t s_cum[8];   // MULTI: records of the bin that come before segment s
+  __shared__ uint64_t s_addr[8];  // MULTI: record i of the bin (in segment s) lives at src[s_addr[s] + i]
+  const uint32_t lane = tid & 31, warp = tid >> 5, nseg = b.nseg;
+  // warp 0: descriptor of bin `bn` from the per-source offsets (so, sn) each lane < nseg holds
+  auto desc_store = [&](uint32_t so, uint32_t sn) {
+    uint32_t c = lane < nseg ? sn - so : 0u, incl = c;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane < nseg) {
+      s_cum[lane] = incl - c;
+      s_addr[lane] = b.seg_base[lane] + so - (incl - c);
+    }
+  };
+  auto desc_load = [&](uint32_t bn, uint32_t& so, uint32_t& sn) {
+    so = sn = 0;
+    if (MULTI && warp == 0 && lane < nseg && bn < B) {
+      so = b.seg_off[lane][(size_t)bn << b.rep_shift];
+      sn = b.seg_off[lane][(size_t)(bn + 1) << b.rep_shift];
+    }
+  };
+  auto rec_addr = [&](uint32_t i, uint64_t off1) -> const uint4* {
+    if (!MULTI) return src + off1 + i;
+    uint32_t sg = 0;
+    while (sg + 1 < nseg && i >= s_cum[sg + 1]) sg++;
+    return src + s_addr[sg] + i;
+  };
 
   uint32_t bin = blockIdx.x;
   uint64_t off = 0;
@@ -571,10 +603,16 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     cnt = bin_count(b, bin);
   }
   uint4 rg[ITEMS];
+  if (MULTI) {
+    uint32_t so, sn;
+    desc_load(bin, so, sn);
+    if (warp == 0) desc_store(so, sn);
+    __syncthreads();
+  }
   if (cnt <= cap) {
 #pragma unroll
     for (int k = 0; k < ITEMS; k++)
-      if (tid + k * T < cnt) rg[k] = ldg_stream(src + off + tid + k * T);
+      if (tid + k * T < cnt) rg[k] = ldg_stream(rec_addr(tid + k * T, off));
   }
   __syncthreads();
   while (bin < B) {
@@ -586,6 +624,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
       noff = bin_start(b, nbin);
       ncnt = bin_count(b, nbin);
     }
+    uint32_t d_so, d_sn;
+    desc_load(nbin, d_so, d_sn);
     if (cnt == 0 || cnt > cap) {  // empty, or oversized (k_big_bins): nothing was loaded
       if (cnt == 0 && tid == 0) b.ucount[bin] = 0;
     } else {
@@ -627,12 +667,13 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
 #pragma unroll
         for (int k = 0; k < ITEMS; k++)
           if (tid + k * T < cnt) sm.rec2[bcnt[br[k] >> 4] + (br[k] & 15u)] = rg[k];
+        if (MULTI && warp == 0) desc_store(d_so, d_sn);  // the current bin's loads were issued an iteration ago
         __syncthreads();
         // the registers are free: start loading the next bin
         if (ncnt <= cap) {
 #pragma unroll
           for (int k = 0; k < ITEMS; k++)
-            if (tid + k * T < ncnt) rg[k] = ldg_stream(src + noff + tid + k * T);
+            if (tid + k * T < ncnt) rg[k] = ldg_stream(rec_addr(tid + k * T, noff));
         }
         // every position of the bucket-ordered buffer ranks itself among its bucket mates
         uint32_t fpos[ITEMS];
@@ -696,10 +737,14 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     bin = nbin;
     off = noff;
     cnt = ncnt;
+    if (MULTI) {
+      if (warp == 0) desc_store(d_so, d_sn);
+      __syncthreads();
+    }
     if (cnt <= cap) {
 #pragma unroll
       for (int k = 0; k < ITEMS; k++)
-        if (tid + k * T < cnt) rg[k] = ldg_stream(src + off + tid + k * T);
+        if (tid + k * T < cnt) rg[k] = ldg_stream(rec_addr(tid + k * T, off));
     }
     __syncthreads();
   }
