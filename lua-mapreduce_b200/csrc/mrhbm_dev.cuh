@@ -120,17 +120,19 @@ __device__ __forceinline__ uint32_t fnv_lua_hash(const uint32_t* r) {
       h = fnv_lua_step(h, (w >> (24 - 8 * (i & 3))) & 0xff);
     }
   } else {
+    // The word loop is unrolled (the record lives in registers), the byte loop is NOT: fully unrolled,
+    // 4 records x 28 bytes of fnv_lua_step overflowed the instruction cache (ncu on k_hist<32>: 43 % of
+    // the stall samples were "no instruction").
 #pragma unroll
     for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
       uint32_t w = r[i];
       if (w == 0) break;  // keys hold no NUL: a zero word is past the end (short keys leave early)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t b = (w >> (8 * j)) & 0xff;
-        if (b == 0) break;
-        h = fnv_lua_step(h, b);
-      }
-      if ((w >> 24) == 0) break;
+#pragma unroll 1
+      do {
+        h = fnv_lua_step(h, w & 0xffu);
+        w >>= 8;
+      } while (w);
+      if ((r[i] >> 24) == 0) break;
     }
   }
   return h;
@@ -166,23 +168,28 @@ __device__ __forceinline__ uint64_t word_hash(const uint32_t* r) {
 template <int RB>
 __device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& bp, uint32_t* pid_out) {
   uint32_t pid;
-  uint64_t frac;  // uniform 64-bit hash independent of pid, feeds the hash sub-bin
-  if (bp.partitioner == 1u && Rec<RB>::kU64) {  // MULHASH
+  uint64_t h = 0;  // uniform 64-bit hash; feeds the hash sub-bin (only computed further when needed)
+  const bool mul = bp.partitioner == 1u && Rec<RB>::kU64;
+  if (mul) {  // MULHASH
     uint64_t key = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h = key * 0x9E3779B97F4A7C15ull;
     pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
-    frac = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);
   } else if (bp.partitioner == 0u) {  // FNV_LUA
     pid = fnv_lua_hash<RB>(r) % bp.P;
-    frac = word_hash<RB>(r);
   } else {  // WORDHASH
-    uint64_t h = word_hash<RB>(r);
+    h = word_hash<RB>(r);
     pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
-    frac = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);
   }
   uint32_t sub = 0;
   if (bp.S > 1) {
-    uint64_t src = bp.ordered ? key_prefix64<RB>(r) : frac;
+    uint64_t src;
+    if (bp.ordered) {
+      src = key_prefix64<RB>(r);
+    } else if (bp.partitioner == 0u) {
+      src = word_hash<RB>(r);
+    } else {
+      src = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);  // independent of pid
+    }
     sub = (uint32_t)__umul64hi(src, (uint64_t)bp.S);
   }
   if (pid_out) *pid_out = pid;

@@ -441,8 +441,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_split(SplitArgs a, 
 // output position, and the copy-out reads the raw tile through it.
 constexpr int kTmaSplitThreads = 512;
 constexpr int kTmaTileBytes = 40 * 1024;
-__host__ __device__ constexpr size_t tma_split_smem(int rb) {
-  return 2 * (size_t)kTmaTileBytes + 2 * (size_t)(kTmaTileBytes / rb) * sizeof(uint16_t);
+__host__ __device__ constexpr size_t tma_split_smem(int rb, int tile_bytes = kTmaTileBytes) {
+  return 2 * (size_t)tile_bytes + 2 * (size_t)(tile_bytes / rb) * sizeof(uint16_t);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -472,17 +472,17 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
       : "memory");
 }
 
-template <int RB>
-__global__ void __launch_bounds__(kTmaSplitThreads, 2) k_split_tma(SplitArgs a, BinParams bp) {
+template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads>
+__global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using R = Rec<RB>;
-  constexpr int THREADS = kTmaSplitThreads;
-  constexpr int T = kTmaTileBytes / RB;              // records per tile
+  constexpr int THREADS = THREADS_;
+  constexpr int T = TILE_BYTES / RB;              // records per tile
   constexpr int U = (T + THREADS - 1) / THREADS;     // records per thread
   constexpr int IPT = kSplitMaxBins / THREADS;       // bins per thread in the scan
   uint4* raw0 = (uint4*)smem_raw;
-  uint4* raw1 = (uint4*)(smem_raw + kTmaTileBytes);
-  uint16_t* perm = (uint16_t*)(smem_raw + 2 * kTmaTileBytes);  // output position -> raw index
+  uint4* raw1 = (uint4*)(smem_raw + TILE_BYTES);
+  uint16_t* perm = (uint16_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index
   uint16_t* pos_sub = perm + T;                                 // output position -> bin
   __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins], sgb[kSplitMaxBins];
   __shared__ uint32_t wsum[THREADS / 32];
@@ -1091,9 +1091,11 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
   const int ctas = 2 * g_sm_count;
   size_t smem = kSplitTileBytes + (kSplitTileBytes / rb) * sizeof(uint16_t);
   static const bool use_tma = !getenv("MRHBM_NO_TMA_SPLIT");
+  // (measured alternatives, same box: 16/24 KB tiles at 4/3 CTAs per SM and 80/88 KB tiles with one
+  // 1024-thread CTA per SM are all slower than 40 KB tiles at 2 CTAs per SM)
   const int tile_bytes = use_tma ? kTmaTileBytes : kSplitTileBytes;
 #define SPLIT_LAUNCH(GRID)                                                                              \
-  if (use_tma) {                                                                                        \
+  if (use_tma) {                                                                                 \
     DISPATCH_RB(rb, (k_split_tma<RB><<<GRID, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));       \
   } else {                                                                                              \
     DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));                \

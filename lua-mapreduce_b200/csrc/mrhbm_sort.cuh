@@ -677,13 +677,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         }
         // every position of the bucket-ordered buffer ranks itself among its bucket mates
         uint32_t fpos[ITEMS];
-        uint64_t hsum[ITEMS], hkey[ITEMS];
+        uint64_t hsum[ITEMS];
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
           const uint32_t j = tid + k * T;
           fpos[k] = 0xffffffffu;
           hsum[k] = 0;
-          hkey[k] = 0;
           if (j < cnt) {
             const uint4 me = sm.rec2[j];
             const uint64_t key = (uint64_t)me.x | ((uint64_t)me.y << 32);
@@ -691,26 +690,43 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
             const uint32_t s0 = bcnt[bk], e0 = (bk + 1 < NB) ? bcnt[bk + 1] : cnt;
             uint32_t rank = 0, head = 1;
             uint64_t sum = (uint64_t)me.z | ((uint64_t)me.w << 32);
-            for (uint32_t m = s0; m < e0; m++) {
-              if (m == j) continue;
-              const uint2 qk = *(const uint2*)(sm.rec2 + m);
-              const uint64_t q = (uint64_t)qk.x | ((uint64_t)qk.y << 32);
-              if (q < key) {
-                rank++;
-              } else if (q == key) {
-                if (m < j) {
+            const uint32_t c = e0 - s0;
+            if (c > 1) {  // 65 % of the records sit alone in their bucket
+              auto mate = [&](uint32_t m, uint64_t q) {
+                if (q < key) {
                   rank++;
-                  if (!out.no_reduce) head = 0;
-                } else if (!out.no_reduce) {
-                  const uint2 qv = *((const uint2*)(sm.rec2 + m) + 1);
-                  sum += (uint64_t)qv.x | ((uint64_t)qv.y << 32);
+                } else if (q == key) {
+                  if (m < j) {
+                    rank++;
+                    if (!out.no_reduce) head = 0;
+                  } else if (!out.no_reduce) {
+                    const uint2 qv = *((const uint2*)(sm.rec2 + m) + 1);
+                    sum += (uint64_t)qv.x | ((uint64_t)qv.y << 32);
+                  }
                 }
+              };
+              // the first four bucket slots: all loads first, then the compares (no load -> branch chain)
+              uint64_t q[4];
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                q[t] = 0;
+                if ((uint32_t)t < c) {
+                  const uint2 qk = *(const uint2*)(sm.rec2 + s0 + t);
+                  q[t] = (uint64_t)qk.x | ((uint64_t)qk.y << 32);
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; t++)
+                if ((uint32_t)t < c && s0 + t != j) mate(s0 + t, q[t]);
+              for (uint32_t m = s0 + 4; m < e0; m++) {
+                if (m == j) continue;
+                const uint2 qk = *(const uint2*)(sm.rec2 + m);
+                mate(m, (uint64_t)qk.x | ((uint64_t)qk.y << 32));
               }
             }
             heads[s0 + rank] = (uint16_t)head;
             fpos[k] = head ? s0 + rank : 0xffffffffu;
             hsum[k] = sum;
-            hkey[k] = key;
           }
         }
         __syncthreads();
@@ -719,7 +735,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         for (int k = 0; k < ITEMS; k++) {
           if (fpos[k] != 0xffffffffu) {
             const uint64_t o = out.base + heads[fpos[k]];
-            ((uint64_t*)out.keys)[o] = hkey[k];
+            const uint2 kk = *(const uint2*)(sm.rec2 + tid + k * T);
+            ((uint64_t*)out.keys)[o] = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
             out.sums[o] = hsum[k];
           }
         }
