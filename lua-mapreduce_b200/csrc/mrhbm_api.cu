@@ -1180,8 +1180,14 @@ int shuffle_multi(mrhbm_ctx* c) {
       rc = ensure_records(c, &c->bigbuf, &c->big_cap, total_recv);
       if (rc) return rc;
     }
-    // one grouped send/recv over NVLink replaces the GridFS / scp store-and-forward
-    rc = comm_alltoallv(c->comm, c->sb.mid, send_off, send_cnt, c->recvbuf, recv_off, recv_cnt, s, &c->err);
+    // one grouped send/recv over NVLink replaces the GridFS / scp store-and-forward.  The rank's own
+    // share never moves: the sort kernels read that segment in place from the send buffer.
+    uint64_t net_send[8], net_recv[8];
+    for (int d = 0; d < G; d++) {
+      net_send[d] = d == me ? 0 : send_cnt[d];
+      net_recv[d] = d == me ? 0 : recv_cnt[d];
+    }
+    rc = comm_alltoallv(c->comm, c->sb.mid, send_off, net_send, c->recvbuf, recv_off, net_recv, s, &c->err);
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     v = c->sb;
@@ -1195,6 +1201,13 @@ int shuffle_multi(mrhbm_ctx* c) {
     for (int r = 0; r < G; r++) {
       v.seg_off[r] = c->d_segoff + (uint64_t)r * (Bl + 1);
       v.seg_base[r] = recv_off[r] / c->rb;
+    }
+    {
+      // own segment: record offset of (send buffer + send_off[me]) relative to v.src, possibly "negative"
+      // (two's complement; the kernels add it to the source pointer with 64-bit wrap-around).  Both
+      // buffers come from cudaMalloc (>= 256-byte aligned), so the difference is a multiple of rb.
+      const int64_t delta = (int64_t)((const char*)c->sb.mid - (const char*)c->recvbuf) + (int64_t)send_off[me];
+      v.seg_base[me] = (uint64_t)(delta / (int64_t)c->rb);
     }
     st.launches += agg ? launch_agg_bins(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s)
                        : launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
