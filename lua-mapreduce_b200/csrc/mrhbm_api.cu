@@ -348,7 +348,7 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaMalloc((void**)&c->d_acc, 8 * sizeof(uint64_t)));
   CU(c, cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
   CU(c, cudaHostAlloc((void**)&c->h_acc, 8 * sizeof(uint64_t), cudaHostAllocDefault));
-  CU(c, cudaMalloc((void**)&c->d_small, 64 * sizeof(uint32_t)));
+  CU(c, cudaMalloc((void**)&c->d_small, (64 + kScanScratchWords) * sizeof(uint32_t)));  // [64..): scan scratch
   CU(c, cudaHostAlloc((void**)&c->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
   c->Pl = cfg->num_partitions;
   for (int r = 1; r <= 8; r++) c->pbase[r] = cfg->num_partitions;
@@ -915,7 +915,7 @@ int shuffle_single(mrhbm_ctx* c) {
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
     st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
-                                 c->sb.counters + CNT_TOTAL, 0, s);
+                                 c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
     c->h_uoff.resize(B + 1);
     CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
     CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -970,7 +970,7 @@ int shuffle_single(mrhbm_ctx* c) {
       for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, with_src(bp, r), c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       st.launches += launch_exscan(c->sb.hist, (uint32_t)Bv, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
-                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s);
+                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s, c->d_small + 64);
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PROBE], s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
@@ -1028,7 +1028,7 @@ int shuffle_single(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_big.data(), c->sb.big_list, nbig * 4, cudaMemcpyDeviceToHost, s));
     }
     st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
-                                 c->sb.counters + CNT_TOTAL, 0, s);
+                                 c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
     c->h_bin_off.resize(B + 1);
     c->h_uoff.resize(B + 1);
     CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->sb.bin_off, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
@@ -1115,14 +1115,14 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       // send layout (destination-major bins) + dense counts for the all-gather
       st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->d_hd, 0xffffffffu, nullptr,
-                                   nullptr, nullptr, c->ctr_shift, s);
+                                   nullptr, nullptr, c->ctr_shift, s, c->d_small + 64);
       rc = comm_allgather_u32(c->comm, c->d_hd, c->d_hall, B, s, &c->err);
       if (rc) return rc;
       // receive layout: per owned bin the total and the per-source offsets
       st.launches += launch_sum_src(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_tot, c->cap,
                                     c->sb.counters + CNT_GBIG, s);
       st.launches += launch_exscan(c->d_tot, (uint32_t)Bl, c->d_outoff, nullptr, nullptr, c->cap, c->sb.big_list,
-                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, 0, s);
+                                   c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
       st.launches += launch_exscan_rows(c->d_hall, G, (uint32_t)B, bin_base, (uint32_t)Bl, c->d_segoff, c->d_small + 32, s);
       for (int d = 0; d <= G; d++)
         CU(c, cudaMemcpyAsync(c->h_small + 48 + d, c->sb.bin_off + (uint64_t)c->pbase[d] * S, 4, cudaMemcpyDeviceToHost, s));
@@ -1215,7 +1215,7 @@ int shuffle_multi(mrhbm_ctx* c) {
     st.launches += launch_big_bins(c->rb, v, nbig, c->cap, s);
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
     st.launches += launch_exscan(c->sb.ucount, (uint32_t)Bl, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
-                                 c->sb.counters + CNT_TOTAL, 0, s);
+                                 c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
     c->h_bin_off.resize(Bl + 1);
     c->h_uoff.resize(Bl + 1);
     CU(c, cudaMemcpyAsync(c->h_bin_off.data(), c->d_outoff, (Bl + 1) * 4, cudaMemcpyDeviceToHost, s));

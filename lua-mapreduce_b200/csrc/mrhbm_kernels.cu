@@ -684,6 +684,67 @@ __global__ void __launch_bounds__(1024) k_exscan(const uint32_t* __restrict__ in
                                                  uint32_t* total, uint32_t shift) {
   exscan_body(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
 }
+// Multi-CTA exclusive scan (bins in the tens of thousands made the single-CTA scan a visible slice of
+// the shuffle): block b owns elements [1024 b, 1024 b + 1024), one per thread.  Pass 1 writes the block
+// sums, pass 2 adds up the sums of the preceding blocks (<= 4096 of them), scans its own elements and
+// writes the same outputs as exscan_body.
+__global__ void __launch_bounds__(1024) k_exscan_partials(const uint32_t* __restrict__ in, uint32_t n, uint32_t shift,
+                                                          uint32_t* __restrict__ partials) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t tid = threadIdx.x, i = blockIdx.x * 1024u + tid;
+  uint32_t v = i < n ? in[(size_t)i << shift] : 0u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((tid & 31) == 0) warp_sums[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = warp_sums[tid];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+    if (tid == 0) partials[blockIdx.x] = w;
+  }
+}
+__global__ void __launch_bounds__(1024) k_exscan_apply(const uint32_t* __restrict__ in, uint32_t n,
+                                                       uint32_t* __restrict__ out_excl, uint32_t* __restrict__ out_copy,
+                                                       uint32_t* __restrict__ out_dense, uint32_t cap,
+                                                       uint32_t* __restrict__ big_list, uint32_t* nbig, uint32_t* total,
+                                                       uint32_t shift, const uint32_t* __restrict__ partials) {
+  __shared__ uint32_t warp_sums[32], warp_pre[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i = blockIdx.x * 1024u + tid;
+  uint32_t pre = 0;  // sum of the preceding blocks
+  for (uint32_t b = tid; b < blockIdx.x; b += 1024u) pre += partials[b];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+  const uint32_t c = i < n ? in[(size_t)i << shift] : 0u;
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  if (lane == 0) warp_pre[warp] = pre;
+  __syncthreads();
+  uint32_t w = warp_sums[lane], wi = w, p = warp_pre[lane];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= (uint32_t)d) wi += t;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) p += __shfl_xor_sync(0xffffffffu, p, d);
+  const uint32_t run = p + __shfl_sync(0xffffffffu, wi - w, warp) + incl - c;  // exclusive prefix of element i
+  if (i < n) {
+    out_excl[i] = run;
+    if (out_copy) out_copy[(size_t)i << shift] = run;
+    if (out_dense) out_dense[i] = c;
+    if (big_list && c > cap) big_list[atomicAdd(nbig, 1u)] = i;
+    if (i == n - 1) {
+      out_excl[n] = run + c;
+      if (total) *total = run + c;
+    }
+  }
+}
 // one CTA per source rank: exclusive scan of that rank's counts for this rank's bins
 __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict__ all, uint32_t stride, uint32_t base,
                                                       uint32_t n, uint32_t* __restrict__ out, uint32_t* __restrict__ totals) {
@@ -1013,7 +1074,13 @@ int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint3
 }
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t* out_dense,
                   uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total, uint32_t shift,
-                  cudaStream_t s) {
+                  cudaStream_t s, uint32_t* scratch) {
+  const uint32_t nb = (n + 1023u) / 1024u;
+  if (scratch && nb >= 4 && nb <= kScanScratchWords) {
+    k_exscan_partials<<<nb, 1024, 0, s>>>(in, n, shift, scratch);
+    k_exscan_apply<<<nb, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift, scratch);
+    return 2;
+  }
   k_exscan<<<1, 1024, 0, s>>>(in, n, out_excl, out_copy, out_dense, cap, big_list, nbig, total, shift);
   return 1;
 }

@@ -92,9 +92,11 @@ int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, cons
 int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* hist, cudaStream_t s);
 // exclusive scan of in[i << shift], i < n: out_excl[n+1]; optional copies: out_copy[i << shift] (scatter
 // cursors), out_dense[i] (the counts, densely packed), entries > cap appended to big_list
+// scratch: kScanScratchWords words for the multi-CTA variant (nullptr: single CTA)
+constexpr uint32_t kScanScratchWords = 4096;
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy,
                   uint32_t* out_dense, uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total,
-                  uint32_t shift, cudaStream_t s);
+                  uint32_t shift, cudaStream_t s, uint32_t* scratch = nullptr);
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                    cudaStream_t s);
 // optimistic variant: fixed `stride` slots per bin, cursors start at 0, a full bin sets ERRF_CAPACITY
