@@ -23,8 +23,9 @@ function hbm.configure(partition_mod, reduce_mod, combiner_mod, opts)
   assert(not combiner_mod or (builtin and combiner_mod.hbm_reducefn == "sum"),
          "a combinerfn runs on the device: it (and the reducefn) must declare hbm_reducefn = 'sum'")
   opts = opts or {}
+  tuple_keys = opts.key_kind == "tuple" -- composite keys travel as encoded byte strings
   local c, err = mrhbm.new{
-    key_kind = opts.key_kind or "str",
+    key_kind = tuple_keys and "str" or opts.key_kind or "str",
     max_key_bytes = opts.max_key_bytes or 123,
     num_partitions = assert(partition_mod.NUM_REDUCERS, "partitionfn module must expose NUM_REDUCERS"),
     partitioner = assert(partition_mod.hbm_partitionfn, "partitionfn module must declare hbm_partitionfn"),
@@ -36,10 +37,112 @@ function hbm.configure(partition_mod, reduce_mod, combiner_mod, opts)
   return ctx
 end
 
+
+-- ---------------------------------------------------------------------------------------------
+-- Composite keys (mapreduce/tuple.lua): a tuple key crosses the C ABI as an ORDER-PRESERVING,
+-- NUL-free byte string (<= 123 bytes) and is decoded again on the reduce side.  Same format as
+-- ../../mapreduce/tuple.py (which is what runs under test):
+--   key       := "\127" component | char(128+n) component*n       (n <= 31, shorter tuples first)
+--   component := "\16" num10 | "\32" bytes "\1" | "\48" key
+--   num10     := the IEEE double, sign-folded so that unsigned order = numeric order, as 10
+--                big-endian 7-bit groups each OR 0x80
+-- Bytewise order = length first, then component-wise: a linear extension of tuple.lua:183-195.
+local tuple = require "mapreduce.tuple"
+local spack, sunpack = string.pack, string.unpack -- Lua >= 5.3; on 5.2 use struct.pack(">d") from lua-struct
+
+local function enc_num(x, out)
+  assert(x == x, "NaN cannot be a key")
+  if x == 0 then x = 0 end -- -0 and 0 are the same table key
+  local hi, lo = sunpack(">I4I4", spack(">d", x))
+  if hi >= 0x80000000 then hi, lo = 0xFFFFFFFF - hi, 0xFFFFFFFF - lo else hi = hi + 0x80000000 end
+  -- 64 bits -> groups of 1,7,7,...,7 bits
+  local bits = {}
+  for i = 31, 0, -1 do bits[#bits + 1] = math.floor(hi / 2 ^ i) % 2 end
+  for i = 31, 0, -1 do bits[#bits + 1] = math.floor(lo / 2 ^ i) % 2 end
+  out[#out + 1] = "\16"
+  out[#out + 1] = string.char(128 + bits[1])
+  for g = 0, 8 do
+    local v = 0
+    for b = 1, 7 do v = v * 2 + bits[1 + g * 7 + b] end
+    out[#out + 1] = string.char(128 + v)
+  end
+end
+
+local enc_key
+local function enc_component(v, out)
+  local mt = type(v) == "table" and getmetatable(v)
+  if mt == "is_tuple" then
+    out[#out + 1] = "\48"
+    enc_key(v, out)
+  elseif type(v) == "string" then
+    assert(not v:find("[%z\1]"), "string components must not contain the bytes 0x00 / 0x01")
+    out[#out + 1] = "\32" .. v .. "\1"
+  else
+    enc_num(assert(tonumber(v), "keys are numbers, strings or tuples of them"), out)
+  end
+end
+enc_key = function(k, out)
+  if type(k) == "table" then
+    assert(#k <= 31, "tuples of more than 31 components are not supported")
+    out[#out + 1] = string.char(128 + #k)
+    for i = 1, #k do enc_component(k[i], out) end
+  else
+    out[#out + 1] = "\127"
+    enc_component(k, out)
+  end
+end
+
+function hbm.encode_key(k)
+  local out = {}
+  enc_key(tuple(k), out)
+  local s = table.concat(out)
+  assert(#s <= 123, "encoded key is longer than 123 bytes")
+  return s
+end
+
+local dec_key
+local function dec_component(s, i)
+  local tag = s:byte(i)
+  if tag == 16 then
+    local hi, lo, nb = 0, 0, 0
+    for k = 1, 10 do
+      local g, w = s:byte(i + k) % 128, (k == 1) and 1 or 7
+      for b = w - 1, 0, -1 do
+        local bit = math.floor(g / 2 ^ b) % 2
+        if nb < 32 then hi = hi * 2 + bit else lo = lo * 2 + bit end
+        nb = nb + 1
+      end
+    end
+    if hi >= 0x80000000 then hi = hi - 0x80000000 else hi, lo = 0xFFFFFFFF - hi, 0xFFFFFFFF - lo end
+    return (sunpack(">d", spack(">I4I4", hi, lo))), i + 11
+  elseif tag == 32 then
+    local j = s:find("\1", i + 1, true)
+    return s:sub(i + 1, j - 1), j + 1
+  elseif tag == 48 then
+    return dec_key(s, i + 1)
+  end
+  error("bad component tag")
+end
+dec_key = function(s, i)
+  local head = s:byte(i)
+  if head == 127 then return dec_component(s, i + 1) end
+  local t, n = {}, head - 128
+  i = i + 1
+  for k = 1, n do t[k], i = dec_component(s, i) end
+  t.n = n
+  return tuple(t), i
+end
+function hbm.decode_key(s) return (dec_key(s, 1)) end
+
+local tuple_keys = false -- hbm.configure(..., { key_kind = "tuple" })
+
 -- job_prepare_map (job.lua:154-228): returns the emit closure and the finisher
 function hbm.map_job(map_key)
   local m = assert(ctx:map_begin(tostring(map_key)))
-  local emit = function(key, value) assert(m:emit(key, value)) end
+  local emit = function(key, value)
+    if tuple_keys then key = hbm.encode_key(key) end
+    assert(m:emit(key, value))
+  end
   local finish = function(ok)
     if ok then assert(m:commit()) else m:abort() end -- BROKEN jobs publish nothing
   end
@@ -53,7 +156,14 @@ function hbm.prepare_reduce()
 end
 
 -- job_prepare_reduce (job.lua:230-296): for k,v in hbm.groups(part_key) do ... end
-function hbm.groups(part_key) return assert(ctx:groups(part_key)) end
+function hbm.groups(part_key)
+  local it = assert(ctx:groups(part_key))
+  if not tuple_keys then return it end
+  return function()
+    local k, v = it()
+    if k ~= nil then return hbm.decode_key(k), v end
+  end
+end
 
 function hbm.reset() assert(ctx:reset()) end
 

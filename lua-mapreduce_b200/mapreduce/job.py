@@ -7,6 +7,7 @@ mrhbm_groups_next; the reducer algebra (job.lua:264-284) is kept."""
 import importlib
 import time
 
+from . import tuple as tuple_keys
 from .utils import STATUS
 
 _initialized = set()
@@ -65,6 +66,10 @@ class Job:
             if cfg["hbm"]["key_kind"] == "u64":
                 def emit(key, value=1):
                     m.emit(int(key), int(value))
+            elif cfg["hbm"]["key_kind"] == "tuple":
+                # composite keys (tuple.lua): order-preserving byte strings across the C ABI
+                def emit(key, value=1):
+                    m.emit(tuple_keys.encode(key), int(value))
             else:
                 def emit(key, value=1):
                     m.emit(_key_bytes(key), int(value))
@@ -90,7 +95,10 @@ class Job:
         def emit(v):
             result.append(v)
 
+        decode = tuple_keys.decode if cfg["hbm"]["key_kind"] == "tuple" else None
         for key, values in ctx.groups(part):
+            if decode:
+                key = decode(key)
             # The device applied the declared built-in (combiner semantics).  The reference
             # skips the reducer on singletons when the ACI flags are set (job.lua:264-274),
             # otherwise it always calls it (job.lua:275-284).
