@@ -304,6 +304,10 @@ def main():
                      "achieved": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9,
                      "frac": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9 / peak},
         "stages_ms": dev_ms,
+        # SURVEY 8d "fusion headroom": the strict end-to-end lower bound N R + U R_out of a single-pass hash
+        # aggregation over the step's time -- reported beside the graded fraction, not instead of it
+        "fusion_headroom": {"lower_bound_bytes": n * R + g_local * R,
+                            "frac_of_peak": (n * R + g_local * R) / (dev_ms["ms_total"] * 1e-3) / 1e9 / peak},
         "kernels": {k: {"algorithmic_bytes": stage_bytes[k], "ms": k_ms[k],
                         "achieved": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9) if k_ms[k] > 0 else None,
                         "frac": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak) if k_ms[k] > 0 else None}
