@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--partitions", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-serial", action="store_true", help="one worker, no overlap between steps")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="pairs in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="pairs in the CPU sample (default: 10^7 for cpu_baseline = ~10 s on 4 threads; "
+                         "2*10^6 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -121,7 +123,7 @@ def host_u64_records(seed, start, n, out):
         out["pad"][a:b] = 0
 
 
-def cpu_baseline(a, wp, table, threads):
+def cpu_baseline(a, wp, table, threads, sample):
     """Reference-shaped CPU path (oracle engine: emit table, sort, text spill, heap merge,
     sum) on a bounded sample of the same stream.  kind = "port" (the reference is Lua+MongoDB
     and cannot run in this image)."""
@@ -129,7 +131,7 @@ def cpu_baseline(a, wp, table, threads):
     import oracle as O
     from lua_mapreduce_b200 import synth
     njobs = max(threads, 8)
-    per = max(1, a.cpu_sample // njobs)
+    per = max(1, sample // njobs)
     if a.workload == "u64":
         eng = O.Engine(O.PART_MULHASH, wp["P"], combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
         ms, rs = O.run_synthetic(eng, 0, synth.SEED, 0, per, njobs, threads)
@@ -154,12 +156,13 @@ def run_reference(a):
     table = synth.zipf_table() if a.workload == "zipf32" else None
     threads = os.cpu_count() or 1
     vals = []
+    sample = a.cpu_sample or 2_000_000
     for _ in range(a.warmup and 1):
-        cpu_baseline(a, wp, table, threads)
+        cpu_baseline(a, wp, table, threads, sample)
     t0 = time.perf_counter()
     last = None
     for _ in range(max(1, a.steps)):
-        last = cpu_baseline(a, wp, table, threads)
+        last = cpu_baseline(a, wp, table, threads, sample)
         vals.append(last["value"])
     dt = time.perf_counter() - t0
     v = float(np.mean(vals))
@@ -420,7 +423,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_baseline(a, wp, table, min(4, os.cpu_count() or 1))
+        cpu = cpu_baseline(a, wp, table, min(4, os.cpu_count() or 1), a.cpu_sample or 10_000_000)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,

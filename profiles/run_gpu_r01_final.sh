@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_r01_n1.json 2> gpurun_out/bench_r01_n1.err; echo "rc=$?" >> gpurun_out/bench_r01_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_n1_reference.json 2>> gpurun_out/bench_r01_n1.err
-timeout 900 python bench.py --workload zipf32 --steps 5 --warmup 3 --cpu-sample 4000000 --e2e-steps 2 > gpurun_out/bench_r01_n1_zipf32.json 2> gpurun_out/bench_r01_zipf.err; echo "rc=$?" >> gpurun_out/bench_r01_zipf.err
+timeout 900 python bench.py --workload zipf32 --steps 5 --warmup 3 --e2e-steps 2 > gpurun_out/bench_r01_n1_zipf32.json 2> gpurun_out/bench_r01_zipf.err; echo "rc=$?" >> gpurun_out/bench_r01_zipf.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r01_zipf32.csv python bench.py --workload zipf32 --pairs 200000000 --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_split|k_sort_reduce' -s 12 -c 3 -o gpurun_out/prof_r01_final -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_final.log 2>&1
