@@ -44,3 +44,18 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = run(["--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--e2e-steps", "0"], timeout=600)
     assert r.returncode != 0
     assert r.stdout.strip() == ""  # no JSON line, no silent CPU path
+
+
+def test_bench_main_dry_run_assembles_the_contract_line():
+    """host logic of the product arm over stand-ins (no measurement meaning): every contract key is present"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py")], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "gpu_launches", "clocks", "e2e", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernels", "pipeline", "fusion_headroom"}
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert d["config"]["workload"].startswith("config2") and d["vs_baseline"] is None
