@@ -51,6 +51,13 @@ struct mrhbm_ctx {
   uint64_t hd_cap = 0, bl_cap = 0;
   void *recvbuf = nullptr, *bigbuf = nullptr;
   uint64_t recv_cap = 0, big_cap = 0;
+  // EXPERIMENTAL fused split -> peer-memory exchange (MRHBM_P2P=1, u64 records): every rank's receive buffer is
+  // exported with cudaIpcGetMemHandle and mapped by its peers; level 2 of the exact split stores into them
+  bool p2p = false;
+  void* peer_recv[8] = {nullptr};
+  uint64_t p2p_cap = 0;                       // records every rank's receive buffer holds (same on all ranks)
+  unsigned long long *d_route = nullptr, *h_route = nullptr;  // kRouteWords each
+  uint32_t *d_ipc = nullptr, *h_ipc = nullptr;                // 16 words per rank: the IPC handles
   uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
   bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
@@ -368,6 +375,12 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
 void mrhbm_destroy(mrhbm_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < 8; r++)
+    if (c->p2p && r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
+  if (c->d_route) cudaFree(c->d_route);
+  if (c->h_route) cudaFreeHost(c->h_route);
+  if (c->d_ipc) cudaFree(c->d_ipc);
+  if (c->h_ipc) cudaFreeHost(c->h_ipc);
   if (c->comm) comm_destroy(c->comm);
   void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
@@ -708,6 +721,47 @@ int ensure_multi_buffers(mrhbm_ctx* c, uint64_t B, uint64_t Bl) {
     CU(c, cudaMalloc((void**)&c->d_segoff, nb * 4 * G));
     c->bl_cap = nb;
   }
+  return 0;
+}
+
+int ensure_records(mrhbm_ctx* c, void** buf, uint64_t* cap, uint64_t need);
+int gather_u32(mrhbm_ctx* c, uint32_t mine, uint32_t* all);
+
+// EXPERIMENTAL (MRHBM_P2P=1).  Collective: every rank calls it with the same `need` (records the fullest
+// receive buffer of the job must hold).  Grows all receive buffers together and re-exchanges their IPC handles.
+int p2p_ensure(mrhbm_ctx* c, uint64_t need) {
+  if (need <= c->p2p_cap) return 0;
+  const int G = c->world, me = c->rank;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < G; r++) {
+    if (r != me && c->peer_recv[r]) CU(c, cudaIpcCloseMemHandle(c->peer_recv[r]));
+    c->peer_recv[r] = nullptr;
+  }
+  uint32_t all[8];
+  int rc = gather_u32(c, 0, all);  // every rank has unmapped its peers before anybody frees
+  if (rc) return rc;
+  need += need / 8 + 1024;
+  rc = ensure_records(c, &c->recvbuf, &c->recv_cap, need);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  CU(c, cudaIpcGetMemHandle(&h, c->recvbuf));
+  memcpy(c->h_ipc, &h, 64);
+  CU(c, cudaMemcpyAsync(c->d_ipc, c->h_ipc, 64, cudaMemcpyHostToDevice, c->stream));
+  rc = comm_allgather_u32(c->comm, c->d_ipc, c->d_ipc + 16, 16, c->stream, &c->err);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_ipc + 16, c->d_ipc + 16, 64 * (size_t)G, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < G; r++) {
+    if (r == me) {
+      c->peer_recv[r] = c->recvbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t hr;
+    memcpy(&hr, c->h_ipc + 16 + 16 * r, 64);
+    CU(c, cudaIpcOpenMemHandle(&c->peer_recv[r], hr, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->p2p_cap = need;
   return 0;
 }
 
@@ -1094,6 +1148,7 @@ int shuffle_multi(mrhbm_ctx* c) {
   cudaStream_t s = c->stream;
   uint64_t B = 0, Bl = 0, total_recv = 0;
   uint64_t send_off[9], send_cnt[8], recv_off[9], recv_cnt[8];
+  bool p2p_done = false;
   ShuffleBuffers v{};
   for (int widen = 0;; widen++) {
     B = (uint64_t)P * S;
@@ -1129,12 +1184,41 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+      p2p_done = false;
       {
         // send buffer (destination-major exact layout) through the two-level coalesced split
         uint32_t F = 1;
         while ((uint64_t)F * F < B) F <<= 1;
         uint32_t C1 = (uint32_t)((B + F - 1) / F);
-        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
+        if (c->p2p && !agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
+          // EXPERIMENTAL fused split -> peer-memory exchange: level 2 stores every bin into its owner's receive
+          // buffer over NVLink; no NCCL data exchange follows.  The routing table needs the all-gathered counts.
+          uint32_t first9[9];
+          for (int d = 0; d <= 8; d++) first9[d] = c->pbase[d < G ? d : G] * S;
+          st.launches += launch_p2p_route(c->d_hall, (uint32_t)G, (uint32_t)B, (uint32_t)me, first9, c->sb.bin_off, c->d_route, s);
+          CU(c, cudaMemcpyAsync(c->h_route + 32, c->d_route + 32, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+          CU(c, cudaStreamSynchronize(s));
+          if (!agg && c->h_counters[CNT_GBIG] && ordered && S > 1) {  // same decision on every rank, see below
+            ordered = 0;
+            continue;
+          }
+          uint64_t fullest = 0;
+          for (int d = 0; d < G; d++) fullest = std::max<uint64_t>(fullest, c->h_route[32 + d]);
+          rc = p2p_ensure(c, fullest);  // collective; the previous sort of every rank is behind the counts all-gather
+          if (rc) return rc;
+          for (int d = 0; d < G; d++) c->h_route[d] = (unsigned long long)(uintptr_t)(d == me ? c->sb.mid : c->peer_recv[d]);
+          CU(c, cudaMemcpyAsync(c->d_route, c->h_route, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+          rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
+          if (rc) return rc;
+          CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
+          CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+          for (auto& r : live)
+            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bp, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
+                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
+          st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
+                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s, c->d_route);
+          p2p_done = true;
+        } else if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
           rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
           if (rc) return rc;
           CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
@@ -1172,8 +1256,10 @@ int shuffle_multi(mrhbm_ctx* c) {
       recv_off[d + 1] = recv_off[d] + recv_cnt[d];
       if (d != me) st.bytes_exchanged += send_cnt[d];
     }
-    rc = ensure_records(c, &c->recvbuf, &c->recv_cap, total_recv);
-    if (rc) return rc;
+    if (!p2p_done) {  // (the P2P path sized and exported the receive buffers before its level 2)
+      rc = ensure_records(c, &c->recvbuf, &c->recv_cap, total_recv);
+      if (rc) return rc;
+    }
     rc = ensure_out(c, total_recv);
     if (rc) return rc;
     if (nbig) {
@@ -1187,7 +1273,13 @@ int shuffle_multi(mrhbm_ctx* c) {
       net_send[d] = d == me ? 0 : send_cnt[d];
       net_recv[d] = d == me ? 0 : recv_cnt[d];
     }
-    rc = comm_alltoallv(c->comm, c->sb.mid, send_off, net_send, c->recvbuf, recv_off, net_recv, s, &c->err);
+    if (p2p_done) {
+      // the peers' stores are behind their level-2 kernels; one small collective orders them before the sort
+      uint32_t dummy[8];
+      rc = gather_u32(c, 0, dummy);
+    } else {
+      rc = comm_alltoallv(c->comm, c->sb.mid, send_off, net_send, c->recvbuf, recv_off, net_recv, s, &c->err);
+    }
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     v = c->sb;
@@ -1469,6 +1561,13 @@ int mrhbm_comm_init(mrhbm_ctx* c, const void* id, int rank, int world) {
     c->pbase[r + 1] = c->pbase[r] + owned;
   }
   c->Pl = c->pbase[rank + 1] - c->pbase[rank];
+  if (getenv("MRHBM_P2P") && atoi(getenv("MRHBM_P2P")) && c->rb == 16) {  // EXPERIMENTAL, see mrhbm_ctx::p2p
+    CU(c, cudaMalloc((void**)&c->d_route, kRouteWords * sizeof(unsigned long long)));
+    CU(c, cudaHostAlloc((void**)&c->h_route, kRouteWords * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU(c, cudaMalloc((void**)&c->d_ipc, 16 * 9 * sizeof(uint32_t)));
+    CU(c, cudaHostAlloc((void**)&c->h_ipc, 16 * 9 * sizeof(uint32_t), cudaHostAllocDefault));
+    c->p2p = true;
+  }
   invalidate(c);
   return MRHBM_OK;
 }

@@ -297,6 +297,14 @@ struct SplitArgs {
   const uint32_t* base_off;
   uint32_t rep_shift;
   uint32_t B;
+  // Fused split -> peer-memory exchange (multi-GPU, exact level 2, P2P instantiation only; EXPERIMENTAL,
+  // opt-in with MRHBM_P2P=1): a device table of kRouteWords u64 --
+  //   route[d]       byte address of rank d's receive buffer (own rank: the local bin buffer),
+  //   route[8 + d]   record offset to add to the local exact slot for bins owned by rank d (two's complement),
+  //   route[16 + d]  first fine bin owned by rank d (d = 0..ndest), so bins [route[16+d], route[16+d+1]) go to d
+  //   route[32 + d]  records rank d receives in total (all sources; written by k_p2p_route)
+  const unsigned long long* route;
+  uint32_t ndest;
 };
 
 template <int RB, int THREADS, int TILE_BYTES>
@@ -472,7 +480,7 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
       : "memory");
 }
 
-template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads>
+template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads, bool P2P = false>
 __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using R = Rec<RB>;
@@ -617,7 +625,14 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       const uint4* r = raw + (size_t)perm[p] * R::kVec;
       uint4* d;
       if (a.base_off) {
-        d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
+        if (P2P && a.level == 2) {  // the bin's owner gets the record straight into its receive buffer (NVLink store)
+          const uint32_t f = coarse * a.F + b;
+          uint32_t dd = 0;
+          while (dd + 1 < a.ndest && f >= (uint32_t)a.route[16 + dd + 1]) dd++;
+          d = (uint4*)a.route[dd] + (uint64_t)((long long)slot + (long long)a.route[8 + dd]) * R::kVec;
+        } else {
+          d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
+        }
       } else {
         if (slot >= a.capacity) continue;  // flagged above
         const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
@@ -628,6 +643,48 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     }
     for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
     __syncthreads();
+  }
+}
+
+// P2P routing table of one rank (EXPERIMENTAL, see SplitArgs::route): block d sums, over the all-gathered
+// counts all[s*B + bin], what every source s sends to rank d.  Records of lower-numbered sources come first
+// in d's receive buffer, so this rank's share starts at sum_{s<me}; its local exact layout starts the bins
+// of d at bin_off[first[d]].
+struct RouteFirst {
+  uint32_t v[9];
+};
+__global__ void __launch_bounds__(256) k_p2p_route(const uint32_t* __restrict__ all, uint32_t G, uint32_t B, uint32_t me,
+                                                   RouteFirst first, const uint32_t* __restrict__ bin_off,
+                                                   unsigned long long* __restrict__ route) {
+  __shared__ unsigned long long s_lo[8], s_all[8];
+  const uint32_t d = blockIdx.x, f0 = first.v[d], f1 = first.v[d + 1];
+  unsigned long long lo = 0, tot = 0;
+  for (uint32_t s = 0; s < G; s++) {
+    unsigned long long acc = 0;
+    for (uint32_t b = f0 + threadIdx.x; b < f1; b += blockDim.x) acc += all[(size_t)s * B + b];
+    tot += acc;
+    if (s < me) lo += acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_all[threadIdx.x >> 5] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lo = tot = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; w++) {
+      lo += s_lo[w];
+      tot += s_all[w];
+    }
+    route[8 + d] = d == me ? 0ull : (unsigned long long)((long long)lo - (long long)bin_off[f0]);
+    route[16 + d] = f0;
+    if (d + 1 == G) route[16 + G] = f1;
+    route[32 + d] = tot;
   }
 }
 
@@ -1040,6 +1097,9 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFGT(16) CFGT(32) CFGT(64) CFGT(128)
 #undef CFGT
+  e = cudaFuncSetAttribute(k_split_tma<16, kTmaTileBytes, 2, kTmaSplitThreads, true>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(16));
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1124,6 +1184,13 @@ int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_
                                                                                       cap, nover);
   return 1;
 }
+int launch_p2p_route(const uint32_t* all, uint32_t G, uint32_t B, uint32_t me, const uint32_t* first9,
+                     const uint32_t* bin_off, unsigned long long* route, cudaStream_t s) {
+  RouteFirst f;
+  for (int i = 0; i < 9; i++) f.v[i] = first9[i];
+  k_p2p_route<<<G, 256, 0, s>>>(all, G, B, me, f, bin_off, route);
+  return 1;
+}
 int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n, uint32_t* out,
                        uint32_t* totals, cudaStream_t s) {
   k_exscan_rows<<<world, 1024, 0, s>>>(all, stride, base, n, out, totals);
@@ -1145,7 +1212,7 @@ int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& 
 // both levels of the coalesced split; cursor1 / l1 are the coarse fill levels and regions
 int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
                   uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, const uint32_t* base_off, cudaStream_t s) {
+                  bool level2, const uint32_t* base_off, cudaStream_t s, const unsigned long long* route) {
   SplitArgs a{};
   a.base_off = base_off;
   a.rep_shift = bp.rep_shift;
@@ -1167,6 +1234,8 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
   } else {                                                                                              \
     DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));                \
   }
+  a.route = route;
+  a.ndest = route ? bp.world : 0;
   if (!level2) {
     if (!n) return 0;
     a.src = (const uint4*)recs;
@@ -1202,6 +1271,10 @@ int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uin
         best = eff;
         x = cand;
       }
+    }
+    if (route) {  // EXPERIMENTAL fused exchange: u64 records only (the caller checks)
+      k_split_tma<16, kTmaTileBytes, 2, kTmaSplitThreads, true><<<dim3(x, C1), kTmaSplitThreads, tma_split_smem(16), s>>>(a, bp);
+      return 1;
     }
     SPLIT_LAUNCH(dim3(x, C1))
   }

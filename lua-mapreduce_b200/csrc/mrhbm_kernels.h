@@ -123,13 +123,18 @@ inline uint32_t agg_table_entries(int rb) { return (uint32_t)((kCapBytes + (kCap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                    uint32_t* tot, uint32_t cap, uint32_t* nover, cudaStream_t s);
 // row r < world: out[r*(n+1) ..] = exclusive scan of all[r*stride + base ..+n), totals[r] = its sum
+// EXPERIMENTAL (MRHBM_P2P=1): routing table of the fused split -> peer-memory exchange, see SplitArgs::route
+constexpr int kRouteWords = 48;
+int launch_p2p_route(const uint32_t* all, uint32_t G, uint32_t B, uint32_t me, const uint32_t* first9,
+                     const uint32_t* bin_off, unsigned long long* route, cudaStream_t s);
 int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                        uint32_t* out, uint32_t* totals, cudaStream_t s);
 // two-level coalesced split into the fixed-stride layout: level 1 (level2 = false) source ->
 // C1 coarse regions of F*cap records in l1, level 2 coarse regions -> fine bins of cap records in mid
 int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
                   uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, const uint32_t* base_off, cudaStream_t s);
+                  bool level2, const uint32_t* base_off, cudaStream_t s,
+                  const unsigned long long* route = nullptr);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);
