@@ -177,4 +177,24 @@ class server:
         return reply
 
 
+    # ---- interchange with a stock lua-mapreduce deployment
+    def export_results(self, directory):
+        """Writes the kept results (finalfn returned false/nil) as the reference's result files: one file per
+        non-empty partition named `<result_ns>.P<kk>` (server.lua:313-321), one line `return <key>,{<values>}`
+        per key in ascending key order (job.lua:272-273).  Returns the file names."""
+        import os
+        from .utils import result_line
+        names = []
+        for j in getattr(self, "results", []):
+            pairs = j["value"].get("pairs")
+            if pairs is None:
+                continue
+            name = j["value"]["result"]
+            with open(os.path.join(directory, name), "wb") as fh:
+                for key, values in pairs:
+                    fh.write(result_line(key, values))
+            names.append(name)
+        return names
+
+
 new = server.new

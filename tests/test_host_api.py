@@ -214,3 +214,34 @@ def test_general_reducer_runs_on_the_host_over_device_groups(corpus, golden_word
     s.loop()
     assert got == {k: [1, sum(c)] for k, _, c in golden_wordcount}
     s.board.ctx.close()
+
+
+def test_exported_result_files_equal_the_oracles(corpus, golden_wordcount, tmp_path):
+    """server:export_results writes result.P<kk> files byte-identical to what the reference's reduce jobs
+    write (oracle restatement of job.lua:272-273 / server.lua:313-321) for the test.sh corpus"""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import oracle as O
+    keep = WordCount.finalfn
+
+    def finalfn_keep(it):  # finalfn returning false keeps the results (server.lua:386-404)
+        keep(it)
+        return False
+    WordCount.finalfn = finalfn_keep
+    try:
+        s = run_config("init-script", "export-results", ctx_factory=StandInCtx)
+    finally:
+        WordCount.finalfn = keep
+    out = tmp_path / "results"
+    out.mkdir()
+    names = s.export_results(str(out))
+    e = O.Engine(O.PART_FNV_LUA, 15, combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
+    for job, path in enumerate(corpus):
+        e.map_job(job + 1, text=open(path, "rb").read())
+    e.reduce_all()
+    want = {n: data for n, _, data in e.results()}
+    e.close()
+    assert sorted(names) == sorted(want)
+    for n in names:
+        assert (out / n).read_bytes() == want[n], n
