@@ -245,3 +245,27 @@ def test_exported_result_files_equal_the_oracles(corpus, golden_wordcount, tmp_p
     assert sorted(names) == sorted(want)
     for n in names:
         assert (out / n).read_bytes() == want[n], n
+
+
+def test_finalfn_loop_runs_another_iteration(corpus, golden_wordcount):
+    """finalfn returning "loop" re-runs taskfn/map/reduce on a reset ctx (server.lua:386-404); results of the
+    previous iteration are dropped, the final answer is the last iteration's"""
+    calls = []
+    keep = WordCount.finalfn
+
+    def finalfn_loop_once(it):
+        pairs = {k: v[0] for k, v in it}
+        calls.append(pairs)
+        return "loop" if len(calls) == 1 else True
+    WordCount.finalfn = finalfn_loop_once
+    try:
+        s = run_config("init-script", "loop-task", ctx_factory=StandInCtx)
+    finally:
+        WordCount.finalfn = keep
+    assert len(calls) == 2 and calls[0] == calls[1] and s.stats["iteration"] == 2 and s.finished
+    want = {}
+    for job in range(4):
+        for t in expand_tokens(golden_wordcount, job):
+            want[t] = want.get(t, 0) + 1
+    assert calls[1] == want
+    assert all("pairs" not in j["value"] for j in s.results)  # true / "loop": results removed (server.lua:395-401)
