@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,7 +26,9 @@ struct Range {
   uint64_t owner;  // map handle serial
 };
 constexpr size_t kStageRecs = 1 << 16;
-enum { EV_START, EV_CSTART, EV_COMBINE, EV_HIST, EV_PLAN, EV_SCATTER, EV_EXCH, EV_SORT, EV_BIG, EV_END, EV_PROBE, EV_N };
+enum { EV_START, EV_CSTART, EV_COMBINE, EV_HIST, EV_PLAN, EV_GATH, EV_SCATTER, EV_EXCH, EV_SORT, EV_BIG, EV_END, EV_PROBE, EV_N };
+constexpr uint32_t kSampleKeys = 1u << 18;      // keys sampled to decide between key-ordered and hash sub-bins
+constexpr uint64_t kSplitMaxBinsHost = 1024;    // bins one level of k_split_tma distinguishes
 }  // namespace
 
 struct mrhbm_ctx {
@@ -51,13 +54,18 @@ struct mrhbm_ctx {
   uint64_t hd_cap = 0, bl_cap = 0;
   void *recvbuf = nullptr, *bigbuf = nullptr;
   uint64_t recv_cap = 0, big_cap = 0;
-  // EXPERIMENTAL fused split -> peer-memory exchange (MRHBM_P2P=1, u64 records): every rank's receive buffer is
-  // exported with cudaIpcGetMemHandle and mapped by its peers; level 2 of the exact split stores into them
-  bool p2p = false;
-  void* peer_recv[8] = {nullptr};
-  uint64_t p2p_cap = 0;                       // records every rank's receive buffer holds (same on all ranks)
-  unsigned long long *d_route = nullptr, *h_route = nullptr;  // kRouteWords each
-  uint32_t *d_ipc = nullptr, *h_ipc = nullptr;                // 16 words per rank: the IPC handles
+  // coarse regions of the two-level split (optimistic layout).  On several GPUs every rank's buffer is exported
+  // with cudaIpcGetMemHandle and mapped by its peers: level 2 of a region's owner pulls it from all of them.
+  void* regions = nullptr;
+  uint64_t regions_cap = 0;                   // records (the same on all ranks)
+  void* peer_regions[8] = {nullptr};          // peer_regions[rank] == regions
+  bool ipc_failed = false;                    // peer mapping unavailable: NCCL exchange (exact layout) instead
+  uint32_t* d_l1all = nullptr;                // all ranks' level-1 fill levels
+  uint64_t l1all_cap = 0;
+  uint32_t *d_ipc = nullptr, *h_ipc = nullptr;  // 16 words per rank: the IPC handles
+  uint32_t *d_sample = nullptr, *h_sample = nullptr;  // 256 buckets of the key sample
+  uint32_t tune = 0;                          // MRHBM_TUNE bits read once at init (measurement hooks): 1 = no fast path
+  std::recursive_mutex mu;                    // entry points serialise per ctx
   uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
   bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
@@ -134,6 +142,23 @@ int fail(mrhbm_ctx* c, int code, const char* fmt, ...) {
                   cudaGetErrorString(e_));                                                        \
     }                                                                                             \
   } while (0)
+
+// Every entry point that touches CUDA runs with the ctx's device current (a ctx may be driven from any
+// thread, and several ctxs on different GPUs may share one thread) and holds the ctx lock: the handle is
+// single-caller by contract (include/mrhbm.h), the lock turns a violation into serialisation instead of a race.
+struct Entry {
+  std::lock_guard<std::recursive_mutex> lk;
+  int prev = -1;
+  explicit Entry(mrhbm_ctx* c) : lk(c->mu) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != c->dev) cudaSetDevice(c->dev);
+    else prev = -1;
+  }
+  ~Entry() {
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+  }
+};
 
 int pool_reserve(mrhbm_ctx* c, uint64_t n, uint64_t* off) {
   if (c->pool_used + n > c->pool_cap) {
@@ -214,7 +239,8 @@ void invalidate(mrhbm_ctx* c) {
   c->compacted = false;
 }
 
-int ensure_buffers(mrhbm_ctx* c, uint64_t B, uint64_t N) {
+// per-bin arrays (offsets, group counts, spread-out atomic counters) for B bins
+int ensure_small_arrays(mrhbm_ctx* c, uint64_t B) {
   if (B + 1 > c->B_cap) {
     uint64_t nb = B + 1 + (B >> 2);
     uint32_t** ptrs[] = {&c->sb.bin_off, &c->sb.ucount, &c->sb.uoff, &c->sb.big_list};
@@ -236,6 +262,12 @@ int ensure_buffers(mrhbm_ctx* c, uint64_t B, uint64_t N) {
     c->ctr_cap = nc;
   }
   if (!c->sb.counters) CU(c, cudaMalloc((void**)&c->sb.counters, 8 * sizeof(uint32_t)));
+  return 0;
+}
+
+int ensure_buffers(mrhbm_ctx* c, uint64_t B, uint64_t N) {
+  int rc = ensure_small_arrays(c, B);
+  if (rc) return rc;
   uint64_t need = std::max<uint64_t>(N, 1);
   if (need > c->mid_cap) {
     if (c->sb.mid) CU(c, cudaFree(c->sb.mid));
@@ -362,7 +394,9 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaMalloc((void**)&c->d_hll, 8 * kHllRegs * sizeof(uint32_t)));
   CU(c, cudaHostAlloc((void**)&c->h_hll, 8 * kHllRegs * sizeof(uint32_t), cudaHostAllocDefault));
   c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
-  if (const char* e = getenv("MRHBM_CTR_SHIFT")) c->ctr_shift = (uint32_t)std::min(7, std::max(0, atoi(e)));  // tuning hook
+  CU(c, cudaMalloc((void**)&c->d_sample, 256 * sizeof(uint32_t)));
+  CU(c, cudaHostAlloc((void**)&c->h_sample, 256 * sizeof(uint32_t), cudaHostAllocDefault));
+  if (const char* e = getenv("MRHBM_TUNE")) c->tune = (uint32_t)strtoul(e, nullptr, 0);  // measurement hooks, read once
   if (cfg->reserve_pairs) {
     uint64_t off;
     int rc = pool_reserve(c, cfg->reserve_pairs, &off);
@@ -374,19 +408,21 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
 
 void mrhbm_destroy(mrhbm_ctx* c) {
   if (!c) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  if (c->stream) cudaSetDevice(c->dev);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int r = 0; r < 8; r++)
-    if (c->p2p && r != c->rank && c->peer_recv[r]) cudaIpcCloseMemHandle(c->peer_recv[r]);
-  if (c->d_route) cudaFree(c->d_route);
-  if (c->h_route) cudaFreeHost(c->h_route);
+    if (c->world > 1 && r != c->rank && c->peer_regions[r]) cudaIpcCloseMemHandle(c->peer_regions[r]);
   if (c->d_ipc) cudaFree(c->d_ipc);
   if (c->h_ipc) cudaFreeHost(c->h_ipc);
+  if (c->h_sample) cudaFreeHost(c->h_sample);
   if (c->comm) comm_destroy(c->comm);
   void* frees[] = {c->pool,        c->sb.hist,     c->sb.bin_off, c->sb.cursor,   c->sb.ucount, c->sb.uoff,
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
                    c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
-                   c->d_hll,       c->l1buf};
+                   c->d_hll,       c->l1buf,       c->regions,    c->d_l1all,     c->d_sample};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -396,6 +432,7 @@ void mrhbm_destroy(mrhbm_ctx* c) {
   for (int i = 0; i < EV_N; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (prev >= 0) cudaSetDevice(prev);
   cudaGetLastError();
   delete c;
 }
@@ -405,6 +442,7 @@ uint32_t mrhbm_record_bytes(const mrhbm_ctx* c) { return c ? (uint32_t)c->rb : 0
 
 void* mrhbm_host_alloc(mrhbm_ctx* c, size_t bytes) {
   void* p = nullptr;
+  Entry g(c);
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     if (c) c->err = "cudaHostAlloc failed";
@@ -421,6 +459,7 @@ void mrhbm_host_free(mrhbm_ctx*, void* p) {
 // ---------------------------------------------------------------------------
 int mrhbm_map_begin(mrhbm_ctx* c, const char* job, mrhbm_map** out) {
   if (!c || !job || !out) return MRHBM_E_INVAL;
+  Entry g(c);
   if (!c->stream) return fail(c, MRHBM_E_INVAL, "ctx failed to initialise");
   mrhbm_map* m = new mrhbm_map();
   m->ctx = c;
@@ -433,6 +472,7 @@ int mrhbm_map_begin(mrhbm_ctx* c, const char* job, mrhbm_map** out) {
 int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
   if (!m) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "ctx holds u64 keys");
   if (klen >= (size_t)c->kb)
     return fail(c, MRHBM_E_KEY, "key of %zu bytes does not fit the %d-byte record class", klen, c->rb);
@@ -449,6 +489,7 @@ int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
 int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint32_t value) {
   if (!m) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (c->cfg.key_kind != MRHBM_KEY_U64) return fail(c, MRHBM_E_INVAL, "ctx holds string keys");
   unsigned char* slot;
   int rc = stage_slot(m, &slot);
@@ -463,6 +504,7 @@ int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint32_t value) {
 int mrhbm_emit_batch(mrhbm_map* m, const void* recs, size_t n) {
   if (!m || (!recs && n)) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (!n) return MRHBM_OK;
   int rc = stage_flush(m);  // keep emission order
   if (rc) return rc;
@@ -481,6 +523,7 @@ int mrhbm_emit_batch(mrhbm_map* m, const void* recs, size_t n) {
 int mrhbm_emit_device(mrhbm_map* m, const void* drecs, size_t n) {
   if (!m || (!drecs && n)) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (!n) return MRHBM_OK;
   int rc = stage_flush(m);
   if (rc) return rc;
@@ -495,6 +538,7 @@ int mrhbm_emit_device(mrhbm_map* m, const void* drecs, size_t n) {
 int mrhbm_map_gen_u64(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n) {
   if (!m) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (c->rb != 16) return fail(c, MRHBM_E_INVAL, "gen_u64 needs a u64-key ctx");
   int rc = stage_flush(m);
   if (rc) return rc;
@@ -511,6 +555,7 @@ int mrhbm_map_gen_zipf(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n, 
                        uint64_t V) {
   if (!m || !table || !V) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (c->rb != 32) return fail(c, MRHBM_E_INVAL, "gen_zipf needs 32-byte string records (max_key_bytes <= 27)");
   if (!c->d_table || c->d_table_V != V || c->d_table_first != table[0] || c->d_table_last != table[V - 1]) {
     if (c->d_table) CU(c, cudaFree(c->d_table));
@@ -536,6 +581,7 @@ int mrhbm_map_gen_zipf(mrhbm_map* m, uint64_t seed, uint64_t start, uint64_t n, 
 int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* words) {
   if (!m || (!text && len)) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   if (words) *words = 0;
   if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "wordcount needs a string-key ctx");
   if (!len) return MRHBM_OK;
@@ -594,6 +640,7 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
 
 int mrhbm_pool_read(mrhbm_ctx* c, uint64_t first, uint64_t n, void* host_out) {
   if (!c || (!host_out && n)) return MRHBM_E_INVAL;
+  Entry g(c);
   uint64_t skip = first, done = 0;
   for (auto& r : live_ranges(c)) {
     if (done == n) break;
@@ -615,6 +662,7 @@ int mrhbm_pool_read(mrhbm_ctx* c, uint64_t first, uint64_t n, void* host_out) {
 int mrhbm_map_commit(mrhbm_map* m) {
   if (!m) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   int rc = stage_flush(m);
   if (rc == 0 && m->async_reads) {
     cudaError_t e = cudaStreamSynchronize(c->stream);  // caller may reuse its pinned buffers now
@@ -637,6 +685,7 @@ int mrhbm_map_commit(mrhbm_map* m) {
 void mrhbm_map_abort(mrhbm_map* m) {
   if (!m) return;
   mrhbm_ctx* c = m->ctx;
+  Entry g(c);
   cudaStreamSynchronize(c->stream);
   for (Range& r : c->ranges)
     if (r.owner == m->serial && r.state == R_OPEN) r.state = R_DEAD;
@@ -650,6 +699,7 @@ void mrhbm_map_abort(mrhbm_map* m) {
 
 int mrhbm_reset(mrhbm_ctx* c) {
   if (!c) return MRHBM_E_INVAL;
+  Entry g(c);
   c->ranges.clear();
   c->pool_used = 0;
   invalidate(c);
@@ -677,8 +727,10 @@ BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered, uint32_t rep
   bp.ordered = ordered;
   bp.ctr_shift = c->ctr_shift;
   bp.world = (uint32_t)c->world;
+  bp.wshift = 0xffffffffu;
+  for (uint32_t k = 0; k < 4; k++)
+    if ((1u << k) == bp.world) bp.wshift = k;
   for (int r = 0; r <= 8; r++) bp.pbase[r] = c->pbase[r];
-  if (const char* e = getenv("MRHBM_DEBUG_SCATTER")) bp.debug = (uint32_t)atoi(e);  // profiling hook, results invalid
   return bp;
 }
 
@@ -695,6 +747,100 @@ int gather_u32(mrhbm_ctx* c, uint32_t mine, uint32_t* all) {
   CU(c, cudaMemcpyAsync(c->h_small + 16, c->d_small + 16, 4 * c->world, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   for (int r = 0; r < c->world; r++) all[r] = c->h_small[16 + r];
+  return 0;
+}
+
+// all ranks: k <= 2 words from every rank (host values in, all[rank * k + i] out); synchronises the stream
+int gather_words(mrhbm_ctx* c, const uint32_t* mine, int k, uint32_t* all) {
+  if (c->world == 1) {
+    for (int i = 0; i < k; i++) all[i] = mine[i];
+    return 0;
+  }
+  for (int i = 0; i < k; i++) c->h_small[i] = mine[i];
+  CU(c, cudaMemcpyAsync(c->d_small, c->h_small, 4 * k, cudaMemcpyHostToDevice, c->stream));
+  int rc = comm_allgather_u32(c->comm, c->d_small, c->d_small + 16, (size_t)k, c->stream, &c->err);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_small + 16, c->d_small + 16, 4 * (size_t)k * c->world, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < k * c->world; i++) all[i] = c->h_small[16 + i];
+  return 0;
+}
+
+int ensure_records(mrhbm_ctx* c, void** buf, uint64_t* cap, uint64_t need);
+
+// The region buffer of the two-level split.  One GPU: a plain allocation.  Several GPUs: COLLECTIVE -- every
+// rank calls it with the same `need`; all buffers grow together and their IPC handles are re-exchanged, so that
+// level 2 of every rank can pull its regions from every peer.  *shared_ok = false (on all ranks alike) when peer
+// mapping is unavailable on any rank.
+int ensure_regions(mrhbm_ctx* c, uint64_t need, bool* shared_ok) {
+  *shared_ok = true;
+  if (c->world == 1) return ensure_records(c, &c->regions, &c->regions_cap, need);
+  if (c->ipc_failed) {
+    *shared_ok = false;
+    return 0;
+  }
+  if (need <= c->regions_cap) return 0;
+  const int G = c->world, me = c->rank;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < G; r++) {
+    if (r != me && c->peer_regions[r]) cudaIpcCloseMemHandle(c->peer_regions[r]);
+    c->peer_regions[r] = nullptr;
+  }
+  cudaGetLastError();
+  uint32_t flags[8];
+  int rc = gather_u32(c, 0, flags);  // every rank has unmapped its peers before anybody frees
+  if (rc) return rc;
+  need += need / 8 + 1024;
+  if (c->regions) CU(c, cudaFree(c->regions));
+  c->regions = nullptr;
+  c->regions_cap = 0;
+  CU(c, cudaMalloc(&c->regions, need * c->rb));
+  bool ok = true;
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof h);
+  if (cudaIpcGetMemHandle(&h, c->regions) != cudaSuccess) {
+    cudaGetLastError();
+    ok = false;
+  }
+  memcpy(c->h_ipc, &h, 64);
+  CU(c, cudaMemcpyAsync(c->d_ipc, c->h_ipc, 64, cudaMemcpyHostToDevice, c->stream));
+  rc = comm_allgather_u32(c->comm, c->d_ipc, c->d_ipc + 16, 16, c->stream, &c->err);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->h_ipc + 16, c->d_ipc + 16, 64 * (size_t)G, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  rc = gather_u32(c, ok ? 0u : 1u, flags);  // a rank that could not export: nobody opens anything
+  if (rc) return rc;
+  for (int r = 0; r < G; r++) ok = ok && flags[r] == 0;
+  if (ok) {
+    for (int r = 0; r < G; r++) {
+      if (r == me) {
+        c->peer_regions[r] = c->regions;
+        continue;
+      }
+      cudaIpcMemHandle_t hr;
+      memcpy(&hr, c->h_ipc + 16 + 16 * r, 64);
+      if (cudaIpcOpenMemHandle(&c->peer_regions[r], hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        c->peer_regions[r] = nullptr;
+        ok = false;
+      }
+    }
+    rc = gather_u32(c, ok ? 0u : 1u, flags);
+    if (rc) return rc;
+    for (int r = 0; r < G; r++) ok = ok && flags[r] == 0;
+  }
+  if (!ok) {
+    for (int r = 0; r < G; r++) {
+      if (r != me && c->peer_regions[r]) cudaIpcCloseMemHandle(c->peer_regions[r]);
+      c->peer_regions[r] = nullptr;
+    }
+    cudaGetLastError();
+    c->ipc_failed = true;
+    *shared_ok = false;
+    return 0;
+  }
+  c->regions_cap = need;
   return 0;
 }
 
@@ -726,44 +872,6 @@ int ensure_multi_buffers(mrhbm_ctx* c, uint64_t B, uint64_t Bl) {
 
 int ensure_records(mrhbm_ctx* c, void** buf, uint64_t* cap, uint64_t need);
 int gather_u32(mrhbm_ctx* c, uint32_t mine, uint32_t* all);
-
-// EXPERIMENTAL (MRHBM_P2P=1).  Collective: every rank calls it with the same `need` (records the fullest
-// receive buffer of the job must hold).  Grows all receive buffers together and re-exchanges their IPC handles.
-int p2p_ensure(mrhbm_ctx* c, uint64_t need) {
-  if (need <= c->p2p_cap) return 0;
-  const int G = c->world, me = c->rank;
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  CU(c, cudaStreamSynchronize(c->stream));
-  for (int r = 0; r < G; r++) {
-    if (r != me && c->peer_recv[r]) CU(c, cudaIpcCloseMemHandle(c->peer_recv[r]));
-    c->peer_recv[r] = nullptr;
-  }
-  uint32_t all[8];
-  int rc = gather_u32(c, 0, all);  // every rank has unmapped its peers before anybody frees
-  if (rc) return rc;
-  need += need / 8 + 1024;
-  rc = ensure_records(c, &c->recvbuf, &c->recv_cap, need);
-  if (rc) return rc;
-  cudaIpcMemHandle_t h;
-  CU(c, cudaIpcGetMemHandle(&h, c->recvbuf));
-  memcpy(c->h_ipc, &h, 64);
-  CU(c, cudaMemcpyAsync(c->d_ipc, c->h_ipc, 64, cudaMemcpyHostToDevice, c->stream));
-  rc = comm_allgather_u32(c->comm, c->d_ipc, c->d_ipc + 16, 16, c->stream, &c->err);
-  if (rc) return rc;
-  CU(c, cudaMemcpyAsync(c->h_ipc + 16, c->d_ipc + 16, 64 * (size_t)G, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  for (int r = 0; r < G; r++) {
-    if (r == me) {
-      c->peer_recv[r] = c->recvbuf;
-      continue;
-    }
-    cudaIpcMemHandle_t hr;
-    memcpy(&hr, c->h_ipc + 16 + 16 * r, 64);
-    CU(c, cudaIpcOpenMemHandle(&c->peer_recv[r], hr, cudaIpcMemLazyEnablePeerAccess));
-  }
-  c->p2p_cap = need;
-  return 0;
-}
 
 int ensure_records(mrhbm_ctx* c, void** buf, uint64_t* cap, uint64_t need) {
   need = std::max<uint64_t>(need, 1);
@@ -901,106 +1009,249 @@ void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
   c->stats = st;
 }
 
-// ---- one GPU: hist -> scan -> scatter -> sort+reduce ---------------------------------------
-int shuffle_single(mrhbm_ctx* c) {
-  uint64_t N_in = 0;
-  for (auto& r : live_ranges(c)) N_in += r.second;
-  if (N_in >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N_in);
+// ---- the default path: optimistic fixed-capacity layout, no histogram pass, any number of GPUs --------
+//
+//   level 1  k_split_tma   committed pairs -> coarse regions (this rank's region buffer, all regions of the job)
+//   [G > 1]  all-gather of the level-1 fill levels (a few KB): counts for the peers + the barrier that orders
+//            every rank's level 1 before anybody's level 2
+//   level 2  k_split_tma   the owner of a region pulls it from every rank's region buffer (NVLink bulk copies
+//            into shared memory, overlapped with the split of the previous tile) -> fine bins
+//   sort     k_sort_reduce_u64 / k_sort_reduce / k_agg_bins on local bins
+// Every bin and region has a fixed capacity (mean + slack); the claim cursor doubles as the count.  A full one
+// sets ERRF_CAPACITY, nothing is lost (the input stays in the pool) and the exact layout below takes over, for
+// good on this ctx.  Returns 0 with *done = true, 0 with *done = false (fall back), or an error.
+int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st,
+                 bool* done) {
+  *done = false;
+  const int G = c->world, me = c->rank;
   const uint32_t P = c->cfg.num_partitions;
-  int rc = 0;
-  uint32_t nbig = 0, ordered = 1;
-  mrhbm_stats st{};
-  st.pairs = N_in;
   cudaStream_t s = c->stream;
-  uint64_t B = 0, N = 0;
-  std::vector<Src> live;
-  CU(c, cudaEventRecord(c->ev[EV_START], s));
-  double distinct = -1;
-  rc = collect_sources(c, live, &N, st, &distinct);
-  if (rc) return rc;
-  CU(c, cudaEventRecord(c->ev[EV_CSTART], s));
   const bool agg = distinct >= 0;  // duplicate-heavy: aggregate per bin, bins sized by distinct keys
-  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, N);
-  bool skip_ordered = c->no_ordered || agg;
-  // ---- optimistic single pass: no histogram.  Hash-balanced bins almost never exceed their
-  // capacity (mean = cap - 6 sigma); the cursor claim doubles as the count.  A full bin sets
-  // ERRF_CAPACITY and the exact two-pass layout below takes over (and stays, for this ctx).
-  if (!agg && !c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && N > 0 && (uint64_t)P * S < (1ull << 31)) {
-    B = (uint64_t)P * S;
-    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !skip_ordered) || S == 1);
-    rc = ensure_buffers(c, B, B * c->cap);
+  int rc = 0;
+  // ---- would key-ordered sub-bins be balanced?  sample the keys before anything moves
+  const bool want_ordered = c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !c->no_ordered && !agg;
+  uint32_t nonuniform = 0;
+  if (want_ordered && N >= 4096) {
+    CU(c, cudaMemsetAsync(c->d_sample, 0, 256 * sizeof(uint32_t), s));
+    uint64_t total = 0;
+    for (auto& r : live) {
+      uint32_t ns = (uint32_t)std::min<uint64_t>(r.n, (uint64_t)((double)kSampleKeys * (double)r.n / (double)N) + 1);
+      st.launches += launch_sample_u64(r.p, r.n, ns, c->d_sample, s);
+      total += ns;
+    }
+    CU(c, cudaMemcpyAsync(c->h_sample, c->d_sample, 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    uint32_t mx = 0;
+    for (int i = 0; i < 256; i++) mx = std::max(mx, c->h_sample[i]);
+    const double mean = (double)total / 256.0;
+    nonuniform = (double)mx > mean * 1.08 + 5.0 * std::sqrt(mean) + 2.0;
+  }
+  // ---- job-wide facts.  On several GPUs this all-gather is also the barrier that keeps a rank from refilling
+  // its region buffer while a peer's level 2 of the previous shuffle may still read it.
+  uint32_t mine[2] = {(uint32_t)N, nonuniform}, all[16];
+  rc = gather_words(c, mine, 2, all);
+  if (rc) return rc;
+  uint64_t Nglobal = 0, Nmax = 0;
+  for (int r = 0; r < G; r++) {
+    Nglobal += all[2 * r];
+    Nmax = std::max<uint64_t>(Nmax, all[2 * r]);
+    nonuniform |= all[2 * r + 1];
+  }
+  if (Nglobal == 0) return 0;  // nothing to do here: the exact path handles the empty shuffle
+  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, Nglobal);
+  for (int widen = 0;; widen++) {
+    const uint64_t B = (uint64_t)P * S;
+    if (B >= (1ull << 31)) return 0;
+    const uint32_t ordered = (want_ordered && !nonuniform) || S == 1;
+    uint64_t Bl_of[8], Bl_max = 0;
+    for (int r = 0; r < G; r++) {
+      Bl_of[r] = (uint64_t)(c->pbase[r + 1] - c->pbase[r]) * S;
+      Bl_max = std::max(Bl_max, Bl_of[r]);
+    }
+    const uint64_t Bl = Bl_of[me];
+    // slots per fine bin: the sort capacity, or (aggregation) the expected records of a bin + 30 %
+    uint32_t bin_stride = c->cap;
+    if (agg) {
+      const double mean = (double)Nglobal / (double)B;
+      bin_stride = (uint32_t)std::min(4.0e9, mean * 1.3 + 8.0 * std::sqrt(mean) + 64.0);
+      bin_stride = (bin_stride + 7u) & ~7u;
+    }
+    // ---- levels.  One GPU, few bins: level 1 goes straight into the fine bins.
+    SplitPlan pl{};
+    const bool single_level = G == 1 && B <= kSplitMaxBinsHost;
+    uint32_t F = 1;
+    if (!single_level) {
+      while ((uint64_t)F * F < B) F <<= 1;  // power of two >= sqrt(B): both levels see about the same fan-out
+      for (;; F <<= 1) {
+        uint64_t c1 = 0;
+        for (int r = 0; r < G; r++) c1 += (Bl_of[r] + F - 1) / F;
+        if (c1 <= kSplitMaxBinsHost) break;
+      }
+      if (F > kSplitMaxBinsHost) return 0;  // more bins than two levels reach: exact path
+    }
+    pl.rbase[0] = 0;
+    for (int r = 0; r < 8; r++) {
+      const uint64_t bl = r < G ? Bl_of[r] : 0;
+      pl.rbase[r + 1] = pl.rbase[r] + (uint32_t)((bl + F - 1) / F);
+      pl.fbase[r] = c->pbase[r] * S;
+    }
+    pl.fbase[8] = c->pbase[8] * S;
+    pl.B = (uint32_t)B;
+    pl.F = F;
+    pl.C1 = pl.rbase[G];
+    pl.C1_local = pl.rbase[me + 1] - pl.rbase[me];
+    pl.cap = bin_stride;
+    pl.ndest = (uint32_t)G;
+    pl.me = (uint32_t)me;
+    {
+      // one rank's contribution to one region: F of the B bins, hash balanced
+      const double mean = (double)Nmax * (double)F / (double)B * (agg ? 1.3 : 1.0);
+      const double ss = single_level ? (double)bin_stride : mean + 8.0 * std::sqrt(mean) + 64.0;
+      if (ss >= 4.0e9) return 0;
+      pl.sub_stride = ((uint64_t)ss + 7u) & ~7ull;
+    }
+    // ---- buffers
+    rc = ensure_small_arrays(c, std::max<uint64_t>(Bl, pl.C1));
     if (rc) return rc;
-    BinParams bp = make_bp(c, S, ordered);
+    rc = ensure_records(c, &c->sb.mid, &c->mid_cap, Bl * bin_stride);
+    if (rc) return rc;
+    rc = ensure_out(c, Bl * (uint64_t)c->cap);
+    if (rc) return rc;
+    if (!single_level) {
+      bool shared_ok = true;
+      rc = ensure_regions(c, (uint64_t)pl.C1 * pl.sub_stride, &shared_ok);
+      if (rc) return rc;
+      if (!shared_ok) {  // peer mapping unavailable (decided by all ranks together): NCCL exchange instead
+        c->no_optimistic = true;
+        return 0;
+      }
+      if (G > 1) {
+        const uint64_t words = ((uint64_t)pl.C1 << c->ctr_shift) * G;
+        if (words > c->l1all_cap) {
+          if (c->d_l1all) CU(c, cudaFree(c->d_l1all));
+          c->d_l1all = nullptr;
+          c->l1all_cap = 0;
+          CU(c, cudaMalloc((void**)&c->d_l1all, (words + words / 4) * sizeof(uint32_t)));
+          c->l1all_cap = words + words / 4;
+        }
+      }
+    }
+    pl.cursor1 = c->sb.hist;
+    pl.cursor = c->sb.cursor;
+    pl.l1 = single_level ? c->sb.mid : c->regions;
+    pl.mid = c->sb.mid;
+    pl.err_flags = c->sb.counters + CNT_ERR;
+    pl.base_off = nullptr;
+    for (int r = 0; r < 8; r++) pl.peer[r] = (unsigned long long)(uintptr_t)(G == 1 ? (r == 0 ? c->regions : nullptr) : c->peer_regions[r]);
+    pl.l1_counts = G == 1 ? c->sb.hist : c->d_l1all;
+    pl.l1_zstride = G == 1 ? 0 : ((uint64_t)pl.C1 << c->ctr_shift);
+    const BinParams bp = make_bp(c, S, ordered);
     st.attempts++;
-    CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
+    CU(c, cudaMemsetAsync(c->sb.hist, 0, (((uint64_t)pl.C1) << c->ctr_shift) * sizeof(uint32_t), s));
+    if (!single_level) CU(c, cudaMemsetAsync(c->sb.cursor, 0, (std::max<uint64_t>(Bl, 1) << c->ctr_shift) * sizeof(uint32_t), s));
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
-    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));  // re-recorded after level 1 when the split runs
-    // many bins: two-level coalesced split (shared-memory claims, contiguous stores); few bins:
-    // direct scatter
-    uint32_t F = 1, C1 = 0;
-    while ((uint64_t)F * F < B) F <<= 1;  // power of two >= sqrt(B)
-    C1 = (uint32_t)((B + F - 1) / F);
-    const bool split = B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT");
-    if (split) {
-      rc = ensure_records(c, &c->l1buf, &c->l1_cap, (uint64_t)C1 * F * c->cap);
+    for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+    CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
+    if (G > 1) {
+      rc = comm_allgather_u32(c->comm, c->sb.hist, c->d_l1all, (size_t)pl.C1 << c->ctr_shift, s, &c->err);
       if (rc) return rc;
-      CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));  // coarse fill levels
-      for (auto& r : live)
-        st.launches += launch_split2(c->rb, r.p, r.n, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                     c->sb.mid, c->sb.counters + CNT_ERR, false, nullptr, s);
-      CU(c, cudaEventRecord(c->ev[EV_PLAN], s));  // ms_plan = level 1, ms_scatter = level 2
-      st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                   c->sb.mid, c->sb.counters + CNT_ERR, true, nullptr, s);
-    } else {
-      for (auto& r : live)
-        st.launches += launch_scatter_fixed(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, c->cap, c->sb.counters + CNT_ERR, s);
     }
+    CU(c, cudaEventRecord(c->ev[EV_GATH], s));
+    if (!single_level) st.launches += launch_split_l2(c->rb, bp, pl, s);
     CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     c->sb.src = c->sb.mid;
     c->sb.nseg = 1;
-    c->sb.stride = c->cap;
+    c->sb.stride = bin_stride;
+    c->sb.out_stride = c->cap;
     c->sb.rep_shift = 0;
     c->sb.ctr_shift = c->ctr_shift;
-    set_range_hint(c->sb, S, ordered);
-    st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+    // single level: the level-1 cursors ARE the fine fill levels
+    uint32_t* fine_cursor = single_level ? c->sb.hist : c->sb.cursor;
+    ShuffleBuffers v = c->sb;
+    v.cursor = fine_cursor;
+    set_range_hint(v, S, ordered);
+    if (Bl) {
+      st.launches += agg ? launch_agg_bins(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s)
+                         : launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
+    }
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
-    st.launches += launch_exscan(c->sb.ucount, (uint32_t)B, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
-                                 c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
-    c->h_uoff.resize(B + 1);
-    CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    c->h_uoff.assign(Bl + 1, 0);
+    if (Bl) {
+      st.launches += launch_exscan(c->sb.ucount, (uint32_t)Bl, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
+                                   c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
+      CU(c, cudaMemcpyAsync(c->h_uoff.data(), c->sb.uoff, (Bl + 1) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    // pairs this rank reduced (and how many of them came from peers)
+    st.launches += launch_region_totals(pl.l1_counts, pl.l1_zstride, (uint32_t)G, (uint32_t)me, pl.rbase[me], pl.C1_local,
+                                        c->ctr_shift, (uint32_t)std::min<uint64_t>(single_level ? bin_stride : pl.sub_stride, 0xffffffffull),
+                                        c->d_acc, s);
+    CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaEventRecord(c->ev[EV_END], s));
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
-    if (!(c->h_counters[CNT_ERR] & ERRF_CAPACITY)) {
-      c->h_big.clear();
-      c->rv = c->sb;
-      c->sb.stride = 0;
-      c->B = (uint32_t)B;
-      c->S = S;
-      c->ordered = ordered;
-      c->N = N_in;
-      c->N_recv = N;
-      c->bin_base = 0;
-      c->groups = c->h_uoff[B];
-      c->shuffled = true;
-      c->compacted = false;
-      st.bins = (uint32_t)B;
-      st.sub_bins = S;
-      st.big_bins = 0;
-      st.groups = c->groups;
-      st.ms_exchange = 0;
-      finish_stats(c, st);
-      return MRHBM_OK;
+    uint32_t ef = c->h_counters[CNT_ERR];
+    if (G > 1) {  // every rank must take the same branch; also: nobody leaves while a peer still reads its regions
+      uint32_t efs[8];
+      rc = gather_u32(c, ef, efs);
+      if (rc) return rc;
+      for (int r = 0; r < G; r++) ef |= efs[r];
     }
+    if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
+    if (ef & ERRF_CAPACITY) {  // skewed keys: the exact layout from now on
+      c->sb.stride = 0;
+      c->no_optimistic = true;
+      if ((ordered && S > 1) || nonuniform) c->no_ordered = true;  // key-ordered sub-bins overflowed, or would
+      return 0;
+    }
+    if (ef & ERRF_SKEW) {  // an aggregation table overflowed: more distinct keys in a bin than estimated
+      if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
+        S *= 2;
+        continue;
+      }
+      return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can aggregate");
+    }
+    c->h_big.clear();
+    c->rv = v;
     c->sb.stride = 0;
-    c->no_optimistic = true;
-    if (ordered && S > 1) skip_ordered = c->no_ordered = true;  // key-ordered sub-bins just overflowed
+    c->B = (uint32_t)Bl;
+    c->S = S;
+    c->ordered = ordered;
+    c->N = N_in;
+    c->N_recv = c->h_acc[0];
+    c->bin_base = c->pbase[me] * S;
+    c->groups = c->h_uoff[Bl];
+    c->shuffled = true;
+    c->compacted = false;
+    st.bins = (uint32_t)Bl;
+    st.sub_bins = S;
+    st.big_bins = 0;
+    st.groups = c->groups;
+    st.bytes_exchanged = (c->h_acc[0] - c->h_acc[1]) * (uint64_t)c->rb;
+    finish_stats(c, st);
+    // plan = level 1, exchange = the fill-level all-gather (waits for the slowest rank's level 1), scatter = level 2
+    // (on several GPUs: including the NVLink pulls)
+    c->stats.ms_exchange = ev_ms(c, EV_PLAN, EV_GATH);
+    c->stats.ms_scatter = ev_ms(c, EV_GATH, EV_SCATTER);
+    *done = true;
+    return MRHBM_OK;
   }
+}
+
+// ---- one GPU, exact layout: hist -> scan -> scatter -> sort+reduce (skewed keys, oversized bins) ---------
+int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st) {
+  const uint32_t P = c->cfg.num_partitions;
+  int rc = 0;
+  uint32_t nbig = 0, ordered = 1;
+  cudaStream_t s = c->stream;
+  uint64_t B = 0;
+  const bool agg = distinct >= 0;  // duplicate-heavy: aggregate per bin, bins sized by distinct keys
+  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, N);
+  bool skip_ordered = c->no_ordered || agg;
   // A bin that holds more distinct keys than one CTA sorts (ERRF_SKEW) is retried with
   // twice the sub-bins: distinct keys spread, hot keys keep collapsing in k_big_bins.
   for (int widen = 0;; widen++) {
@@ -1034,20 +1285,26 @@ int shuffle_single(mrhbm_ctx* c) {
         uint32_t F = 1;
         while ((uint64_t)F * F < B) F <<= 1;
         uint32_t C1 = (uint32_t)((B + F - 1) / F);
-        // (not for the aggregation pass: its few, very unevenly filled bins make the tile-local
-        // shared-memory claims collide; measured slower than the direct scatter there)
-        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
+        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
           rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
           if (rc) return rc;
           // relative fill levels: coarse levels live in hist (dead after the scan), fine levels in cursor
           CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
           CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
-          BinParams bq = bp;
-          for (auto& r : live)
-            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bq, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
-                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
-          st.launches += launch_split2(c->rb, nullptr, 0, bq, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s);
+          SplitPlan pl{};
+          pl.B = (uint32_t)B;
+          pl.F = F;
+          pl.C1 = pl.C1_local = C1;
+          pl.cap = c->cap;
+          pl.cursor1 = c->sb.hist;
+          pl.cursor = c->sb.cursor;
+          pl.l1 = c->l1buf;
+          pl.mid = c->sb.mid;
+          pl.err_flags = c->sb.counters + CNT_ERR;
+          pl.base_off = c->sb.bin_off;
+          pl.ndest = 1;
+          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+          st.launches += launch_split_l2(c->rb, bp, pl, s);
         } else {
           for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
         }
@@ -1121,24 +1378,13 @@ int shuffle_single(mrhbm_ctx* c) {
   return MRHBM_OK;
 }
 
-// ---- several GPUs: hist -> all-gather counts -> scatter (destination-major) -> all-to-all
+// ---- several GPUs, exact layout: hist -> all-gather counts -> scatter (destination-major) -> NCCL all-to-all
 //      -> sort+reduce of the owned partitions, each bin gathered from one segment per source
-int shuffle_multi(mrhbm_ctx* c) {
+int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st) {
   const int G = c->world, me = c->rank;
-  uint64_t N_in = 0, N = 0;
-  for (auto& r : live_ranges(c)) N_in += r.second;
-  if (N_in >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N_in);
   const uint32_t P = c->cfg.num_partitions;
   uint32_t all[8];
-  mrhbm_stats st{};
-  st.pairs = N_in;
-  std::vector<Src> live;
-  CU(c, cudaEventRecord(c->ev[EV_START], c->stream));
-  double distinct = -1;
-  int rc = collect_sources(c, live, &N, st, &distinct);
-  if (rc) return rc;
-  CU(c, cudaEventRecord(c->ev[EV_CSTART], c->stream));
-  rc = gather_u32(c, (uint32_t)N, all);
+  int rc = gather_u32(c, (uint32_t)N, all);
   if (rc) return rc;
   uint64_t Nglobal = 0;
   for (int r = 0; r < G; r++) Nglobal += all[r];
@@ -1148,7 +1394,6 @@ int shuffle_multi(mrhbm_ctx* c) {
   cudaStream_t s = c->stream;
   uint64_t B = 0, Bl = 0, total_recv = 0;
   uint64_t send_off[9], send_cnt[8], recv_off[9], recv_cnt[8];
-  bool p2p_done = false;
   ShuffleBuffers v{};
   for (int widen = 0;; widen++) {
     B = (uint64_t)P * S;
@@ -1159,7 +1404,8 @@ int shuffle_multi(mrhbm_ctx* c) {
     if (rc) return rc;
     rc = ensure_multi_buffers(c, B, Bl);
     if (rc) return rc;
-    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !agg) || S == 1);
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !agg && !c->no_ordered) || S == 1);
+    c->sb.stride = 0;
     for (int attempt = 0;; attempt++) {
       st.attempts++;
       BinParams bp = make_bp(c, S, ordered);
@@ -1184,50 +1430,30 @@ int shuffle_multi(mrhbm_ctx* c) {
       CU(c, cudaMemcpyAsync(c->h_small + 32, c->d_small + 32, 4 * G, cudaMemcpyDeviceToHost, s));
       CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
-      p2p_done = false;
       {
         // send buffer (destination-major exact layout) through the two-level coalesced split
         uint32_t F = 1;
         while ((uint64_t)F * F < B) F <<= 1;
         uint32_t C1 = (uint32_t)((B + F - 1) / F);
-        if (c->p2p && !agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
-          // EXPERIMENTAL fused split -> peer-memory exchange: level 2 stores every bin into its owner's receive
-          // buffer over NVLink; no NCCL data exchange follows.  The routing table needs the all-gathered counts.
-          uint32_t first9[9];
-          for (int d = 0; d <= 8; d++) first9[d] = c->pbase[d < G ? d : G] * S;
-          st.launches += launch_p2p_route(c->d_hall, (uint32_t)G, (uint32_t)B, (uint32_t)me, first9, c->sb.bin_off, c->d_route, s);
-          CU(c, cudaMemcpyAsync(c->h_route + 32, c->d_route + 32, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-          CU(c, cudaStreamSynchronize(s));
-          if (!agg && c->h_counters[CNT_GBIG] && ordered && S > 1) {  // same decision on every rank, see below
-            ordered = 0;
-            continue;
-          }
-          uint64_t fullest = 0;
-          for (int d = 0; d < G; d++) fullest = std::max<uint64_t>(fullest, c->h_route[32 + d]);
-          rc = p2p_ensure(c, fullest);  // collective; the previous sort of every rank is behind the counts all-gather
-          if (rc) return rc;
-          for (int d = 0; d < G; d++) c->h_route[d] = (unsigned long long)(uintptr_t)(d == me ? c->sb.mid : c->peer_recv[d]);
-          CU(c, cudaMemcpyAsync(c->d_route, c->h_route, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
           rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
           if (rc) return rc;
           CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
           CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
-          for (auto& r : live)
-            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bp, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
-                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
-          st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s, c->d_route);
-          p2p_done = true;
-        } else if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024 && !getenv("MRHBM_NO_SPLIT")) {
-          rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
-          if (rc) return rc;
-          CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
-          CU(c, cudaMemsetAsync(c->sb.cursor, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
-          for (auto& r : live)
-            st.launches += launch_split2(c->rb, r.p, r.n, with_src(bp, r), (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf,
-                                         c->sb.cursor, c->sb.mid, c->sb.counters + CNT_ERR, false, c->sb.bin_off, s);
-          st.launches += launch_split2(c->rb, nullptr, 0, bp, (uint32_t)B, c->cap, F, C1, c->sb.hist, c->l1buf, c->sb.cursor,
-                                       c->sb.mid, c->sb.counters + CNT_ERR, true, c->sb.bin_off, s);
+          SplitPlan pl{};
+          pl.B = (uint32_t)B;
+          pl.F = F;
+          pl.C1 = pl.C1_local = C1;
+          pl.cap = c->cap;
+          pl.cursor1 = c->sb.hist;
+          pl.cursor = c->sb.cursor;
+          pl.l1 = c->l1buf;
+          pl.mid = c->sb.mid;
+          pl.err_flags = c->sb.counters + CNT_ERR;
+          pl.base_off = c->sb.bin_off;
+          pl.ndest = 1;
+          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+          st.launches += launch_split_l2(c->rb, bp, pl, s);
         } else {
           for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
         }
@@ -1256,10 +1482,8 @@ int shuffle_multi(mrhbm_ctx* c) {
       recv_off[d + 1] = recv_off[d] + recv_cnt[d];
       if (d != me) st.bytes_exchanged += send_cnt[d];
     }
-    if (!p2p_done) {  // (the P2P path sized and exported the receive buffers before its level 2)
-      rc = ensure_records(c, &c->recvbuf, &c->recv_cap, total_recv);
-      if (rc) return rc;
-    }
+    rc = ensure_records(c, &c->recvbuf, &c->recv_cap, total_recv);
+    if (rc) return rc;
     rc = ensure_out(c, total_recv);
     if (rc) return rc;
     if (nbig) {
@@ -1273,13 +1497,7 @@ int shuffle_multi(mrhbm_ctx* c) {
       net_send[d] = d == me ? 0 : send_cnt[d];
       net_recv[d] = d == me ? 0 : recv_cnt[d];
     }
-    if (p2p_done) {
-      // the peers' stores are behind their level-2 kernels; one small collective orders them before the sort
-      uint32_t dummy[8];
-      rc = gather_u32(c, 0, dummy);
-    } else {
-      rc = comm_alltoallv(c->comm, c->sb.mid, send_off, net_send, c->recvbuf, recv_off, net_recv, s, &c->err);
-    }
+    rc = comm_alltoallv(c->comm, c->sb.mid, send_off, net_send, c->recvbuf, recv_off, net_recv, s, &c->err);
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[EV_EXCH], s));
     v = c->sb;
@@ -1347,6 +1565,7 @@ int shuffle_multi(mrhbm_ctx* c) {
   st.groups = c->groups;
   st.ms_exchange = ev_ms(c, EV_SCATTER, EV_EXCH);
   finish_stats(c, st);
+  c->stats.ms_exchange = st.ms_exchange;
   return MRHBM_OK;
 }
 
@@ -1361,20 +1580,40 @@ extern "C" {
 
 int mrhbm_shuffle(mrhbm_ctx* c) {
   if (!c || !c->stream) return MRHBM_E_INVAL;
+  Entry g(c);
   for (const Range& r : c->ranges)
     if (r.state == R_OPEN) return fail(c, MRHBM_E_INVAL, "map job '%s' is still open", r.job.c_str());
   invalidate(c);
-  return c->world > 1 ? shuffle_multi(c) : shuffle_single(c);
+  uint64_t N_in = 0, N = 0;
+  for (auto& r : live_ranges(c)) N_in += r.second;
+  if (N_in >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "more than 2^32 pairs on one GPU (%llu)", (unsigned long long)N_in);
+  mrhbm_stats st{};
+  st.pairs = N_in;
+  std::vector<Src> live;
+  CU(c, cudaEventRecord(c->ev[EV_START], c->stream));
+  double distinct = -1;
+  int rc = collect_sources(c, live, &N, st, &distinct);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[EV_CSTART], c->stream));
+  if (!c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && !(c->tune & 1u)) {
+    bool done = false;
+    rc = shuffle_fast(c, live, N, N_in, distinct, st, &done);
+    if (rc) return rc;
+    if (done) return MRHBM_OK;
+  }
+  return c->world > 1 ? shuffle_multi_exact(c, live, N, N_in, distinct, st) : shuffle_single_exact(c, live, N, N_in, distinct, st);
 }
 
 int mrhbm_stats_get(mrhbm_ctx* c, mrhbm_stats* out) {
   if (!c || !out) return MRHBM_E_INVAL;
+  Entry g(c);
   *out = c->stats;
   return MRHBM_OK;
 }
 
 int mrhbm_partitions(mrhbm_ctx* c, uint32_t* ids, size_t cap, size_t* n) {
   if (!c || !n) return MRHBM_E_INVAL;
+  Entry g(c);
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   size_t k = 0;
   for (uint32_t i = 0; i < c->Pl; i++) {
@@ -1389,6 +1628,7 @@ int mrhbm_partitions(mrhbm_ctx* c, uint32_t* ids, size_t cap, size_t* n) {
 
 int mrhbm_result_info_get(mrhbm_ctx* c, mrhbm_result_info* info) {
   if (!c || !info) return MRHBM_E_INVAL;
+  Entry g(c);
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   size_t np = 0;
   mrhbm_partitions(c, nullptr, 0, &np);
@@ -1404,6 +1644,7 @@ int mrhbm_result_info_get(mrhbm_ctx* c, mrhbm_result_info* info) {
 
 int mrhbm_result_copy(mrhbm_ctx* c, void* keys, uint64_t* sums, uint64_t* part_off) {
   if (!c) return MRHBM_E_INVAL;
+  Entry g(c);
   int rc = ensure_compact(c);
   if (rc) return rc;
   if (keys && c->groups) CU(c, cudaMemcpyAsync(keys, c->ckeys, c->groups * c->kb, cudaMemcpyDeviceToHost, c->stream));
@@ -1420,6 +1661,7 @@ int mrhbm_result_copy(mrhbm_ctx* c, void* keys, uint64_t* sums, uint64_t* part_o
 
 int mrhbm_checksum_input(mrhbm_ctx* c, uint64_t in[4]) {
   if (!c || !in) return MRHBM_E_INVAL;
+  Entry g(c);
   CU(c, cudaMemsetAsync(c->d_acc, 0, 8 * sizeof(uint64_t), c->stream));
   for (auto& r : live_ranges(c)) launch_checksum_in(c->rb, (char*)c->pool + r.first * c->rb, r.second, c->d_acc, c->stream);
   CU(c, cudaGetLastError());
@@ -1431,6 +1673,7 @@ int mrhbm_checksum_input(mrhbm_ctx* c, uint64_t in[4]) {
 
 int mrhbm_checksum_result(mrhbm_ctx* c, uint64_t out[6]) {
   if (!c || !out) return MRHBM_E_INVAL;
+  Entry g(c);
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   CU(c, cudaMemsetAsync(c->d_acc, 0, 8 * sizeof(uint64_t), c->stream));
   launch_checksum_out(c->rb, c->rv, c->B, make_bp(c, c->S, c->ordered), c->bin_base, c->d_acc, c->stream);
@@ -1456,6 +1699,7 @@ static inline int slot_cmp(const mrhbm_ctx* c, const unsigned char* a, const uns
 
 int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
   if (!c || !out) return MRHBM_E_INVAL;
+  Entry g(c);
   if (part >= c->cfg.num_partitions) return fail(c, MRHBM_E_INVAL, "partition %u out of range", part);
   int rc = ensure_compact(c);
   if (rc) return rc;
@@ -1547,6 +1791,7 @@ int mrhbm_comm_unique_id(mrhbm_ctx* c, void* id) {
 }
 int mrhbm_comm_init(mrhbm_ctx* c, const void* id, int rank, int world) {
   if (!c || !id || world < 1 || rank < 0 || rank >= world) return MRHBM_E_INVAL;
+  Entry g(c);
   if (world > 8) return fail(c, MRHBM_E_INVAL, "at most 8 ranks (one NVSwitch box)");
   if (c->world != 1) return fail(c, MRHBM_E_INVAL, "communicator already initialised");
   if (world == 1) return MRHBM_OK;
@@ -1561,13 +1806,8 @@ int mrhbm_comm_init(mrhbm_ctx* c, const void* id, int rank, int world) {
     c->pbase[r + 1] = c->pbase[r] + owned;
   }
   c->Pl = c->pbase[rank + 1] - c->pbase[rank];
-  if (getenv("MRHBM_P2P") && atoi(getenv("MRHBM_P2P")) && c->rb == 16) {  // EXPERIMENTAL, see mrhbm_ctx::p2p
-    CU(c, cudaMalloc((void**)&c->d_route, kRouteWords * sizeof(unsigned long long)));
-    CU(c, cudaHostAlloc((void**)&c->h_route, kRouteWords * sizeof(unsigned long long), cudaHostAllocDefault));
-    CU(c, cudaMalloc((void**)&c->d_ipc, 16 * 9 * sizeof(uint32_t)));
-    CU(c, cudaHostAlloc((void**)&c->h_ipc, 16 * 9 * sizeof(uint32_t), cudaHostAllocDefault));
-    c->p2p = true;
-  }
+  CU(c, cudaMalloc((void**)&c->d_ipc, 16 * 9 * sizeof(uint32_t)));
+  CU(c, cudaHostAlloc((void**)&c->h_ipc, 16 * 9 * sizeof(uint32_t), cudaHostAllocDefault));
   invalidate(c);
   return MRHBM_OK;
 }

@@ -164,21 +164,28 @@ __device__ __forceinline__ uint64_t word_hash(const uint32_t* r) {
   return h;
 }
 
-// partition id and bin (= pid*S + sub) of a record held in registers / smem words
+// floor(x * m / 2^64) for a 32-bit m: two 32x32 multiplies instead of the four of __umul64hi
+__host__ __device__ __forceinline__ uint32_t mulhi_u64_u32(uint64_t x, uint32_t m) {
+  const uint64_t lo = (uint64_t)(uint32_t)x * m, hi = (uint64_t)(uint32_t)(x >> 32) * m;
+  return (uint32_t)((hi + (lo >> 32)) >> 32);
+}
+
+// partition id, owning rank and bin (= slot(pid)*S + sub) of a record held in registers / smem words
 template <int RB>
-__device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& bp, uint32_t* pid_out) {
+__device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& bp, uint32_t* pid_out,
+                                           uint32_t* dest_out = nullptr) {
   uint32_t pid;
   uint64_t h = 0;  // uniform 64-bit hash; feeds the hash sub-bin (only computed further when needed)
   const bool mul = bp.partitioner == 1u && Rec<RB>::kU64;
   if (mul) {  // MULHASH
     uint64_t key = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
     h = key * 0x9E3779B97F4A7C15ull;
-    pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
+    pid = mulhi_u64_u32(h, bp.P);
   } else if (bp.partitioner == 0u) {  // FNV_LUA
     pid = fnv_lua_hash<RB>(r) % bp.P;
   } else {  // WORDHASH
     h = word_hash<RB>(r);
-    pid = (uint32_t)__umul64hi(h, (uint64_t)bp.P);
+    pid = mulhi_u64_u32(h, bp.P);
   }
   uint32_t sub = 0;
   if (bp.S > 1) {
@@ -190,10 +197,24 @@ __device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& b
     } else {
       src = mix64(h * (uint64_t)bp.P + 0x632BE59BD9B4E019ull);  // independent of pid
     }
-    sub = (uint32_t)__umul64hi(src, (uint64_t)bp.S);
+    sub = mulhi_u64_u32(src, bp.S);
   }
   if (pid_out) *pid_out = pid;
-  return partition_slot(bp, pid) * bp.S + sub;
+  // partition p is owned by rank p % world and sits in slot pbase[rank] + p / world
+  uint32_t slot = pid, dest = 0;
+  if (bp.world > 1) {
+    uint32_t q;
+    if (bp.wshift != 0xffffffffu) {  // power-of-two world: no integer division
+      dest = pid & (bp.world - 1u);
+      q = pid >> bp.wshift;
+    } else {
+      dest = pid % bp.world;
+      q = pid / bp.world;
+    }
+    slot = bp.pbase[dest] + q;
+  }
+  if (dest_out) *dest_out = dest;
+  return slot * bp.S + sub;
 }
 
 // checksum mixers over the whole key slot (input and result share the slot format)

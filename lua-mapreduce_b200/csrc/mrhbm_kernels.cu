@@ -11,7 +11,6 @@
 #include "mrhbm_kernels.h"
 
 #include <algorithm>
-#include <cstdlib>
 
 #include "mrhbm_dev.cuh"
 #include "mrhbm_sort.cuh"
@@ -205,17 +204,9 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
     for (int k = 0; k < U; k++) {
       if (base + k * stride < n) {
         uint32_t bin = bin_of<RB>(w[k], bp, nullptr);
-        if (bp.debug == 0) {
-          pos[k] = atomicAdd(cursor + (((((size_t)bin) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);
-        } else if (bp.debug == 1) {  // profiling only: stores without the claim (results invalid)
-          pos[k] = cursor[(size_t)bin << bp.ctr_shift] + (uint32_t)((base + k * stride) & 1023);
-          if (pos[k] >= n) pos[k] = (uint32_t)(n - 1);
-        } else {  // profiling only: claim without the scattered store
-          pos[k] = atomicAdd(cursor + ((size_t)bin << bp.ctr_shift), 1u);
-        }
+        pos[k] = atomicAdd(cursor + (((((size_t)bin) << bp.rep_shift) | (blockIdx.x & ((1u << bp.rep_shift) - 1u))) << bp.ctr_shift), 1u);
       }
     }
-    if (bp.debug == 2) continue;
 #pragma unroll
     for (int k = 0; k < U; k++) {
       if (base + k * stride < n) {
@@ -228,65 +219,57 @@ __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs,
   }
 }
 
-// Optimistic single pass: no histogram.  Every bin owns `stride` slots; the claim on the bin
-// cursor is both the slot and, afterwards, the bin's count.
-template <int RB>
-__global__ void __launch_bounds__(256) k_scatter_fixed(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
-                                                       uint32_t* __restrict__ cursor, uint4* __restrict__ mid,
-                                                       uint32_t slots, uint32_t* __restrict__ err_flags) {
-  constexpr int U = Unroll<RB>::U;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
-    uint32_t w[U][Rec<RB>::kWords];
-    uint32_t pos[U], bin[U];
-#pragma unroll
-    for (int k = 0; k < U; k++)
-      if (base + k * stride < n) load_rec<RB>(recs + (base + k * stride) * Rec<RB>::kVec, w[k]);
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      if (base + k * stride < n) {
-        bin[k] = bin_of<RB>(w[k], bp, nullptr);
-        pos[k] = atomicAdd(cursor + ((size_t)bin[k] << bp.ctr_shift), 1u);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      if (base + k * stride < n) {
-        if (pos[k] >= slots) {
-          atomicOr(err_flags, (uint32_t)ERRF_CAPACITY);
-          continue;
-        }
-        uint4* d = mid + ((uint64_t)bin[k] * slots + pos[k]) * Rec<RB>::kVec;
-#pragma unroll
-        for (int v = 0; v < Rec<RB>::kVec; v++)
-          stg_stream(d + v, make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]));
-      }
-    }
+// Strided sample of the u64 keys, histogram of their top 8 bits: decides BEFORE any record moves whether
+// key-ordered sub-bins (sub = mulhi(key, S)) would be balanced.  Sequential or clustered keys show up as
+// overfull buckets and the shuffle uses hash sub-bins from the start instead of paying a discarded attempt.
+__global__ void __launch_bounds__(256) k_sample_u64(const uint4* __restrict__ recs, uint64_t n, uint32_t nsample,
+                                                    uint32_t* __restrict__ hist256) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nsample; i += gridDim.x * 256) {
+    const uint64_t idx = (uint64_t)(((unsigned __int128)i * n) / nsample);
+    const uint4 r = __ldg(recs + idx);
+    atomicAdd(&h[r.y >> 24], 1u);
   }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(hist256 + threadIdx.x, h[threadIdx.x]);
 }
 
 // ============================================================================
-// two-level coalesced split (optimistic layout, many bins)
+// two-level coalesced split (many bins)
 // ============================================================================
-// k_scatter_fixed pays one L2 round trip (cursor claim) and one 16-byte scattered store per pair.
-// k_split instead partitions a TILE of records inside shared memory (one shared-memory atomic per
-// pair), claims global space once per (tile, bin) and copies the tile out bin by bin, so stores
-// are contiguous runs.  With F fine bins per coarse bin it runs twice:
-//   level 1: source -> coarse regions (coarse = fine / F), level 2: coarse region c -> fine bins.
-constexpr int kSplitThreads = 512;
-constexpr int kSplitTileBytes = 64 * 1024;
+// A per-pair scatter pays one L2 round trip (cursor claim) and one scattered store per pair.
+// k_split_tma instead partitions a TILE of records inside shared memory (one shared-memory atomic
+// per pair -- measured 4.9 cycles per warp on B200, profiles/microbench/smem_rank.cu), claims global
+// space once per (tile, bin) and copies the tile out bin by bin, so stores are contiguous runs.
+// With F fine bins per coarse region it runs twice:
+//   level 1: source -> coarse regions (local memory), level 2: coarse region -> its F fine bins.
+// On several GPUs level 2 IS the exchange: a coarse region belongs to the rank that owns its
+// partitions; every rank's level 1 fills its own copy of ALL regions, and level 2 of the owner pulls
+// region y from every rank's buffer (peer-mapped memory over NVLink) with the same 40 KB bulk copies
+// that feed it on one GPU, tile by tile, while it splits the previous tile -- transfer and split
+// overlap inside one kernel, and the sort then runs on local data only.  Replaces
+// mapreduce/job.lua:203-221 (partitionfn + spill) and the GridFS / scp transport (job.lua:255-260,
+// fs.lua:143-160).
 constexpr int kSplitMaxBins = 1024;
 
 struct SplitArgs {
-  const uint4* src;       // level 1: records; level 2: the coarse regions (segment y = coarse bin)
+  const uint4* src;       // level 1: records
   uint64_t n;             // level 1: number of records
-  const uint32_t* seg_counts;  // level 2: fill level of coarse region y at seg_counts[y << ctr_shift]
-  uint64_t seg_stride;    // level 2: records per coarse region
-  uint4* dst;
-  uint64_t dst_stride;    // records per destination bin region
-  uint32_t* cursor;       // destination bin fill levels (index << ctr_shift)
-  uint32_t capacity;      // records a destination bin can take
-  uint32_t F;             // fine bins per coarse bin (a power of two)
+  // level 2 source: region y = blockIdx.y of this rank as filled by source rank z = blockIdx.z:
+  // seg_stride records at peer[z] + (region_first + y) * seg_stride, holding
+  // seg_counts[z * seg_zstride + ((region_first + y) << ctr_shift)] records
+  unsigned long long peer[8];  // every rank's region buffer as mapped into this process (one GPU: peer[0] = l1)
+  const uint32_t* seg_counts;
+  uint64_t seg_zstride;
+  uint64_t seg_stride;
+  uint32_t region_first;
+  uint4* dst;             // destination regions
+  uint64_t dst_stride;    // records per destination region (optimistic layout)
+  uint32_t* cursor;       // destination fill levels (index << ctr_shift)
+  uint32_t capacity;      // records a destination region can take
+  uint32_t F;             // fine bins per coarse region (a power of two)
   uint32_t logF;
   uint32_t nbins;         // bins this level distinguishes inside one tile (<= kSplitMaxBins)
   uint32_t level;         // 1 or 2
@@ -297,156 +280,12 @@ struct SplitArgs {
   const uint32_t* base_off;
   uint32_t rep_shift;
   uint32_t B;
-  // Fused split -> peer-memory exchange (multi-GPU, exact level 2, P2P instantiation only; EXPERIMENTAL,
-  // opt-in with MRHBM_P2P=1): a device table of kRouteWords u64 --
-  //   route[d]       byte address of rank d's receive buffer (own rank: the local bin buffer),
-  //   route[8 + d]   record offset to add to the local exact slot for bins owned by rank d (two's complement),
-  //   route[16 + d]  first fine bin owned by rank d (d = 0..ndest), so bins [route[16+d], route[16+d+1]) go to d
-  //   route[32 + d]  records rank d receives in total (all sources; written by k_p2p_route)
-  const unsigned long long* route;
-  uint32_t ndest;
+  // optimistic layout: rank d owns the coarse regions [rbase[d], rbase[d+1]) = its fine bins
+  // [fbase[d], fbase[d+1]) in blocks of F (one GPU: rbase = {0, C1}, fbase = {0, B})
+  uint32_t rbase[9], fbase[9];
+  uint32_t ndest, me;
 };
 
-template <int RB, int THREADS, int TILE_BYTES>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_split(SplitArgs a, BinParams bp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using R = Rec<RB>;
-  constexpr int T = TILE_BYTES / RB;            // records per tile
-  constexpr int U = T / THREADS;               // records per thread
-  static_assert(T % THREADS == 0, "tile");
-  uint4* stage = (uint4*)smem_raw;                   // T records in bin order
-  uint16_t* pos_sub = (uint16_t*)(smem_raw + TILE_BYTES);  // bin of staged position
-  __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins + 1], sgb[kSplitMaxBins];
-  const uint32_t tid = threadIdx.x;
-  const uint4* src = a.src;
-  uint64_t n = a.n;
-  uint32_t coarse = 0;
-  if (a.level == 1 && bp.seg_counts) {  // segmented source (the combiner's per-CTA regions)
-    src += (size_t)blockIdx.y * bp.seg_stride * R::kVec;
-    n = bp.seg_counts[blockIdx.y];
-  }
-  if (a.level == 2) {
-    coarse = blockIdx.y;
-    if (a.base_off) {  // exact: the coarse region is the union of its fine bins
-      uint32_t f0 = coarse * a.F, f1 = f0 + a.F < a.B ? f0 + a.F : a.B;
-      uint32_t o0 = a.base_off[(size_t)f0 << a.rep_shift], o1 = a.base_off[(size_t)f1 << a.rep_shift];
-      src += (size_t)o0 * R::kVec;
-      n = o1 - o0;
-    } else {
-      src += (size_t)coarse * a.seg_stride * R::kVec;
-      uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
-      n = c < a.seg_stride ? c : a.seg_stride;
-    }
-  }
-  const uint64_t ntiles = (n + T - 1) / T;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint64_t t0 = tile * T;
-    const uint32_t tn = (uint32_t)((n - t0) < (uint64_t)T ? (n - t0) : (uint64_t)T);
-    for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
-    __syncthreads();
-    uint32_t w[U][R::kWords];
-    uint32_t sub[U], rk[U];
-#pragma unroll
-    for (int k = 0; k < U; k++)
-      if (tid + k * THREADS < tn) load_rec<RB>(src + (t0 + tid + k * THREADS) * R::kVec, w[k]);
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      if (tid + k * THREADS < tn) {
-        uint32_t fine = bin_of<RB>(w[k], bp, nullptr);
-        sub[k] = a.level == 1 ? fine >> a.logF : fine & (a.F - 1u);
-        rk[k] = atomicAdd(scnt + sub[k], 1u);
-      }
-    }
-    __syncthreads();
-    // exclusive scan of the per-bin counts (nbins <= 1024: two items per thread) + global claims
-    {
-      constexpr int IPT = kSplitMaxBins / THREADS;  // bins per thread in the scan
-      uint32_t v[IPT], s = 0;
-#pragma unroll
-      for (int i = 0; i < IPT; i++) {
-        v[i] = IPT * tid + i < a.nbins ? scnt[IPT * tid + i] : 0u;
-        s += v[i];
-      }
-      uint32_t incl = s;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((tid & 31) >= (uint32_t)d) incl += t;
-      }
-      __shared__ uint32_t wsum[THREADS / 32];
-      if ((tid & 31) == 31) wsum[tid >> 5] = incl;
-      __syncthreads();
-      if (tid < 32) {  // exclusive scan of the warp sums
-        uint32_t ws = tid < THREADS / 32 ? wsum[tid] : 0u, wi = ws;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-          if (tid >= (uint32_t)d) wi += t;
-        }
-        if (tid < THREADS / 32) wsum[tid] = wi - ws;
-      }
-      __syncthreads();
-      uint32_t ex = wsum[tid >> 5] + incl - s;
-#pragma unroll
-      for (int i = 0; i < IPT; i++) {
-        if (IPT * tid + i < a.nbins) soff[IPT * tid + i] = ex;
-        ex += v[i];
-      }
-      for (uint32_t b = tid; b < a.nbins; b += THREADS) {
-        uint32_t c = scnt[b];
-        uint32_t g = 0;
-        if (c) {
-          uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-          g = atomicAdd(a.cursor + ((size_t)dbin << a.ctr_shift), c);
-          if (a.base_off) {  // exact layout: absolute start of the destination region, always large enough
-            uint32_t f = a.level == 1 ? b * a.F : dbin;
-            g += a.base_off[(size_t)f << a.rep_shift];
-          } else if (g + c > a.capacity) {
-            atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
-          }
-        }
-        sgb[b] = g;
-      }
-    }
-    __syncthreads();
-    // records into bin order inside the tile
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      if (tid + k * THREADS < tn) {
-        uint32_t p = soff[sub[k]] + rk[k];
-        pos_sub[p] = (uint16_t)sub[k];
-#pragma unroll
-        for (int v = 0; v < R::kVec; v++)
-          stage[p * R::kVec + v] = make_uint4(w[k][4 * v], w[k][4 * v + 1], w[k][4 * v + 2], w[k][4 * v + 3]);
-      }
-    }
-    __syncthreads();
-    // copy out: consecutive staged positions of one bin are consecutive in global memory
-    for (uint32_t p = tid; p < tn; p += THREADS) {
-      uint32_t b = pos_sub[p];
-      uint32_t slot = sgb[b] + (p - soff[b]);
-      uint4* d;
-      if (a.base_off) {
-        d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
-      } else {
-        if (slot >= a.capacity) continue;  // flagged above
-        uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-        d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
-      }
-#pragma unroll
-      for (int v = 0; v < R::kVec; v++) stg_stream(d + v, stage[p * R::kVec + v]);
-    }
-    __syncthreads();
-  }
-}
-
-// ---- k_split_tma: the same tile split, fed by the bulk-copy engine ------------------------------
-// ncu source view of k_split: ~40 % of the stall samples wait on the tile's global loads (each
-// thread loads 8 records into registers and needs them at once) and the staging pass moves every
-// record through shared memory a second time.  Here one thread issues ONE cp.async.bulk per tile
-// (global -> shared, completion on an mbarrier), double-buffered, so tile t+1 lands while tile t
-// is split; the tile is not re-staged: a u16 permutation says which raw record goes to which
-// output position, and the copy-out reads the raw tile through it.
 constexpr int kTmaSplitThreads = 512;
 constexpr int kTmaTileBytes = 40 * 1024;
 __host__ __device__ constexpr size_t tma_split_smem(int rb, int tile_bytes = kTmaTileBytes) {
@@ -480,7 +319,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
       : "memory");
 }
 
-template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads, bool P2P = false>
+// One thread issues ONE cp.async.bulk per tile (global -> shared, completion on an mbarrier),
+// double-buffered, so tile t+1 lands while tile t is split; the tile is not re-staged: a u16
+// permutation says which raw record goes to which output position, and the copy-out reads the raw
+// tile through it.
+template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads>
 __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using R = Rec<RB>;
@@ -493,9 +336,17 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   uint16_t* perm = (uint16_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index
   uint16_t* pos_sub = perm + T;                                 // output position -> bin
   __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins], sgb[kSplitMaxBins];
+  __shared__ unsigned long long sdst[kSplitMaxBins];  // byte address of slot 0 of the bin's destination region
   __shared__ uint32_t wsum[THREADS / 32];
+  __shared__ uint32_t s_rbase[9], s_fbase[9];  // (kernel-parameter arrays indexed by a register would be copied to local memory)
   __shared__ __align__(8) uint64_t mbar[2];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < 9; i++)
+    if (tid == (uint32_t)i) {
+      s_rbase[i] = a.rbase[i];
+      s_fbase[i] = a.fbase[i];
+    }
   const uint4* src = a.src;
   uint64_t n = a.n;
   uint32_t coarse = 0;
@@ -511,11 +362,19 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       src += (size_t)o0 * R::kVec;
       n = o1 - o0;
     } else {
-      src += (size_t)coarse * a.seg_stride * R::kVec;
-      uint32_t c = a.seg_counts[(size_t)coarse << a.ctr_shift];
+      unsigned long long base = a.peer[0];
+#pragma unroll
+      for (int z = 1; z < 8; z++)
+        if (blockIdx.z == (uint32_t)z) base = a.peer[z];
+      src = (const uint4*)(uintptr_t)base + (size_t)(a.region_first + coarse) * a.seg_stride * R::kVec;
+      uint32_t c = a.seg_counts[(size_t)blockIdx.z * a.seg_zstride + ((size_t)(a.region_first + coarse) << a.ctr_shift)];
       n = c < a.seg_stride ? c : a.seg_stride;
     }
   }
+  uint32_t fine_base = a.fbase[0];  // first fine bin of this rank
+#pragma unroll
+  for (int z = 1; z < 8; z++)
+    if (a.me == (uint32_t)z) fine_base = a.fbase[z];
   const uint64_t ntiles = (n + T - 1) / T;
   auto tile_len = [&](uint64_t tile) -> uint32_t {
     uint64_t t0 = tile * T;
@@ -527,6 +386,15 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (uint32_t b = tid; b < kSplitMaxBins; b += THREADS) scnt[b] = 0;
+  // destination region of every bin of this level (constant over the tiles)
+  for (uint32_t b = tid; b < a.nbins; b += THREADS) {
+    unsigned long long p = (unsigned long long)(uintptr_t)a.dst;
+    if (!a.base_off) {  // (exact layout: slots are absolute)
+      const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+      p += (unsigned long long)dbin * a.dst_stride * RB;
+    }
+    sdst[b] = p;
+  }
   __syncthreads();
   if (tid == 0 && blockIdx.x < ntiles)
     bulk_load(raw0, src + (uint64_t)blockIdx.x * T * R::kVec, tile_len(blockIdx.x) * RB, &mbar[0]);
@@ -544,8 +412,14 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     for (int k = 0; k < U; k++) {
       const uint32_t i = tid + k * THREADS;
       if (i < tn) {
-        uint32_t fine = bin_of<RB>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr);
-        sub[k] = a.level == 1 ? fine >> a.logF : fine & (a.F - 1u);
+        uint32_t dest;
+        const uint32_t fine = bin_of<RB>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr, &dest);
+        if (a.level == 1) {
+          const uint32_t d = a.ndest > 1 ? dest : 0u;
+          sub[k] = s_rbase[d] + ((fine - s_fbase[d]) >> a.logF);
+        } else {
+          sub[k] = (fine - fine_base) & (a.F - 1u);
+        }
         rk[k] = atomicAdd(scnt + sub[k], 1u);
       }
     }
@@ -618,73 +492,18 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       }
     }
     __syncthreads();
-    // copy out: consecutive output positions of one bin are consecutive in global memory
+    // copy out: consecutive output positions of one bin are consecutive in global (or peer) memory
     for (uint32_t p = tid; p < tn; p += THREADS) {
       const uint32_t b = pos_sub[p];
       const uint32_t slot = sgb[b] + p;
       const uint4* r = raw + (size_t)perm[p] * R::kVec;
-      uint4* d;
-      if (a.base_off) {
-        if (P2P && a.level == 2) {  // the bin's owner gets the record straight into its receive buffer (NVLink store)
-          const uint32_t f = coarse * a.F + b;
-          uint32_t dd = 0;
-          while (dd + 1 < a.ndest && f >= (uint32_t)a.route[16 + dd + 1]) dd++;
-          d = (uint4*)a.route[dd] + (uint64_t)((long long)slot + (long long)a.route[8 + dd]) * R::kVec;
-        } else {
-          d = a.dst + (uint64_t)slot * R::kVec;  // slot is absolute
-        }
-      } else {
-        if (slot >= a.capacity) continue;  // flagged above
-        const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-        d = a.dst + ((uint64_t)dbin * a.dst_stride + slot) * R::kVec;
-      }
+      if (!a.base_off && slot >= a.capacity) continue;  // flagged above
+      uint4* d = (uint4*)(uintptr_t)(sdst[b] + (unsigned long long)slot * RB);
 #pragma unroll
       for (int vv = 0; vv < R::kVec; vv++) stg_stream(d + vv, r[vv]);
     }
     for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
     __syncthreads();
-  }
-}
-
-// P2P routing table of one rank (EXPERIMENTAL, see SplitArgs::route): block d sums, over the all-gathered
-// counts all[s*B + bin], what every source s sends to rank d.  Records of lower-numbered sources come first
-// in d's receive buffer, so this rank's share starts at sum_{s<me}; its local exact layout starts the bins
-// of d at bin_off[first[d]].
-struct RouteFirst {
-  uint32_t v[9];
-};
-__global__ void __launch_bounds__(256) k_p2p_route(const uint32_t* __restrict__ all, uint32_t G, uint32_t B, uint32_t me,
-                                                   RouteFirst first, const uint32_t* __restrict__ bin_off,
-                                                   unsigned long long* __restrict__ route) {
-  __shared__ unsigned long long s_lo[8], s_all[8];
-  const uint32_t d = blockIdx.x, f0 = first.v[d], f1 = first.v[d + 1];
-  unsigned long long lo = 0, tot = 0;
-  for (uint32_t s = 0; s < G; s++) {
-    unsigned long long acc = 0;
-    for (uint32_t b = f0 + threadIdx.x; b < f1; b += blockDim.x) acc += all[(size_t)s * B + b];
-    tot += acc;
-    if (s < me) lo += acc;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo += __shfl_xor_sync(0xffffffffu, lo, o);
-    tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_lo[threadIdx.x >> 5] = lo;
-    s_all[threadIdx.x >> 5] = tot;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    lo = tot = 0;
-    for (uint32_t w = 0; w < blockDim.x / 32; w++) {
-      lo += s_lo[w];
-      tot += s_all[w];
-    }
-    route[8 + d] = d == me ? 0ull : (unsigned long long)((long long)lo - (long long)bin_off[f0]);
-    route[16 + d] = f0;
-    if (d + 1 == G) route[16 + G] = f1;
-    route[32 + d] = tot;
   }
 }
 
@@ -937,6 +756,41 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
     if (hll[i]) atomicMax(g_hll + i, hll[i]);
 }
 
+// pairs a rank reduces = the fill levels (clamped to the region capacity) of its regions in every rank's
+// level-1 cursors; acc2[0] = all of them, acc2[1] = the ones that were already local (source == me)
+__global__ void __launch_bounds__(256) k_region_totals(const uint32_t* __restrict__ counts, uint64_t zstride, uint32_t G,
+                                                       uint32_t me, uint32_t first, uint32_t nreg, uint32_t shift,
+                                                       uint32_t clamp, unsigned long long* __restrict__ acc2) {
+  __shared__ unsigned long long s_tot[8], s_own[8];
+  unsigned long long tot = 0, own = 0;
+  for (uint64_t i = threadIdx.x; i < (uint64_t)nreg * G; i += blockDim.x) {
+    const uint32_t z = (uint32_t)(i / nreg), r = (uint32_t)(i % nreg);
+    uint32_t c = counts[(size_t)z * zstride + ((size_t)(first + r) << shift)];
+    c = c < clamp ? c : clamp;
+    tot += c;
+    if (z == me) own += c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    own += __shfl_xor_sync(0xffffffffu, own, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_tot[threadIdx.x >> 5] = tot;
+    s_own[threadIdx.x >> 5] = own;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tot = own = 0;
+    for (int w = 0; w < 8; w++) {
+      tot += s_tot[w];
+      own += s_own[w];
+    }
+    acc2[0] = tot;
+    acc2[1] = own;
+  }
+}
+
 // global per-bin totals from the all-gathered counts: this rank's bins go to tot[], and every
 // rank counts the bins (of ALL ranks) above cap, so that all ranks take the same decision
 __global__ void k_sum_src(const uint32_t* __restrict__ all, uint32_t world, uint32_t stride, uint32_t base,
@@ -961,7 +815,7 @@ __global__ void __launch_bounds__(256) k_compact(ShuffleBuffers b, uint32_t B, u
   const uint32_t* skeys = (const uint32_t*)b.out_keys;
   for (uint32_t bin = warp; bin < B; bin += nwarps) {
     uint32_t len = b.ucount[bin];
-    uint64_t so = bin_start(b, bin), d0 = b.uoff[bin];
+    uint64_t so = out_start(b, bin), d0 = b.uoff[bin];
     for (uint32_t i = lane; i < len * KW; i += 32) dkeys[d0 * KW + i] = skeys[so * KW + i];
     for (uint32_t i = lane; i < len; i += 32) dsums[d0 + i] = b.out_sums[so + i];
   }
@@ -1010,7 +864,7 @@ __global__ void __launch_bounds__(256) k_checksum_out(ShuffleBuffers b, uint32_t
   uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, bad_order = 0, bad_part = 0;
   for (uint32_t bin = warp; bin < B; bin += nwarps) {
     uint32_t len = b.ucount[bin];
-    uint64_t so = bin_start(b, bin);
+    uint64_t so = out_start(b, bin);
     for (uint32_t i = lane; i < len; i += 32) {
       uint32_t w[Rec<RB>::kWords], p[Rec<RB>::kWords];
 #pragma unroll
@@ -1086,20 +940,11 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
 #undef CFGC
-#define CFGS(RB)                                                                                         \
-  e = cudaFuncSetAttribute(k_split<RB, 512, kSplitTileBytes>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                           kSplitTileBytes + (kSplitTileBytes / RB) * (int)sizeof(uint16_t));              \
-  if (e != cudaSuccess) return e;
-  CFGS(16) CFGS(32) CFGS(64) CFGS(128)
-#undef CFGS
 #define CFGT(RB)                                                                                         \
   e = cudaFuncSetAttribute(k_split_tma<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(RB)); \
   if (e != cudaSuccess) return e;
   CFGT(16) CFGT(32) CFGT(64) CFGT(128)
 #undef CFGT
-  e = cudaFuncSetAttribute(k_split_tma<16, kTmaTileBytes, 2, kTmaSplitThreads, true>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(16));
-  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1184,16 +1029,19 @@ int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_
                                                                                       cap, nover);
   return 1;
 }
-int launch_p2p_route(const uint32_t* all, uint32_t G, uint32_t B, uint32_t me, const uint32_t* first9,
-                     const uint32_t* bin_off, unsigned long long* route, cudaStream_t s) {
-  RouteFirst f;
-  for (int i = 0; i < 9; i++) f.v[i] = first9[i];
-  k_p2p_route<<<G, 256, 0, s>>>(all, G, B, me, f, bin_off, route);
+int launch_region_totals(const uint32_t* counts, uint64_t zstride, uint32_t G, uint32_t me, uint32_t first, uint32_t nreg,
+                         uint32_t shift, uint32_t clamp, uint64_t* acc2, cudaStream_t s) {
+  k_region_totals<<<1, 256, 0, s>>>(counts, zstride, G, me, first, nreg, shift, clamp, (unsigned long long*)acc2);
   return 1;
 }
 int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n, uint32_t* out,
                        uint32_t* totals, cudaStream_t s) {
   k_exscan_rows<<<world, 1024, 0, s>>>(all, stride, base, n, out, totals);
+  return 1;
+}
+int launch_sample_u64(const void* recs, uint64_t n, uint32_t nsample, uint32_t* hist256, cudaStream_t s) {
+  if (!n || !nsample) return 0;
+  k_sample_u64<<<(nsample + 255) / 256 < 256 ? (nsample + 255) / 256 : 256, 256, 0, s>>>((const uint4*)recs, n, nsample, hist256);
   return 1;
 }
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
@@ -1202,83 +1050,75 @@ int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, ui
   DISPATCH_RB(rb, (k_scatter<RB><<<source_grid(n, bp), 256, 0, s>>>((const uint4*)recs, n, bp, cursor, (uint4*)mid)));
   return 1;
 }
-int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
-                         uint32_t stride, uint32_t* err_flags, cudaStream_t s) {
+// level 1 (source -> coarse regions, possibly on peers) and level 2 (coarse regions -> fine bins) of the split
+static SplitArgs split_args(const BinParams& bp, const SplitPlan& pl) {
+  SplitArgs a{};
+  a.base_off = pl.base_off;
+  a.rep_shift = bp.rep_shift;
+  a.B = pl.B;
+  a.F = pl.F;
+  a.logF = 0;
+  while ((1u << a.logF) < pl.F) a.logF++;
+  a.ctr_shift = bp.ctr_shift;
+  a.err_flags = pl.err_flags;
+  a.ndest = pl.base_off ? 1u : pl.ndest;
+  a.me = pl.base_off ? 0u : pl.me;
+  for (int d = 0; d < 8; d++) a.peer[d] = pl.base_off ? 0ull : pl.peer[d];
+  for (int d = 0; d <= 8; d++) {
+    a.rbase[d] = pl.base_off ? (d ? pl.C1 : 0u) : pl.rbase[d];
+    a.fbase[d] = pl.base_off ? (d ? pl.B : 0u) : pl.fbase[d];
+  }
+  return a;
+}
+int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, const SplitPlan& pl, cudaStream_t s) {
   if (!n) return 0;
-  DISPATCH_RB(rb, (k_scatter_fixed<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor,
-                                                                             (uint4*)mid, stride, err_flags)));
+  SplitArgs a = split_args(bp, pl);
+  const int ctas = 2 * g_sm_count;
+  a.src = (const uint4*)recs;
+  a.n = n;
+  a.dst = (uint4*)pl.l1;
+  a.dst_stride = pl.sub_stride;
+  a.cursor = pl.cursor1;
+  a.capacity = (uint32_t)std::min<uint64_t>(pl.sub_stride, 0xffffffffull);
+  a.nbins = pl.C1;
+  a.level = 1;
+  dim3 grid(ctas);
+  if (bp.seg_counts) grid = dim3((ctas + bp.nseg - 1) / bp.nseg, bp.nseg);
+  DISPATCH_RB(rb, (k_split_tma<RB><<<grid, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
   return 1;
 }
-// both levels of the coalesced split; cursor1 / l1 are the coarse fill levels and regions
-int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
-                  uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, const uint32_t* base_off, cudaStream_t s, const unsigned long long* route) {
-  SplitArgs a{};
-  a.base_off = base_off;
-  a.rep_shift = bp.rep_shift;
-  a.B = B;
-  a.F = F;
-  a.logF = 0;
-  while ((1u << a.logF) < F) a.logF++;
-  a.ctr_shift = bp.ctr_shift;
-  a.err_flags = err_flags;
+int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s) {
+  SplitArgs a = split_args(bp, pl);
   const int ctas = 2 * g_sm_count;
-  size_t smem = kSplitTileBytes + (kSplitTileBytes / rb) * sizeof(uint16_t);
-  static const bool use_tma = !getenv("MRHBM_NO_TMA_SPLIT");
-  // (measured alternatives, same box: 16/24 KB tiles at 4/3 CTAs per SM and 80/88 KB tiles with one
-  // 1024-thread CTA per SM are all slower than 40 KB tiles at 2 CTAs per SM)
-  const int tile_bytes = use_tma ? kTmaTileBytes : kSplitTileBytes;
-#define SPLIT_LAUNCH(GRID)                                                                              \
-  if (use_tma) {                                                                                 \
-    DISPATCH_RB(rb, (k_split_tma<RB><<<GRID, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));       \
-  } else {                                                                                              \
-    DISPATCH_RB(rb, (k_split<RB, 512, kSplitTileBytes><<<GRID, 512, smem, s>>>(a, bp)));                \
-  }
-  a.route = route;
-  a.ndest = route ? bp.world : 0;
-  if (!level2) {
-    if (!n) return 0;
-    a.src = (const uint4*)recs;
-    a.n = n;
-    a.dst = (uint4*)l1;
-    a.dst_stride = (uint64_t)F * cap;
-    a.cursor = cursor1;
-    a.capacity = (uint32_t)std::min<uint64_t>((uint64_t)F * cap, 0xffffffffull);
-    a.nbins = C1;
-    a.level = 1;
-    dim3 grid(ctas);
-    if (bp.seg_counts) grid = dim3((ctas + bp.nseg - 1) / bp.nseg, bp.nseg);
-    SPLIT_LAUNCH(grid)
-  } else {
-    a.src = (const uint4*)l1;
-    a.seg_counts = cursor1;
-    a.seg_stride = (uint64_t)F * cap;
-    a.dst = (uint4*)mid;
-    a.dst_stride = cap;
-    a.cursor = cursor;
-    a.capacity = cap;
-    a.nbins = F;
-    a.level = 2;
-    // x CTAs per coarse region, chosen so that x*C1 CTAs fill whole waves of `ctas` resident CTAs
-    // (C1 = 220, x = 2 ran 440 CTAs = 1.49 waves on 296 slots: 26 % of the second wave idle)
-    int x = 1;
-    double best = 0;
-    const uint64_t tiles_per_region = ((uint64_t)F * cap * rb + tile_bytes - 1) / tile_bytes;
-    for (int cand = 1; cand <= 16 && (uint64_t)cand <= std::max<uint64_t>(1, tiles_per_region / 4); cand++) {
-      uint64_t total = (uint64_t)cand * C1, waves = (total + ctas - 1) / ctas;
-      double eff = (double)total / (double)(waves * ctas);
-      if (eff > best + 0.02) {
-        best = eff;
-        x = cand;
-      }
+  const uint32_t nsub = pl.base_off ? 1u : pl.ndest;
+  const uint32_t regions = pl.base_off ? pl.C1 : pl.C1_local;
+  if (!regions) return 0;
+  a.src = (const uint4*)pl.l1;
+  a.seg_counts = pl.l1_counts;
+  a.seg_zstride = pl.l1_zstride;
+  a.seg_stride = pl.sub_stride;
+  a.region_first = a.rbase[a.me];
+  a.dst = (uint4*)pl.mid;
+  a.dst_stride = pl.cap;
+  a.cursor = pl.cursor;
+  a.capacity = pl.cap;
+  a.nbins = pl.F;
+  a.level = 2;
+  // x CTAs per (region, sub-region), chosen so that all CTAs fill whole waves of `ctas` resident CTAs
+  // (C1 = 220, x = 2 ran 440 CTAs = 1.49 waves on 296 slots: 26 % of the second wave idle)
+  int x = 1;
+  double best = 0;
+  const uint64_t region_recs = pl.base_off ? (uint64_t)pl.F * pl.cap : pl.sub_stride;
+  const uint64_t tiles = (region_recs * rb + kTmaTileBytes - 1) / kTmaTileBytes;
+  for (int cand = 1; cand <= 16 && (uint64_t)cand <= std::max<uint64_t>(1, tiles / 4); cand++) {
+    uint64_t total = (uint64_t)cand * regions * nsub, waves = (total + ctas - 1) / ctas;
+    double eff = (double)total / (double)(waves * ctas);
+    if (eff > best + 0.02) {
+      best = eff;
+      x = cand;
     }
-    if (route) {  // EXPERIMENTAL fused exchange: u64 records only (the caller checks)
-      k_split_tma<16, kTmaTileBytes, 2, kTmaSplitThreads, true><<<dim3(x, C1), kTmaSplitThreads, tma_split_smem(16), s>>>(a, bp);
-      return 1;
-    }
-    SPLIT_LAUNCH(dim3(x, C1))
   }
-#undef SPLIT_LAUNCH
+  DISPATCH_RB(rb, (k_split_tma<RB><<<dim3(x, regions, nsub), kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
@@ -1286,7 +1126,7 @@ int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap
   int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
   if (grid < 1) grid = 1;
   // u64 keys in key-ordered sub-bins read from one segment: the register-pipelined variant
-  if (rb == 16 && b.hint_S > 1 && !getenv("MRHBM_NO_PIPELINED_SORT")) {
+  if (rb == 16 && b.hint_S > 1) {
     if (b.stride || b.nseg == 1)
       k_sort_reduce_u64<false><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
     else

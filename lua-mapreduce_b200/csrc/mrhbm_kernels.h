@@ -22,8 +22,8 @@ struct BinParams {
   // multi-GPU: partition p is owned by rank p % world and sits in slot pbase[p % world] + p / world,
   // so that the bins of one destination rank are contiguous (its all-to-all send region)
   uint32_t world;        // 1 = single GPU (slot == p)
+  uint32_t wshift;       // log2(world) when world is a power of two, else 0xffffffff
   uint32_t pbase[9];
-  uint32_t debug;        // MRHBM_DEBUG_SCATTER profiling variants (0 = product path)
   // segmented source (the combiner's per-CTA output regions): blockIdx.y selects segment y =
   // seg_counts[y] records at recs + y * seg_stride records.  seg_counts == nullptr: one range.
   const uint32_t* seg_counts;
@@ -64,6 +64,8 @@ struct ShuffleBuffers {
   // Optimistic single-pass layout (no histogram pass): bin b owns the fixed slots
   // [b*stride, (b+1)*stride) of mid / out and its fill level is its scatter cursor.
   uint32_t stride;     // 0 = exact layout through bin_off
+  uint32_t out_stride; // optimistic layout: the groups of bin b start at out slot b * out_stride (<= stride: a
+                       // duplicate-heavy bin holds many records but at most one CTA's worth of distinct keys)
   uint32_t ctr_shift;  // cursor[b << ctr_shift]
   // key-ordered sub-bins of u64 keys (sub = mulhi(key, S)): lets the sort kernel skip the
   // min/max pass.  hint_S = 0: unknown.
@@ -74,6 +76,9 @@ struct ShuffleBuffers {
 };
 MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
   return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[(size_t)bin << b.rep_shift];
+}
+MRHBM_HD inline uint64_t out_start(const ShuffleBuffers& b, uint32_t bin) {
+  return b.stride ? (uint64_t)bin * b.out_stride : (uint64_t)b.bin_off[(size_t)bin << b.rep_shift];
 }
 MRHBM_HD inline uint32_t bin_count(const ShuffleBuffers& b, uint32_t bin) {
   if (b.stride) {
@@ -97,11 +102,10 @@ constexpr uint32_t kScanScratchWords = 4096;
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy,
                   uint32_t* out_dense, uint32_t cap, uint32_t* big_list, uint32_t* nbig, uint32_t* total,
                   uint32_t shift, cudaStream_t s, uint32_t* scratch = nullptr);
+// histogram of the top 8 key bits of `nsample` evenly spaced u64 records (hist256 += counts)
+int launch_sample_u64(const void* recs, uint64_t n, uint32_t nsample, uint32_t* hist256, cudaStream_t s);
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                    cudaStream_t s);
-// optimistic variant: fixed `stride` slots per bin, cursors start at 0, a full bin sets ERRF_CAPACITY
-int launch_scatter_fixed(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
-                         uint32_t stride, uint32_t* err_flags, cudaStream_t s);
 // map-side combine of one committed range into out (appends; *out_count is the running total)
 // device-side tokeniser: word starts per 256-byte block, then (after an exclusive scan of the
 // block counts) one record per word; *flags gets ERRF_KEYLEN when a word exceeds the key slot
@@ -123,18 +127,38 @@ inline uint32_t agg_table_entries(int rb) { return (uint32_t)((kCapBytes + (kCap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                    uint32_t* tot, uint32_t cap, uint32_t* nover, cudaStream_t s);
 // row r < world: out[r*(n+1) ..] = exclusive scan of all[r*stride + base ..+n), totals[r] = its sum
-// EXPERIMENTAL (MRHBM_P2P=1): routing table of the fused split -> peer-memory exchange, see SplitArgs::route
-constexpr int kRouteWords = 48;
-int launch_p2p_route(const uint32_t* all, uint32_t G, uint32_t B, uint32_t me, const uint32_t* first9,
-                     const uint32_t* bin_off, unsigned long long* route, cudaStream_t s);
+// acc2[0] = sum over source ranks z < G and regions r in [first, first+nreg) of min(counts[z*zstride + (r << shift)], clamp),
+// acc2[1] = the z == me part of it
+int launch_region_totals(const uint32_t* counts, uint64_t zstride, uint32_t G, uint32_t me, uint32_t first, uint32_t nreg,
+                         uint32_t shift, uint32_t clamp, uint64_t* acc2, cudaStream_t s);
 int launch_exscan_rows(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
                        uint32_t* out, uint32_t* totals, cudaStream_t s);
-// two-level coalesced split into the fixed-stride layout: level 1 (level2 = false) source ->
-// C1 coarse regions of F*cap records in l1, level 2 coarse regions -> fine bins of cap records in mid
-int launch_split2(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t B, uint32_t cap, uint32_t F,
-                  uint32_t C1, uint32_t* cursor1, void* l1, uint32_t* cursor, void* mid, uint32_t* err_flags,
-                  bool level2, const uint32_t* base_off, cudaStream_t s,
-                  const unsigned long long* route = nullptr);
+// Two-level coalesced split.  Optimistic layout (base_off == nullptr): level 1 sends every record to the
+// coarse region of its bin inside this rank's region buffer l1 (all C1 regions of the job, sub_stride slots
+// each); level 2 of the rank that owns region y pulls it from every rank's buffer (peer[z], NVLink) and splits
+// it into fine bins of `cap` slots in mid.  C1 == B_local, F == 1 on one GPU = single level straight into mid.
+// Exact layout (base_off = bin offsets after k_hist + k_exscan): both levels write absolute slots, one GPU.
+struct SplitPlan {
+  uint32_t B;                 // fine bins (of the whole job)
+  uint32_t F;                 // fine bins per coarse region (power of two)
+  uint32_t C1;                // coarse regions of the whole job (bins level 1 distinguishes, <= 1024)
+  uint32_t C1_local;          // regions this rank owns (level 2 splits these)
+  uint32_t cap;               // slots per fine bin (optimistic)
+  uint64_t sub_stride;        // slots per coarse region in a rank's region buffer
+  uint32_t* cursor1;          // level-1 fill levels, [C1 << ctr_shift]
+  uint32_t* cursor;           // fine fill levels, [B_local << ctr_shift]
+  void* l1;                   // this rank's region buffer: C1 * sub_stride records
+  void* mid;                  // fine bins
+  uint32_t* err_flags;
+  const uint32_t* base_off;
+  uint32_t ndest, me;         // ranks, this rank (1, 0 on a single GPU)
+  unsigned long long peer[8]; // byte address of every rank's region buffer as mapped into this process
+  uint32_t rbase[9], fbase[9];  // first region / first fine bin of every rank
+  const uint32_t* l1_counts;  // level 2: fill of region r on rank z at l1_counts[z * l1_zstride + (r << ctr_shift)]
+  uint64_t l1_zstride;
+};
+int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);
+int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,
                        cudaStream_t s);
 int launch_big_bins(int rb, const ShuffleBuffers& b, uint32_t nbig, uint32_t cap, cudaStream_t s);

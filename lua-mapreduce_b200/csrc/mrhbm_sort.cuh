@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce(ShuffleBuffers 
       if (threadIdx.x == 0) b.ucount[bin] = 0;
       continue;
     }
-    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
+    ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
     // gather the bin's segments (one per source rank after the all-to-all; one on a single GPU)
     uint32_t filled = 0;
     if (b.stride) {
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     if (cnt == 0 || cnt > cap) {  // empty, or oversized (k_big_bins): nothing was loaded
       if (cnt == 0 && tid == 0) b.ucount[bin] = 0;
     } else {
-      ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
+      ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
       // sub = mulhi(key, S): keys of sub-bin `sub` lie in [sub*q, (sub+1)*(q+1)]
       const uint32_t sub = bin % b.hint_S;
       const uint64_t pmin = (uint64_t)sub * b.hint_q;
@@ -799,9 +799,15 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_agg_bins(ShuffleBuffers b, 
       __syncthreads();
       continue;
     }
-    for (uint32_t sgm = 0; sgm < b.nseg; sgm++) {
-      uint32_t so = b.seg_off[sgm][(size_t)bin << b.rep_shift], sc = b.seg_off[sgm][(size_t)(bin + 1) << b.rep_shift] - so;
-      const uint4* src = (const uint4*)b.src + (b.seg_base[sgm] + so) * R::kVec;
+    const uint32_t nsegs = b.stride ? 1u : b.nseg;  // optimistic layout: the bin is one contiguous run
+    for (uint32_t sgm = 0; sgm < nsegs; sgm++) {
+      uint32_t so = 0, sc = cnt;
+      const uint4* src = (const uint4*)b.src + off * R::kVec;
+      if (!b.stride) {
+        so = b.seg_off[sgm][(size_t)bin << b.rep_shift];
+        sc = b.seg_off[sgm][(size_t)(bin + 1) << b.rep_shift] - so;
+        src = (const uint4*)b.src + (b.seg_base[sgm] + so) * R::kVec;
+      }
       for (uint32_t i = tid; i < sc; i += blockDim.x) {
         uint32_t w[W];
 #pragma unroll
@@ -878,7 +884,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_agg_bins(ShuffleBuffers b, 
       }
       continue;
     }
-    ChunkOut out{b.out_keys, b.out_sums, off, b.counters + CNT_ERR, b.no_reduce};
+    ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
     uint32_t g = process_loaded<RB, MODE_FINAL>(sm, n, out);
     if (tid == 0) b.ucount[bin] = g;
   }

@@ -1079,6 +1079,244 @@ size_t mro_groupby_rec(const void *recs, size_t n, uint32_t rec_bytes, int parti
 }
 
 /* ======================================================================== */
+/* job-size flat oracles (bench.py / tests: parity at the BASELINE.json sizes) */
+/* ======================================================================== */
+/* Same result semantics as mro_groupby_u64 / mro_groupby_rec -- per partition the distinct keys in
+ * ascending bytewise order with the sum of their values -- computed for the synthetic streams of
+ * SURVEY App. B with several threads, so that 10^8..10^9 pairs are checked in seconds.  A rank of a
+ * multi-GPU job checks the partitions it owns (p % world == rank, server.lua:316-323 ids kept); the
+ * other partitions come out empty, exactly like mrhbm_result_copy's part_off. */
+typedef struct {
+  uint64_t key, val;
+} kv64_t;
+static int kv64_cmp(const void *a, const void *b) {
+  const kv64_t *x = (const kv64_t *)a, *y = (const kv64_t *)b;
+  return (x->key > y->key) - (x->key < y->key);
+}
+typedef struct {
+  int tid, nthreads, pass;
+  uint64_t seed, start;
+  size_t n;
+  int partitioner;
+  uint32_t nparts, world, rank;
+  size_t *cnt;  /* [nthreads][nparts] counts, later write cursors */
+  kv64_t *buf;
+  size_t *pstart; /* [nparts+1] */
+  size_t *groups; /* [nparts] */
+  uint32_t *next_part;
+  pthread_mutex_t *mu;
+  uint64_t *out_keys, *out_sums;
+  const size_t *gstart;
+} gb64_t;
+static uint32_t part_of_u64(int partitioner, uint64_t key, uint32_t nparts) {
+  if (partitioner == MRO_PART_MULHASH) return mro_part_mulhash(key, nparts);
+  unsigned char be[8];
+  for (int j = 0; j < 8; j++) be[j] = (unsigned char)(key >> (56 - 8 * j));
+  return partitioner == MRO_PART_FNV_LUA ? mro_part_fnv_lua(be, 8, nparts) : mro_part_fnv64(be, 8, nparts);
+}
+static void *gb64_worker(void *arg) {
+  gb64_t *g = (gb64_t *)arg;
+  size_t i0 = g->n / g->nthreads * g->tid, i1 = g->tid + 1 == g->nthreads ? g->n : g->n / g->nthreads * (g->tid + 1);
+  size_t *cnt = g->cnt + (size_t)g->tid * g->nparts;
+  if (g->pass == 0 || g->pass == 1) {
+    for (size_t i = i0; i < i1; i++) {
+      uint64_t k = mro_splitmix64(g->seed + g->start + i);
+      uint32_t p = part_of_u64(g->partitioner, k, g->nparts);
+      if (p % g->world != g->rank) continue;
+      if (g->pass == 0) {
+        cnt[p]++;
+      } else {
+        kv64_t *d = g->buf + cnt[p]++;
+        d->key = k;
+        d->val = (uint32_t)(mro_splitmix64(g->seed + (1ull << 40) + g->start + i) >> 32);
+      }
+    }
+  } else if (g->pass == 2) { /* sort + reduce each partition in place */
+    for (;;) {
+      pthread_mutex_lock(g->mu);
+      uint32_t p = (*g->next_part)++;
+      pthread_mutex_unlock(g->mu);
+      if (p >= g->nparts) break;
+      kv64_t *a = g->buf + g->pstart[p];
+      size_t m = g->pstart[p + 1] - g->pstart[p], w = 0;
+      qsort(a, m, sizeof *a, kv64_cmp);
+      for (size_t i = 0; i < m;) {
+        size_t j = i;
+        uint64_t sum = 0;
+        while (j < m && a[j].key == a[i].key) sum += a[j++].val;
+        if (sum >= (1ull << 53)) { /* Lua sums are doubles */
+          fprintf(stderr, "mr_oracle: sum exceeds 2^53\n");
+          abort();
+        }
+        a[w].key = a[i].key;
+        a[w].val = sum;
+        w++;
+        i = j;
+      }
+      g->groups[p] = w;
+    }
+  } else { /* pass 3: compact */
+    for (;;) {
+      pthread_mutex_lock(g->mu);
+      uint32_t p = (*g->next_part)++;
+      pthread_mutex_unlock(g->mu);
+      if (p >= g->nparts) break;
+      const kv64_t *a = g->buf + g->pstart[p];
+      size_t o = g->gstart[p];
+      for (size_t i = 0; i < g->groups[p]; i++) {
+        g->out_keys[o + i] = a[i].key;
+        g->out_sums[o + i] = a[i].val;
+      }
+    }
+  }
+  return NULL;
+}
+static void gb64_run(gb64_t *proto, int nthreads, int pass) {
+  pthread_t th[256];
+  gb64_t args[256];
+  for (int t = 0; t < nthreads; t++) {
+    args[t] = *proto;
+    args[t].tid = t;
+    args[t].pass = pass;
+    pthread_create(&th[t], NULL, gb64_worker, &args[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+size_t mro_groupby_u64_stream(uint64_t seed, uint64_t start, size_t n, int partitioner, uint32_t nparts,
+                              uint32_t world, uint32_t rank, int nthreads, uint64_t *out_keys,
+                              uint64_t *out_sums, size_t out_cap, uint64_t *part_off) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (world < 1) world = 1;
+  gb64_t g;
+  memset(&g, 0, sizeof g);
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  uint32_t next = 0;
+  g.nthreads = nthreads;
+  g.seed = seed;
+  g.start = start;
+  g.n = n;
+  g.partitioner = partitioner;
+  g.nparts = nparts;
+  g.world = world;
+  g.rank = rank;
+  g.mu = &mu;
+  g.next_part = &next;
+  g.cnt = (size_t *)calloc((size_t)nthreads * nparts, sizeof(size_t));
+  g.pstart = (size_t *)calloc(nparts + 1, sizeof(size_t));
+  g.groups = (size_t *)calloc(nparts, sizeof(size_t));
+  gb64_run(&g, nthreads, 0);
+  size_t run = 0; /* counts -> write cursors, partition-major then thread-major */
+  for (uint32_t p = 0; p < nparts; p++) {
+    g.pstart[p] = run;
+    for (int t = 0; t < nthreads; t++) {
+      size_t c = g.cnt[(size_t)t * nparts + p];
+      g.cnt[(size_t)t * nparts + p] = run;
+      run += c;
+    }
+  }
+  g.pstart[nparts] = run;
+  g.buf = (kv64_t *)malloc((run ? run : 1) * sizeof(kv64_t));
+  gb64_run(&g, nthreads, 1);
+  next = 0;
+  gb64_run(&g, nthreads, 2);
+  size_t *gstart = (size_t *)calloc(nparts + 1, sizeof(size_t));
+  for (uint32_t p = 0; p < nparts; p++) gstart[p + 1] = gstart[p] + g.groups[p];
+  size_t total = gstart[nparts];
+  for (uint32_t p = 0; p <= nparts; p++) part_off[p] = gstart[p];
+  if (total <= out_cap) {
+    g.gstart = gstart;
+    g.out_keys = out_keys;
+    g.out_sums = out_sums;
+    next = 0;
+    gb64_run(&g, nthreads, 3);
+  }
+  free(gstart);
+  free(g.buf);
+  free(g.cnt);
+  free(g.pstart);
+  free(g.groups);
+  return total; /* > out_cap: nothing was written */
+}
+
+/* occurrences of every Zipf rank in pairs [start, start+n) of the word stream: counts[r-1] for rank r */
+typedef struct {
+  int tid, nthreads;
+  uint64_t seed, start;
+  size_t n;
+  const uint64_t *table;
+  uint64_t V;
+  uint32_t *priv;
+} zc_t;
+static void *zc_worker(void *arg) {
+  zc_t *z = (zc_t *)arg;
+  size_t i0 = z->n / z->nthreads * z->tid, i1 = z->tid + 1 == z->nthreads ? z->n : z->n / z->nthreads * (z->tid + 1);
+  for (size_t i = i0; i < i1; i++) {
+    uint64_t u = mro_splitmix64(z->seed + (1ull << 41) + z->start + i);
+    z->priv[mro_zipf_rank(z->table, z->V, u) - 1]++;
+  }
+  return NULL;
+}
+int mro_zipf_counts(uint64_t seed, uint64_t start, size_t n, const uint64_t *table, uint64_t V, int nthreads,
+                    uint64_t *counts) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  if (n / (size_t)nthreads >= 0xffffffffull) return -1; /* private counters are 32 bit */
+  pthread_t th[256];
+  zc_t args[256];
+  for (int t = 0; t < nthreads; t++) {
+    zc_t a = {t, nthreads, seed, start, n, table, V, (uint32_t *)calloc(V, sizeof(uint32_t))};
+    args[t] = a;
+    pthread_create(&th[t], NULL, zc_worker, &args[t]);
+  }
+  memset(counts, 0, V * sizeof(uint64_t));
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    for (uint64_t r = 0; r < V; r++) counts[r] += args[t].priv[r];
+    free(args[t].priv);
+  }
+  return 0;
+}
+/* word count of a stream given its rank counts: keys = rank -> string (App. B), 28-byte zero padded slots */
+typedef struct {
+  uint32_t part;
+  unsigned char key[28];
+  uint64_t count;
+} wcr_t;
+static int wcr_cmp(const void *a, const void *b) {
+  const wcr_t *x = (const wcr_t *)a, *y = (const wcr_t *)b;
+  if (x->part != y->part) return x->part < y->part ? -1 : 1;
+  return memcmp(x->key, y->key, 28);
+}
+size_t mro_wordcount_from_counts(const uint64_t *counts, uint64_t V, int partitioner, uint32_t nparts,
+                                 uint32_t world, uint32_t rank, void *out_keys, uint64_t *out_sums,
+                                 uint64_t *part_off) {
+  if (world < 1) world = 1;
+  wcr_t *a = (wcr_t *)malloc((V ? V : 1) * sizeof *a);
+  size_t g = 0;
+  for (uint64_t r = 1; r <= V; r++) {
+    if (!counts[r - 1]) continue;
+    wcr_t *e = a + g;
+    memset(e->key, 0, 28);
+    size_t len = mro_rank_to_key(r, (char *)e->key);
+    e->part = partitioner == MRO_PART_FNV_LUA ? mro_part_fnv_lua(e->key, len, nparts) : mro_part_fnv64(e->key, len, nparts);
+    if (e->part % world != rank) continue;
+    e->count = counts[r - 1];
+    g++;
+  }
+  qsort(a, g, sizeof *a, wcr_cmp);
+  memset(part_off, 0, (nparts + 1) * sizeof(uint64_t));
+  for (size_t i = 0; i < g; i++) {
+    memcpy((unsigned char *)out_keys + 28 * i, a[i].key, 28);
+    out_sums[i] = a[i].count;
+    part_off[a[i].part + 1]++;
+  }
+  for (uint32_t p = 0; p < nparts; p++) part_off[p + 1] += part_off[p];
+  free(a);
+  return g;
+}
+
+/* ======================================================================== */
 /* reference-shaped baseline runner                                         */
 /* ======================================================================== */
 #include <time.h>

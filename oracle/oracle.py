@@ -84,6 +84,9 @@ def lib():
     sig("mro_gen_zipf_rec32", None, u64, u64, sz, vp, u64, vp)
     sig("mro_groupby_u64", sz, vp, vp, sz, i, u32, vp, vp, vp)
     sig("mro_groupby_rec", sz, vp, sz, u32, i, u32, vp, vp, vp)
+    sig("mro_groupby_u64_stream", sz, u64, u64, sz, i, u32, u32, u32, i, vp, vp, sz, vp)
+    sig("mro_zipf_counts", i, u64, u64, sz, vp, u64, i, vp)
+    sig("mro_wordcount_from_counts", sz, vp, u64, i, u32, u32, u32, vp, vp, vp)
     sig("mro_run_synthetic", i, vp, i, u64, u64, u64, u32, i, vp, u64, C.POINTER(dbl), C.POINTER(dbl))
     _lib = L
     return L
@@ -264,6 +267,42 @@ def groupby_rec(recs, partitioner, nparts):
     g = lib().mro_groupby_rec(recs.ctypes.data, n, rb, partitioner, nparts, okeys.ctypes.data,
                               os_.ctypes.data, po.ctypes.data)
     return okeys[:g].copy(), os_[:g].copy(), po
+
+
+def groupby_u64_stream(seed, start, n, partitioner, nparts, world=1, rank=0, nthreads=None, max_groups=None):
+    """job-size oracle for the uniform u64 stream: (keys, sums, part_off) of the partitions rank owns"""
+    nthreads = nthreads or min(os.cpu_count() or 1, 128)
+    cap = int(max_groups if max_groups is not None else n)
+    ok = np.empty(max(cap, 1), dtype=np.uint64)
+    os_ = np.empty(max(cap, 1), dtype=np.uint64)
+    po = np.empty(nparts + 1, dtype=np.uint64)
+    g = lib().mro_groupby_u64_stream(seed, start, n, partitioner, nparts, world, rank, nthreads,
+                                     ok.ctypes.data, os_.ctypes.data, cap, po.ctypes.data)
+    if g > cap:
+        raise RuntimeError("groupby_u64_stream: %d groups exceed the output capacity %d" % (g, cap))
+    return ok[:g], os_[:g], po
+
+
+def zipf_counts(seed, start, n, table, nthreads=None):
+    """occurrences of every Zipf rank (index r-1) in pairs [start, start+n) of the word stream"""
+    nthreads = nthreads or min(os.cpu_count() or 1, 128)
+    t = np.ascontiguousarray(table, dtype=np.uint64)
+    counts = np.zeros(t.size, dtype=np.uint64)
+    if lib().mro_zipf_counts(seed, start, n, t.ctypes.data, t.size, nthreads, counts.ctypes.data) != 0:
+        raise RuntimeError("zipf_counts: n too large")
+    return counts
+
+
+def wordcount_from_counts(counts, partitioner, nparts, world=1, rank=0):
+    """(keys[g,28] uint8, sums, part_off) of the word count the rank counts mean, for the partitions rank owns"""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    V = counts.size
+    okeys = np.empty((max(V, 1), 28), dtype=np.uint8)
+    os_ = np.empty(max(V, 1), dtype=np.uint64)
+    po = np.empty(nparts + 1, dtype=np.uint64)
+    g = lib().mro_wordcount_from_counts(counts.ctypes.data, V, partitioner, nparts, world, rank,
+                                        okeys.ctypes.data, os_.ctypes.data, po.ctypes.data)
+    return okeys[:g], os_[:g], po
 
 
 def run_synthetic(engine, kind, seed, start, pairs_per_job, njobs, nthreads, table=None):

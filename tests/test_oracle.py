@@ -153,3 +153,34 @@ def test_flat_groupby_matches_engine():
     flat = [(int(np.searchsorted(po, i, side="right")) - 1, bytes(okk[i]).rstrip(b"\0"), int(osum[i]))
             for i in range(len(osum))]
     assert eng == flat
+
+
+def test_job_size_oracles_agree_with_the_flat_ones():
+    """the threaded stream oracles bench.py uses at 10^8..10^9 pairs are the flat group-by oracles
+    (themselves pinned to the engine above) on the same pairs, incl. the per-rank partition filter"""
+    import mrhbm_loader
+    mrhbm_loader.load()
+    from lua_mapreduce_b200 import synth
+    S, n = synth.SEED, 400_000
+    k, v = O.gen_u64(S, 11, n)
+    flat = O.groupby_u64(k, v, O.PART_MULHASH, 1024)
+    mt = O.groupby_u64_stream(S, 11, n, O.PART_MULHASH, 1024, nthreads=5)
+    assert all((a == b).all() for a, b in zip(flat, mt))
+    flat7 = O.groupby_u64(k, v, O.PART_MULHASH, 7)
+    for rank in range(3):
+        keys, sums, po = O.groupby_u64_stream(S, 11, n, O.PART_MULHASH, 7, world=3, rank=rank, nthreads=2)
+        want_k = [flat7[0][int(flat7[2][p]):int(flat7[2][p + 1])] for p in range(7) if p % 3 == rank]
+        want_s = [flat7[1][int(flat7[2][p]):int(flat7[2][p + 1])] for p in range(7) if p % 3 == rank]
+        assert (np.concatenate(want_k) == keys).all() and (np.concatenate(want_s) == sums).all()
+        for p in range(7):
+            assert int(po[p + 1] - po[p]) == (int(flat7[2][p + 1] - flat7[2][p]) if p % 3 == rank else 0)
+    table = synth.zipf_table(1 << 13)
+    recs = O.gen_zipf_rec32(S, 3, 150_000, table)
+    fk, fs, fpo = O.groupby_rec(recs, O.PART_FNV_LUA, 15)
+    counts = O.zipf_counts(S, 3, 150_000, table, nthreads=3)
+    assert int(counts.sum()) == 150_000
+    wk, ws, wpo = O.wordcount_from_counts(counts, O.PART_FNV_LUA, 15)
+    assert (wk == fk).all() and (ws == fs).all() and (wpo == fpo).all()
+    wk1, ws1, wpo1 = O.wordcount_from_counts(counts, O.PART_FNV_LUA, 15, world=2, rank=1)
+    sel = np.concatenate([np.arange(int(fpo[p]), int(fpo[p + 1])) for p in range(15) if p % 2 == 1])
+    assert (wk1 == fk[sel]).all() and (ws1 == fs[sel]).all()
