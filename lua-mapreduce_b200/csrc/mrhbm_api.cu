@@ -71,9 +71,12 @@ struct mrhbm_ctx {
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
   void* l1buf = nullptr;  // coarse regions of the two-level split
   uint64_t l1_cap = 0;
-  void* comb = nullptr;  // map-side combined pairs
-  uint32_t *d_hll = nullptr, *h_hll = nullptr;  // HyperLogLog registers of the combined stream (8 ranks x kHllRegs on the host)
-  uint64_t comb_cap = 0;
+  // map-side combiner: the global (L2 resident) hash table and the records compacted out of it
+  void *comb = nullptr, *gtab = nullptr;
+  uint64_t comb_cap = 0, gtab_cap = 0;  // records
+  uint32_t gtab_extra = 0;              // log2 growth of the table beyond its L2-resident size after it filled up once
+  bool no_combine = false;              // sticky: more distinct keys than the largest table takes
+  bool combine_checked = false;         // sticky: values large enough that u32 sums must be checked add by add
   uint64_t N = 0, groups = 0;
   bool shuffled = false;
   std::vector<uint32_t> h_bin_off, h_uoff;
@@ -391,8 +394,6 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaHostAlloc((void**)&c->h_small, 64 * sizeof(uint32_t), cudaHostAllocDefault));
   c->Pl = cfg->num_partitions;
   for (int r = 1; r <= 8; r++) c->pbase[r] = cfg->num_partitions;
-  CU(c, cudaMalloc((void**)&c->d_hll, 8 * kHllRegs * sizeof(uint32_t)));
-  CU(c, cudaHostAlloc((void**)&c->h_hll, 8 * kHllRegs * sizeof(uint32_t), cudaHostAllocDefault));
   c->cap = (cfg->flags & MRHBM_F_SMALL_BINS) ? 96 : cap_records(c->rb);
   CU(c, cudaMalloc((void**)&c->d_sample, 256 * sizeof(uint32_t)));
   CU(c, cudaHostAlloc((void**)&c->h_sample, 256 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -422,13 +423,12 @@ void mrhbm_destroy(mrhbm_ctx* c) {
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
                    c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
-                   c->d_hll,       c->l1buf,       c->regions,    c->d_l1all,     c->d_sample};
+                   c->gtab,        c->l1buf,       c->regions,    c->d_l1all,     c->d_sample};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_acc) cudaFreeHost(c->h_acc);
   if (c->h_small) cudaFreeHost(c->h_small);
-  if (c->h_hll) cudaFreeHost(c->h_hll);
   for (int i = 0; i < EV_N; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -718,9 +718,9 @@ void set_range_hint(ShuffleBuffers& b, uint32_t S, uint32_t ordered) {
   b.hint_q = S > 1 ? (uint64_t)(((unsigned __int128)1 << 64) / S) : 0;
 }
 
-BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered, uint32_t rep_shift = 0) {
+BinParams make_bp(const mrhbm_ctx* c, uint32_t S, uint32_t ordered) {
   BinParams bp{};
-  bp.rep_shift = rep_shift;
+  bp.rep_shift = 0;
   bp.P = c->cfg.num_partitions;
   bp.S = S;
   bp.partitioner = c->cfg.partitioner;
@@ -901,39 +901,15 @@ int ensure_out(mrhbm_ctx* c, uint64_t need) {
 struct Src {
   const char* p;
   uint64_t n;
-  // segmented (combiner output): nseg regions of seg_stride records, fill levels in d_seg_counts
-  const uint32_t* d_seg_counts = nullptr;
-  uint64_t seg_stride = 0;
-  uint32_t nseg = 0;
 };
-inline BinParams with_src(BinParams bp, const Src& sr) {
-  bp.seg_counts = sr.d_seg_counts;
-  bp.seg_stride = sr.seg_stride;
-  bp.nseg = sr.nseg;
-  return bp;
-}
-// The pairs the shuffle partitions: the committed pool ranges, or -- with a combiner declared
-// (job.lua:92-96,198-202) -- their map-side combined image.  EV_START .. EV_COMBINE.
-// HyperLogLog estimate from max-merged registers of `ranks` sketches
-double hll_estimate(const uint32_t* regs, int ranks) {
-  const double m = (double)kHllRegs;
-  double sum = 0;
-  uint32_t zeros = 0;
-  for (uint32_t i = 0; i < kHllRegs; i++) {
-    uint32_t r = 0;
-    for (int k = 0; k < ranks; k++) r = std::max(r, regs[(size_t)k * kHllRegs + i]);
-    sum += std::ldexp(1.0, -(int)r);
-    zeros += r == 0;
-  }
-  double e = 0.7213 / (1.0 + 1.079 / m) * m * m / sum;
-  if (e < 2.5 * m && zeros) e = m * std::log(m / zeros);  // small-range correction
-  return e;
-}
+constexpr uint64_t kGtabL2Bytes = 64ull << 20;  // global combiner table sized to stay resident in the 126 MB L2
+constexpr uint32_t kGtabMaxExtra = 4;           // ... grown up to 16x (1 GB) when the keys do not fit
 
-// *distinct: < 0 when no combine ran, else the estimated number of distinct keys in the
-// combined stream of the whole job (all ranks)
-int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_stats& st, double* distinct) {
-  *distinct = -1.0;
+// The pairs the shuffle partitions: the committed pool ranges, or -- with a combiner declared
+// (job.lua:92-96,198-202) and enough pairs to pay for it -- one record per distinct key of this rank's pairs
+// with their sum (shared-memory table per SM + one L2-resident global table, see k_combine).  A rank-local
+// decision: the stages that follow only see "the pairs this rank contributes".  EV_START .. EV_CSTART.
+int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_stats& st) {
   srcs.clear();
   uint64_t n = 0;
   for (auto& r : live_ranges(c)) {
@@ -941,54 +917,44 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
     n += r.second;
   }
   *N = n;
-  // collective in a multi-GPU job: every rank must take the same branch
-  uint32_t all[8];
-  int rc = gather_u32(c, (c->cfg.combiner && n >= (1u << 20)) ? 1u : 0u, all);
-  if (rc) return rc;
-  bool any = false;
-  for (int r = 0; r < c->world; r++) any |= all[r] != 0;
-  if (!c->cfg.combiner || !any) return 0;
-  // every combiner CTA owns one output region (no global append counter): size it for the worst case
-  const uint32_t nseg = (uint32_t)c->sm_count;
-  uint64_t region = 0;
-  for (auto& sr : srcs) region += sr.n / nseg + combine_region_slack(c->rb);
-  if (region >= 0xfffffff0ull) return fail(c, MRHBM_E_INVAL, "combiner region too large");
-  rc = ensure_records(c, &c->comb, &c->comb_cap, region * nseg);
-  if (rc) return rc;
-  uint32_t* segc = c->d_hll + kHllRegs;  // [nseg] fill levels, after the sketch registers
-  CU(c, cudaMemsetAsync(c->d_hll, 0, (kHllRegs + nseg) * sizeof(uint32_t), c->stream));
-  for (auto& sr : srcs)
-    st.launches += launch_combine(c->rb, sr.p, sr.n, c->comb, (uint32_t)region, segc, c->d_hll, c->sm_count, c->stream);
-  CU(c, cudaGetLastError());
-  int ranks = 1;
-  CU(c, cudaMemcpyAsync(c->h_hll, c->d_hll, (kHllRegs + nseg) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  double est = hll_estimate(c->h_hll, ranks);
-  if (c->world > 1) {  // upper bound: sum of the per-rank estimates (exact merge would need an all-reduce max)
-    rc = gather_u32(c, (uint32_t)std::min(est, 4.0e9), all);
+  if (!c->cfg.combiner || c->no_combine || n < (1u << 20)) return 0;
+  cudaStream_t s = c->stream;
+  bool checked = c->combine_checked;
+  for (;;) {
+    const uint32_t glog = gtab_log_slots(c->rb, kGtabL2Bytes) + c->gtab_extra;
+    const uint64_t slots = 1ull << glog;
+    int rc = ensure_records(c, &c->gtab, &c->gtab_cap, slots);
     if (rc) return rc;
-    est = 0;
-    for (int r = 0; r < c->world; r++) est += all[r];
+    rc = ensure_records(c, &c->comb, &c->comb_cap, slots);
+    if (rc) return rc;
+    CU(c, cudaMemsetAsync(c->gtab, 0, slots * c->rb, s));
+    CU(c, cudaMemsetAsync(c->d_small, 0, 3 * sizeof(uint32_t), s));  // [0] flags, [1] records out, [2] largest value
+    for (auto& sr : srcs)
+      st.launches += launch_combine(c->rb, sr.p, sr.n, (uint32_t*)c->gtab, glog, c->d_small, checked, c->sm_count, s);
+    st.launches += launch_gtab_compact(c->rb, (const uint32_t*)c->gtab, glog, c->comb, c->d_small + 1, s);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->h_small, c->d_small, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    const uint32_t ef = c->h_small[0];
+    if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
+    if (ef & ERRF_SKEW) {  // the table filled up: more distinct keys than it takes
+      if (c->gtab_extra < kGtabMaxExtra && (slots << 1) * c->rb <= (4ull << 30)) {
+        c->gtab_extra++;
+        continue;
+      }
+      c->no_combine = true;  // the partition / sort / reduce stages take the raw pairs
+      return 0;
+    }
+    if (!checked && c->rb != 16 && (uint64_t)c->h_small[2] * n >= 0xfffffff0ull) {
+      // the fire-and-forget adds could have wrapped a u32 sum unnoticed: again, with checked adds (sticky)
+      checked = c->combine_checked = true;
+      continue;
+    }
+    srcs.clear();
+    srcs.push_back(Src{(const char*)c->comb, c->h_small[1]});
+    *N = c->h_small[1];
+    return 0;
   }
-  *distinct = est;
-  uint64_t n2 = 0;
-  for (uint32_t i = 0; i < nseg; i++) n2 += c->h_hll[kHllRegs + i];
-  srcs.clear();
-  Src out{(const char*)c->comb, n2};
-  out.d_seg_counts = segc;
-  out.seg_stride = region;
-  out.nseg = nseg;
-  srcs.push_back(out);
-  *N = n2;
-  return 0;
-}
-
-// sub-bins per partition when bins are sized by distinct keys (aggregation pass)
-uint32_t pick_sub_bins_agg(const mrhbm_ctx* c, double distinct) {
-  double keys_per_bin = std::min<double>(agg_table_entries(c->rb) * 0.4, c->cap * 0.5);
-  double bins = std::ceil(distinct * 1.15 / keys_per_bin);
-  double P = c->cfg.num_partitions;
-  return (uint32_t)std::max(1.0, std::ceil(bins / P));
 }
 
 uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
@@ -1016,20 +982,18 @@ void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
 //            every rank's level 1 before anybody's level 2
 //   level 2  k_split_tma   the owner of a region pulls it from every rank's region buffer (NVLink bulk copies
 //            into shared memory, overlapped with the split of the previous tile) -> fine bins
-//   sort     k_sort_reduce_u64 / k_sort_reduce / k_agg_bins on local bins
+//   sort     k_sort_reduce_u64 / k_sort_reduce on local bins
 // Every bin and region has a fixed capacity (mean + slack); the claim cursor doubles as the count.  A full one
 // sets ERRF_CAPACITY, nothing is lost (the input stays in the pool) and the exact layout below takes over, for
 // good on this ctx.  Returns 0 with *done = true, 0 with *done = false (fall back), or an error.
-int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st,
-                 bool* done) {
+int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, mrhbm_stats& st, bool* done) {
   *done = false;
   const int G = c->world, me = c->rank;
   const uint32_t P = c->cfg.num_partitions;
   cudaStream_t s = c->stream;
-  const bool agg = distinct >= 0;  // duplicate-heavy: aggregate per bin, bins sized by distinct keys
   int rc = 0;
   // ---- would key-ordered sub-bins be balanced?  sample the keys before anything moves
-  const bool want_ordered = c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !c->no_ordered && !agg;
+  const bool want_ordered = c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && !c->no_ordered;
   uint32_t nonuniform = 0;
   if (want_ordered && N >= 4096) {
     CU(c, cudaMemsetAsync(c->d_sample, 0, 256 * sizeof(uint32_t), s));
@@ -1058,8 +1022,8 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     nonuniform |= all[2 * r + 1];
   }
   if (Nglobal == 0) return 0;  // nothing to do here: the exact path handles the empty shuffle
-  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, Nglobal);
-  for (int widen = 0;; widen++) {
+  const uint32_t S = pick_sub_bins(c, Nglobal);
+  {
     const uint64_t B = (uint64_t)P * S;
     if (B >= (1ull << 31)) return 0;
     const uint32_t ordered = (want_ordered && !nonuniform) || S == 1;
@@ -1069,13 +1033,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
       Bl_max = std::max(Bl_max, Bl_of[r]);
     }
     const uint64_t Bl = Bl_of[me];
-    // slots per fine bin: the sort capacity, or (aggregation) the expected records of a bin + 30 %
-    uint32_t bin_stride = c->cap;
-    if (agg) {
-      const double mean = (double)Nglobal / (double)B;
-      bin_stride = (uint32_t)std::min(4.0e9, mean * 1.3 + 8.0 * std::sqrt(mean) + 64.0);
-      bin_stride = (bin_stride + 7u) & ~7u;
-    }
+    const uint32_t bin_stride = c->cap;  // slots per fine bin: what one CTA sorts in shared memory
     // ---- levels.  One GPU, few bins: level 1 goes straight into the fine bins.
     SplitPlan pl{};
     const bool single_level = G == 1 && B <= kSplitMaxBinsHost;
@@ -1105,7 +1063,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     pl.me = (uint32_t)me;
     {
       // one rank's contribution to one region: F of the B bins, hash balanced
-      const double mean = (double)Nmax * (double)F / (double)B * (agg ? 1.3 : 1.0);
+      const double mean = (double)Nmax * (double)F / (double)B;
       const double ss = single_level ? (double)bin_stride : mean + 8.0 * std::sqrt(mean) + 64.0;
       if (ss >= 4.0e9) return 0;
       pl.sub_stride = ((uint64_t)ss + 7u) & ~7ull;
@@ -1152,7 +1110,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
-    for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+    for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, bp, pl, s);
     CU(c, cudaEventRecord(c->ev[EV_PLAN], s));
     if (G > 1) {
       rc = comm_allgather_u32(c->comm, c->sb.hist, c->d_l1all, (size_t)pl.C1 << c->ctr_shift, s, &c->err);
@@ -1173,10 +1131,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     ShuffleBuffers v = c->sb;
     v.cursor = fine_cursor;
     set_range_hint(v, S, ordered);
-    if (Bl) {
-      st.launches += agg ? launch_agg_bins(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s)
-                         : launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
-    }
+    if (Bl) st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
     c->h_uoff.assign(Bl + 1, 0);
@@ -1208,13 +1163,6 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
       if ((ordered && S > 1) || nonuniform) c->no_ordered = true;  // key-ordered sub-bins overflowed, or would
       return 0;
     }
-    if (ef & ERRF_SKEW) {  // an aggregation table overflowed: more distinct keys in a bin than estimated
-      if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
-        S *= 2;
-        continue;
-      }
-      return fail(c, MRHBM_E_SKEW, "a bin holds more distinct keys than one SM can aggregate");
-    }
     c->h_big.clear();
     c->rv = v;
     c->sb.stride = 0;
@@ -1243,36 +1191,31 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
 }
 
 // ---- one GPU, exact layout: hist -> scan -> scatter -> sort+reduce (skewed keys, oversized bins) ---------
-int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st) {
+int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, mrhbm_stats& st) {
   const uint32_t P = c->cfg.num_partitions;
   int rc = 0;
   uint32_t nbig = 0, ordered = 1;
   cudaStream_t s = c->stream;
   uint64_t B = 0;
-  const bool agg = distinct >= 0;  // duplicate-heavy: aggregate per bin, bins sized by distinct keys
-  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, N);
-  bool skip_ordered = c->no_ordered || agg;
+  uint32_t S = pick_sub_bins(c, N);
+  bool skip_ordered = c->no_ordered;
   // A bin that holds more distinct keys than one CTA sorts (ERRF_SKEW) is retried with
   // twice the sub-bins: distinct keys spread, hot keys keep collapsing in k_big_bins.
   for (int widen = 0;; widen++) {
     B = (uint64_t)P * S;
     if (B >= (1ull << 31)) return fail(c, MRHBM_E_INVAL, "too many bins");
-    // few, heavily hit bins (aggregation pass): spread every bin's counter over 2^rep copies
-    uint32_t rep = 0;
-    if (agg)
-      while (rep < 6 && (B << (rep + 1)) <= 65536) rep++;
-    const uint64_t Bv = B << rep;
+    const uint64_t Bv = B;
     rc = ensure_buffers(c, Bv, N);
     if (rc) return rc;
     ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !skip_ordered) || S == 1);
     c->sb.stride = 0;
     for (int attempt = 0;; attempt++) {
       st.attempts++;
-      BinParams bp = make_bp(c, S, ordered, rep);
+      BinParams bp = make_bp(c, S, ordered);
       CU(c, cudaMemsetAsync(c->sb.hist, 0, (Bv << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, with_src(bp, r), c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       st.launches += launch_exscan(c->sb.hist, (uint32_t)Bv, c->sb.bin_off, c->sb.cursor, nullptr, c->cap, c->sb.big_list,
                                    c->sb.counters + CNT_NBIG, c->sb.counters + CNT_TOTAL, c->ctr_shift, s, c->d_small + 64);
@@ -1285,7 +1228,7 @@ int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint6
         uint32_t F = 1;
         while ((uint64_t)F * F < B) F <<= 1;
         uint32_t C1 = (uint32_t)((B + F - 1) / F);
-        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
+        if (B >= 2048 && F <= 1024 && C1 <= 1024) {
           rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
           if (rc) return rc;
           // relative fill levels: coarse levels live in hist (dead after the scan), fine levels in cursor
@@ -1303,10 +1246,10 @@ int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint6
           pl.err_flags = c->sb.counters + CNT_ERR;
           pl.base_off = c->sb.bin_off;
           pl.ndest = 1;
-          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, bp, pl, s);
           st.launches += launch_split_l2(c->rb, bp, pl, s);
         } else {
-          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
         }
       }
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
@@ -1315,14 +1258,13 @@ int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint6
       c->sb.nseg = 1;
       c->sb.seg_off[0] = c->sb.bin_off;
       c->sb.seg_base[0] = 0;
-      c->sb.rep_shift = rep;
+      c->sb.rep_shift = 0;
       set_range_hint(c->sb, S, ordered);
-      st.launches += agg ? launch_agg_bins(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s)
-                         : launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
+      st.launches += launch_sort_reduce(c->rb, c->sb, (uint32_t)B, c->cap, c->sm_count, s);
       CU(c, cudaEventRecord(c->ev[EV_SORT], s));
       CU(c, cudaGetLastError());
       CU(c, cudaEventSynchronize(c->ev[EV_PROBE]));  // overlaps with scatter / sort on the device
-      nbig = agg ? 0 : c->h_counters[CNT_NBIG];
+      nbig = c->h_counters[CNT_NBIG];
       if (nbig && ordered && S > 1) {
         // key-ordered sub-bins are unbalanced for this key distribution: redo with hash sub-bins
         ordered = 0;
@@ -1380,7 +1322,7 @@ int shuffle_single_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint6
 
 // ---- several GPUs, exact layout: hist -> all-gather counts -> scatter (destination-major) -> NCCL all-to-all
 //      -> sort+reduce of the owned partitions, each bin gathered from one segment per source
-int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, double distinct, mrhbm_stats& st) {
+int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in, mrhbm_stats& st) {
   const int G = c->world, me = c->rank;
   const uint32_t P = c->cfg.num_partitions;
   uint32_t all[8];
@@ -1388,8 +1330,7 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
   if (rc) return rc;
   uint64_t Nglobal = 0;
   for (int r = 0; r < G; r++) Nglobal += all[r];
-  const bool agg = distinct >= 0;
-  uint32_t S = agg ? pick_sub_bins_agg(c, distinct) : pick_sub_bins(c, Nglobal);
+  uint32_t S = pick_sub_bins(c, Nglobal);
   uint32_t nbig = 0, ordered = 1;
   cudaStream_t s = c->stream;
   uint64_t B = 0, Bl = 0, total_recv = 0;
@@ -1404,7 +1345,7 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
     if (rc) return rc;
     rc = ensure_multi_buffers(c, B, Bl);
     if (rc) return rc;
-    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !agg && !c->no_ordered) || S == 1);
+    ordered = ((c->cfg.key_kind == MRHBM_KEY_U64 && !(c->cfg.flags & MRHBM_F_FORCE_RUNS) && widen == 0 && !c->no_ordered) || S == 1);
     c->sb.stride = 0;
     for (int attempt = 0;; attempt++) {
       st.attempts++;
@@ -1412,7 +1353,7 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
       CU(c, cudaMemsetAsync(c->sb.hist, 0, (B << c->ctr_shift) * sizeof(uint32_t), s));
       CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
       CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
-      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, with_src(bp, r), c->sb.hist, s);
+      for (auto& r : live) st.launches += launch_hist(c->rb, r.p, r.n, bp, c->sb.hist, s);
       CU(c, cudaEventRecord(c->ev[EV_HIST], s));
       // send layout (destination-major bins) + dense counts for the all-gather
       st.launches += launch_exscan(c->sb.hist, (uint32_t)B, c->sb.bin_off, c->sb.cursor, c->d_hd, 0xffffffffu, nullptr,
@@ -1435,7 +1376,7 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
         uint32_t F = 1;
         while ((uint64_t)F * F < B) F <<= 1;
         uint32_t C1 = (uint32_t)((B + F - 1) / F);
-        if (!agg && B >= 2048 && F <= 1024 && C1 <= 1024) {
+        if (B >= 2048 && F <= 1024 && C1 <= 1024) {
           rc = ensure_records(c, &c->l1buf, &c->l1_cap, N);
           if (rc) return rc;
           CU(c, cudaMemsetAsync(c->sb.hist, 0, ((uint64_t)C1 << c->ctr_shift) * sizeof(uint32_t), s));
@@ -1452,20 +1393,20 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
           pl.err_flags = c->sb.counters + CNT_ERR;
           pl.base_off = c->sb.bin_off;
           pl.ndest = 1;
-          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, with_src(bp, r), pl, s);
+          for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, bp, pl, s);
           st.launches += launch_split_l2(c->rb, bp, pl, s);
         } else {
-          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, with_src(bp, r), c->sb.cursor, c->sb.mid, s);
+          for (auto& r : live) st.launches += launch_scatter(c->rb, r.p, r.n, bp, c->sb.cursor, c->sb.mid, s);
         }
       }
       CU(c, cudaEventRecord(c->ev[EV_SCATTER], s));
       CU(c, cudaGetLastError());
       CU(c, cudaStreamSynchronize(s));
-      nbig = agg ? 0 : c->h_counters[CNT_NBIG];
+      nbig = c->h_counters[CNT_NBIG];
       total_recv = c->h_counters[CNT_TOTAL];
       // every rank counted the oversized bins of ALL ranks from the same all-gathered counts:
       // the decision is identical everywhere without another collective
-      bool redo = !agg && c->h_counters[CNT_GBIG] && ordered && S > 1;
+      bool redo = c->h_counters[CNT_GBIG] && ordered && S > 1;
       if (redo) {
         ordered = 0;
         continue;
@@ -1519,8 +1460,7 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
       const int64_t delta = (int64_t)((const char*)c->sb.mid - (const char*)c->recvbuf) + (int64_t)send_off[me];
       v.seg_base[me] = (uint64_t)(delta / (int64_t)c->rb);
     }
-    st.launches += agg ? launch_agg_bins(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s)
-                       : launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
+    st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     st.launches += launch_big_bins(c->rb, v, nbig, c->cap, s);
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
@@ -1591,17 +1531,16 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
   st.pairs = N_in;
   std::vector<Src> live;
   CU(c, cudaEventRecord(c->ev[EV_START], c->stream));
-  double distinct = -1;
-  int rc = collect_sources(c, live, &N, st, &distinct);
+  int rc = collect_sources(c, live, &N, st);
   if (rc) return rc;
   CU(c, cudaEventRecord(c->ev[EV_CSTART], c->stream));
   if (!c->no_optimistic && !(c->cfg.flags & MRHBM_F_NO_OPTIMISTIC) && !(c->tune & 1u)) {
     bool done = false;
-    rc = shuffle_fast(c, live, N, N_in, distinct, st, &done);
+    rc = shuffle_fast(c, live, N, N_in, st, &done);
     if (rc) return rc;
     if (done) return MRHBM_OK;
   }
-  return c->world > 1 ? shuffle_multi_exact(c, live, N, N_in, distinct, st) : shuffle_single_exact(c, live, N, N_in, distinct, st);
+  return c->world > 1 ? shuffle_multi_exact(c, live, N, N_in, st) : shuffle_single_exact(c, live, N, N_in, st);
 }
 
 int mrhbm_stats_get(mrhbm_ctx* c, mrhbm_stats* out) {

@@ -165,10 +165,6 @@ template <int RB>
 __global__ void __launch_bounds__(256) k_hist(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                               uint32_t* __restrict__ hist) {
   constexpr int U = Unroll<RB>::U;
-  if (bp.seg_counts) {
-    recs += (size_t)blockIdx.y * bp.seg_stride * Rec<RB>::kVec;
-    n = bp.seg_counts[blockIdx.y];
-  }
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
     uint32_t w[U][Rec<RB>::kWords];
@@ -189,10 +185,6 @@ template <int RB>
 __global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ recs, uint64_t n, BinParams bp,
                                                  uint32_t* __restrict__ cursor, uint4* __restrict__ mid) {
   constexpr int U = Unroll<RB>::U;
-  if (bp.seg_counts) {
-    recs += (size_t)blockIdx.y * bp.seg_stride * Rec<RB>::kVec;
-    n = bp.seg_counts[blockIdx.y];
-  }
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * U) {
     uint32_t w[U][Rec<RB>::kWords];
@@ -289,7 +281,7 @@ struct SplitArgs {
 constexpr int kTmaSplitThreads = 512;
 constexpr int kTmaTileBytes = 40 * 1024;
 __host__ __device__ constexpr size_t tma_split_smem(int rb, int tile_bytes = kTmaTileBytes) {
-  return 2 * (size_t)tile_bytes + 2 * (size_t)(tile_bytes / rb) * sizeof(uint16_t);
+  return 2 * (size_t)tile_bytes + (size_t)(tile_bytes / rb) * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -333,10 +325,10 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   constexpr int IPT = kSplitMaxBins / THREADS;       // bins per thread in the scan
   uint4* raw0 = (uint4*)smem_raw;
   uint4* raw1 = (uint4*)(smem_raw + TILE_BYTES);
-  uint16_t* perm = (uint16_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index
-  uint16_t* pos_sub = perm + T;                                 // output position -> bin
-  __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins], sgb[kSplitMaxBins];
-  __shared__ unsigned long long sdst[kSplitMaxBins];  // byte address of slot 0 of the bin's destination region
+  uint32_t* perm = (uint32_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index | bin << 16
+  __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins];
+  __shared__ unsigned long long sbase[kSplitMaxBins];  // this tile: byte address output position 0 would have in the
+                                                       // bin's run (0: the run does not fit, nothing is stored)
   __shared__ uint32_t wsum[THREADS / 32];
   __shared__ uint32_t s_rbase[9], s_fbase[9];  // (kernel-parameter arrays indexed by a register would be copied to local memory)
   __shared__ __align__(8) uint64_t mbar[2];
@@ -350,10 +342,6 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   const uint4* src = a.src;
   uint64_t n = a.n;
   uint32_t coarse = 0;
-  if (a.level == 1 && bp.seg_counts) {  // segmented source (the combiner's per-CTA regions)
-    src += (size_t)blockIdx.y * bp.seg_stride * R::kVec;
-    n = bp.seg_counts[blockIdx.y];
-  }
   if (a.level == 2) {
     coarse = blockIdx.y;
     if (a.base_off) {  // exact: the coarse region is the union of its fine bins
@@ -386,15 +374,6 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (uint32_t b = tid; b < kSplitMaxBins; b += THREADS) scnt[b] = 0;
-  // destination region of every bin of this level (constant over the tiles)
-  for (uint32_t b = tid; b < a.nbins; b += THREADS) {
-    unsigned long long p = (unsigned long long)(uintptr_t)a.dst;
-    if (!a.base_off) {  // (exact layout: slots are absolute)
-      const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-      p += (unsigned long long)dbin * a.dst_stride * RB;
-    }
-    sdst[b] = p;
-  }
   __syncthreads();
   if (tid == 0 && blockIdx.x < ntiles)
     bulk_load(raw0, src + (uint64_t)blockIdx.x * T * R::kVec, tile_len(blockIdx.x) * RB, &mbar[0]);
@@ -469,9 +448,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     for (int k = 0; k < U; k++) {
       const uint32_t i = tid + k * THREADS;
       if (i < tn) {
-        uint32_t p = soff[sub[k]] + rk[k];
-        perm[p] = (uint16_t)i;
-        pos_sub[p] = (uint16_t)sub[k];
+        perm[soff[sub[k]] + rk[k]] = i | (sub[k] << 16);
       }
     }
 #pragma unroll
@@ -479,6 +456,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       const uint32_t b = IPT * tid + i;
       if (b < a.nbins) {
         uint32_t gg = g[i];
+        bool fits = true;
         if (v[i]) {
           if (a.base_off) {  // exact layout: absolute start of the destination region, always large enough
             const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
@@ -486,19 +464,23 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
             gg += a.base_off[(size_t)f << a.rep_shift];
           } else if (gg + v[i] > a.capacity) {
             atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
+            fits = false;
           }
         }
-        sgb[b] = gg - ex[i];  // slot of output position p in bin b = sgb[b] + p
+        // output position p of this tile goes to slot gg - ex[i] + p of the bin (64-bit wrap-around arithmetic)
+        unsigned long long dstb = (unsigned long long)(uintptr_t)a.dst;
+        if (!a.base_off) dstb += (unsigned long long)(a.level == 1 ? b : coarse * a.F + b) * a.dst_stride * RB;
+        sbase[b] = fits ? dstb + ((unsigned long long)gg - (unsigned long long)ex[i]) * RB : 0ull;
       }
     }
     __syncthreads();
     // copy out: consecutive output positions of one bin are consecutive in global (or peer) memory
     for (uint32_t p = tid; p < tn; p += THREADS) {
-      const uint32_t b = pos_sub[p];
-      const uint32_t slot = sgb[b] + p;
-      const uint4* r = raw + (size_t)perm[p] * R::kVec;
-      if (!a.base_off && slot >= a.capacity) continue;  // flagged above
-      uint4* d = (uint4*)(uintptr_t)(sdst[b] + (unsigned long long)slot * RB);
+      const uint32_t pb = perm[p];
+      const unsigned long long base = sbase[pb >> 16];
+      const uint4* r = raw + (size_t)(pb & 0xffffu) * R::kVec;
+      if (!base) continue;  // flagged above
+      uint4* d = (uint4*)(uintptr_t)(base + (unsigned long long)p * RB);
 #pragma unroll
       for (int vv = 0; vv < R::kVec; vv++) stg_stream(d + vv, r[vv]);
     }
@@ -632,23 +614,25 @@ __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict
 // ============================================================================
 // map-side combiner (mapreduce/job.lua:92-96,198-202 with the built-in sum)
 // ============================================================================
-// Each CTA keeps an open-addressing table of whole records in shared memory for its lifetime;
-// a pair whose key is resident adds its value there, everything else passes through.  Hot
-// keys (Zipf) collapse to at most one record per CTA before the partition pass.
+// Two hash tables of whole records.
+//  * Every CTA keeps an open-addressing table in SHARED memory for its lifetime: hot keys (Zipf) are summed
+//    there with shared-memory atomics and never travel further.
+//  * Whatever does not find a place there -- the long tail -- is added to ONE open-addressing table in GLOBAL
+//    memory sized to stay resident in the 126 MB L2 (2^21 32-byte entries = 64 MB): one L2 atomic per pair
+//    instead of a partition pass, a sort pass and a reduce pass over that pair.  At its end every CTA flushes
+//    its shared table into the global one; k_gtab_compact then emits one record per table entry.
+// The result (one record per distinct key, in the common case) is what the partition/sort/reduce stages see.
+// The global table does not have to be perfect: two entries for one key only mean that the sort+reduce stage
+// adds them up, so reads of a slot another thread is publishing need no stronger ordering than "state first".
+// A full table raises ERRF_SKEW and the host retries with a larger one (not L2 resident any more) or without
+// the combiner; a u32 sum about to wrap raises ERRF_OVERFLOW (string records carry u32 values).
 constexpr uint32_t kCombineLock = 0xffffffffu;
 constexpr int kCombineThreads = 1024;
 constexpr int kCombineSmem = 200 * 1024;
-// HyperLogLog sketch of the keys the combiner lets through: sizes the bins of the aggregation
-// pass by DISTINCT keys (a duplicate-heavy stream must not be binned by record count)
-__device__ __forceinline__ void hll_update(uint32_t* regs, uint64_t h) {
-  uint32_t idx = (uint32_t)h & (kHllRegs - 1);
-  uint64_t x = h >> 11;  // 53 bits
-  uint32_t rho = x ? (uint32_t)__clzll((long long)x) - 10u : 54u;
-  atomicMax(regs + idx, rho);
-}
+constexpr int kGtabMaxProbes = 96;
 
-// cheap 32-bit slot hash (one IMAD per key word): any hash works for the table, the 64-bit
-// word_hash is only needed for the HyperLogLog sketch of what passes through
+// cheap 32-bit hash of the key words (one IMAD per word); the shared table takes its top bits, the global
+// table a remix of it
 template <int RB>
 __device__ __forceinline__ uint32_t slot_hash(const uint32_t* w) {
   uint32_t h = 0x9E3779B9u;
@@ -658,76 +642,200 @@ __device__ __forceinline__ uint32_t slot_hash(const uint32_t* w) {
   h *= 0xC2B2AE35u;
   return h ^ (h >> 13);
 }
+__device__ __forceinline__ uint32_t ldv_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ldv_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldv_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 
-template <int RB>
-__global__ void __launch_bounds__(kCombineThreads, 1)
-    k_combine(const uint4* __restrict__ recs, uint64_t n, uint4* __restrict__ out, uint32_t region_cap,
-              uint32_t* __restrict__ seg_counts, uint32_t entries, uint32_t* __restrict__ g_hll) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t hll[kHllRegs];
-  __shared__ uint32_t s_fill;  // fill level of this CTA's output region
+__device__ __forceinline__ void stv_v4(uint4* p, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// adds (key of w, v) to the global table.  Entry = one record slot: strings {key words, u32 state}, state =
+// 0 empty / kCombineLock being written / sum + 1; u64 keys {u64 key, u64 state} with the same encoding.
+// CHECKED: use the returned old value to catch a u32 sum about to wrap (otherwise the add is fire-and-forget
+// and the caller has bounded the sums: pairs x largest value < 2^32).
+// Entries of 16 / 32 bytes are read with ONE round of independent 16-byte loads (state included).  Such a
+// snapshot may pair a published state with key words from before the publication (zeros): that can only look
+// like a match for a key whose leading 16 bytes are all zero, so those keys take the two-step path (state,
+// then key) that the larger record classes always take.
+template <int RB, bool CHECKED>
+__device__ __forceinline__ void gtab_add(uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint64_t v, uint32_t h,
+                                         uint32_t* __restrict__ flags) {
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
-  uint32_t* tab = (uint32_t*)smem_raw;  // entries whole records; value word: 0 empty, lock, else the sum
-  const uint32_t tid = threadIdx.x, lane = tid & 31;
-  for (uint32_t i = tid; i < entries * W; i += blockDim.x) tab[i] = 0;
-  for (uint32_t i = tid; i < kHllRegs; i += blockDim.x) hll[i] = 0;
-  if (tid == 0) s_fill = seg_counts[blockIdx.x];
-  __syncthreads();
-  uint4* region = out + (size_t)blockIdx.x * region_cap * R::kVec;
-  auto append = [&](bool want, const uint32_t* w) {  // warp-aggregated append to the CTA's region
-    uint32_t mask = __ballot_sync(0xffffffffu, want);
-    if (!mask) return;
-    if (want) hll_update(hll, word_hash<RB>(w));
-    uint32_t basepos = 0;
-    if (lane == (uint32_t)(__ffs(mask) - 1)) basepos = atomicAdd(&s_fill, (uint32_t)__popc(mask));
-    basepos = __shfl_sync(0xffffffffu, basepos, __ffs(mask) - 1);
-    if (want) {
-      uint4* d = region + (size_t)(basepos + __popc(mask & ((1u << lane) - 1))) * R::kVec;
-#pragma unroll
-      for (int v = 0; v < R::kVec; v++) stg_stream(d + v, make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]));
+  uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+  g ^= g >> 12;
+  g *= 0x297A2D39u;
+  g ^= g >> 15;
+  const uint32_t mask = (1u << glog) - 1u;
+  uint32_t slot = g >> (32 - glog);
+  if constexpr (R::kU64) {
+    const unsigned long long key = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32), lock = ~0ull;
+#pragma unroll 1
+    for (int probe = 0; probe < kGtabMaxProbes; probe++) {
+      unsigned long long* e = (unsigned long long*)gtab + 2 * (size_t)slot;
+      unsigned long long st, k;
+      if (key != 0) {  // one 16-byte load: key and state
+        const uint4 x = ldv_v4((const uint4*)e);
+        k = (unsigned long long)x.x | ((unsigned long long)x.y << 32);
+        st = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
+      } else {
+        st = ldv_u64(e + 1);
+        k = 0;
+      }
+      if (st == 0) {
+        const unsigned long long old = atomicCAS(e + 1, 0ull, lock);
+        if (old == 0) {
+          *(volatile unsigned long long*)e = key;
+          __threadfence();
+          atomicExch(e + 1, v + 1ull);
+          return;
+        }
+        st = old;
+      }
+      if (st == lock || key == 0) {  // published meanwhile (or the zero key): read the key after the state
+        while (st == lock) st = ldv_u64(e + 1);
+        k = ldv_u64(e);
+      }
+      if (k == key) {
+        if (v) atomicAdd(e + 1, (unsigned long long)v);
+        return;
+      }
+      slot = (slot + 1) & mask;
     }
+  } else {
+    if (v >= 0xfffffff0ull) {
+      atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+      return;
+    }
+    const uint32_t v32 = (uint32_t)v;
+    const bool snapshot_ok = RB == 32 && (w[0] | w[1] | w[2] | w[3]) != 0;
+#pragma unroll 1
+    for (int probe = 0; probe < kGtabMaxProbes; probe++) {
+      uint32_t* e = gtab + (size_t)slot * W;
+      uint4 x[R::kVec];
+      uint32_t st;
+      if (snapshot_ok) {
+#pragma unroll
+        for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i);
+        st = x[R::kVec - 1].w;
+      } else {
+        st = ldv_u32(e + KW);
+      }
+      if (st == 0) {
+        const uint32_t old = atomicCAS(e + KW, 0u, kCombineLock);
+        if (old == 0) {
+#pragma unroll
+          for (int i = 0; i < R::kVec; i++)  // the last vector rewrites the lock word with itself
+            stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]));
+          __threadfence();
+          atomicExch(e + KW, v32 + 1u);
+          return;
+        }
+        st = old;
+      }
+      if (st == kCombineLock || !snapshot_ok) {  // read the key after the (published) state
+        while (st == kCombineLock) st = ldv_u32(e + KW);
+#pragma unroll
+        for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i);
+      }
+      bool eq = true;
+#pragma unroll
+      for (int i = 0; i < R::kVec; i++)
+        eq = eq && x[i].x == w[4 * i] && x[i].y == w[4 * i + 1] && x[i].z == w[4 * i + 2] && (4 * i + 3 == KW || x[i].w == w[4 * i + 3]);
+      if (eq) {
+        if (v32) {
+          if (CHECKED) {
+            const uint32_t old = atomicAdd(e + KW, v32);
+            if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+          } else {
+            atomicAdd(e + KW, v32);
+          }
+        }
+        return;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+  atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
+}
+
+// flags[0] |= ERRF_*, flags[2] = max over the values seen (saturated to u32)
+template <int RB, bool CHECKED>
+__global__ void __launch_bounds__(kCombineThreads, 1)
+    k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t entries, uint32_t* __restrict__ gtab, uint32_t glog,
+              uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = Rec<RB>;
+  constexpr int W = R::kWords, KW = R::kKeyWords;
+  // shared table, WORD-MAJOR: word k of entry e at tab[k * entries + e] (k = KW: 0 empty, lock, else the u32 partial
+  // sum), so that 32 lanes probing 32 random entries hit 32 random banks instead of the four a record stride allows
+  uint32_t* tab = (uint32_t*)smem_raw;
+  uint32_t* state = tab + (size_t)KW * entries;
+  // pairs that found no place in the shared table wait in a per-warp queue (record indices) until 32 of them are
+  // there: the global-table walk, a chain of L2 round trips, then runs with all lanes busy instead of the ~30 %
+  // that miss in one batch
+  __shared__ uint32_t queue[kCombineThreads / 32][64];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  uint32_t* q = queue[tid >> 5];
+  uint32_t qn = 0, vmax = 0;
+  for (uint32_t i = tid; i < entries * (KW + 1); i += blockDim.x) tab[i] = 0;
+  __syncthreads();
+  auto to_gtab = [&](uint32_t idx) {
+    uint32_t w[W];
+    load_rec<RB>(recs + (size_t)idx * R::kVec, w);
+    gtab_add<RB, CHECKED>(gtab, glog, w, rec_value<RB>(w), slot_hash<RB>(w), flags);
   };
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t n_round = (n + 31) / 32 * 32;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n_round; i += stride) {
-    uint32_t w[W];
-    bool valid = i < n, pass = valid;
-    if (valid) {
+    bool need = false;
+    if (i < n) {
+      uint32_t w[W];
       load_rec<RB>(recs + i * R::kVec, w);
-      uint32_t v = w[KW];
-      bool small = v != 0 && v <= 0xffffu && (!R::kU64 || w[3] == 0);
-      if (small) {
+      const uint64_t v = rec_value<RB>(w);
+      vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
+      need = true;
+      if (v != 0 && v <= 0xffffull) {  // (a zero cannot live in the shared table: its state word would read "empty")
         uint32_t slot = __umulhi(slot_hash<RB>(w), entries);
-        // The kernel is bound by shared-memory load throughput: leave the probe loop as early as
-        // possible and stop comparing at the first zero word (keys are zero padded, no NUL inside).
 #pragma unroll 1
         for (int probe = 0; probe < 4; probe++) {
-          uint32_t* e = tab + (size_t)slot * W;
-          uint32_t st = *(volatile uint32_t*)(e + KW);
+          const uint32_t st = *(volatile uint32_t*)(state + slot);
           if (st == 0) {
-            if (atomicCAS(e + KW, 0u, kCombineLock) == 0u) {
+            if (atomicCAS(state + slot, 0u, kCombineLock) == 0u) {
 #pragma unroll
-              for (int k = 0; k < KW; k++) e[k] = w[k];
+              for (int k = 0; k < KW; k++) tab[(size_t)k * entries + slot] = w[k];
               __threadfence_block();
-              atomicExch(e + KW, v);
-              pass = false;
+              atomicExch(state + slot, (uint32_t)v);
+              need = false;
               break;
             }
           } else if (st != kCombineLock && st <= 0x7fffffffu) {
             bool eq = true;
 #pragma unroll
             for (int k = 0; k < KW; k++) {
-              uint32_t x = ((volatile uint32_t*)e)[k];
+              const uint32_t x = ((volatile uint32_t*)tab)[(size_t)k * entries + slot];
               if (x != w[k]) {
                 eq = false;
                 break;
               }
-              if (!R::kU64 && x == 0) break;  // both keys end here
+              if (!R::kU64 && x == 0) break;  // both keys end here (zero padded, no NUL inside)
             }
             if (eq) {
-              atomicAdd(e + KW, v);  // <= 0x7fffffff + 0xffff: never wraps, never looks empty or locked
-              pass = false;
+              atomicAdd(state + slot, (uint32_t)v);  // <= 0x7fffffff + 0xffff: never wraps, never looks empty or locked
+              need = false;
               break;
             }
           }
@@ -735,25 +843,77 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
         }
       }
     }
-    append(pass, w);
-  }
-  __syncthreads();
-  // flush the table
-  const uint32_t e_round = (entries + 31) / 32 * 32;
-  for (uint32_t e = tid; e < e_round; e += blockDim.x) {
-    uint32_t w[W];
-    bool want = false;
-    if (e < entries) {
-#pragma unroll
-      for (int k = 0; k < W; k++) w[k] = tab[(size_t)e * W + k];
-      want = w[KW] != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, need);
+    if (m) {
+      if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        to_gtab(q[qn + lane]);
+        __syncwarp();
+      }
     }
-    append(want, w);
   }
+  if (lane < qn) to_gtab(q[lane]);
   __syncthreads();
-  if (tid == 0) seg_counts[blockIdx.x] = s_fill;
-  for (uint32_t i = tid; i < kHllRegs; i += blockDim.x)
-    if (hll[i]) atomicMax(g_hll + i, hll[i]);
+  // flush the shared table into the global one
+  for (uint32_t e = tid; e < entries; e += blockDim.x) {
+    const uint32_t st = state[e];
+    if (!st) continue;
+    uint32_t w[W];
+#pragma unroll
+    for (int k = 0; k < KW; k++) w[k] = tab[(size_t)k * entries + e];
+#pragma unroll
+    for (int k = KW; k < W; k++) w[k] = 0;
+    gtab_add<RB, CHECKED>(gtab, glog, w, (uint64_t)st, slot_hash<RB>(w), flags);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane == 0 && vmax) atomicMax(flags + 2, vmax);
+}
+
+// one record per non-empty entry of the global table, appended to out (order unspecified)
+template <int RB>
+__global__ void __launch_bounds__(256) k_gtab_compact(const uint32_t* __restrict__ gtab, uint32_t glog, uint4* __restrict__ out,
+                                                      uint32_t* __restrict__ count) {
+  using R = Rec<RB>;
+  constexpr int W = R::kWords, KW = R::kKeyWords;
+  const uint32_t slots = 1u << glog, lane = threadIdx.x & 31;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < slots; base += gridDim.x * blockDim.x) {
+    const uint32_t s = base + lane;
+    uint32_t w[W];
+    const uint4* e = (const uint4*)(gtab + (size_t)s * W);
+#pragma unroll
+    for (int i = 0; i < R::kVec; i++) {
+      const uint4 x = e[i];
+      w[4 * i] = x.x;
+      w[4 * i + 1] = x.y;
+      w[4 * i + 2] = x.z;
+      w[4 * i + 3] = x.w;
+    }
+    bool has;
+    if constexpr (R::kU64) {
+      unsigned long long st = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
+      has = st != 0;
+      st -= 1ull;
+      w[2] = (uint32_t)st;
+      w[3] = (uint32_t)(st >> 32);
+    } else {
+      has = w[KW] != 0;
+      w[KW] -= 1u;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, has);
+    if (!m) continue;
+    uint32_t pos = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) pos = atomicAdd(count, (uint32_t)__popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+    if (has) {
+      uint4* d = out + (size_t)pos * R::kVec;
+#pragma unroll
+      for (int i = 0; i < R::kVec; i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+  }
 }
 
 // pairs a rank reduces = the fill levels (clamped to the region capacity) of its regions in every rank's
@@ -926,17 +1086,17 @@ cudaError_t kernels_configure() {
   e = cudaFuncSetAttribute(k_big_bins<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                            (int)sort_smem_bytes(RB));                                             \
   if (e != cudaSuccess) return e;                                                                 \
-  e = cudaFuncSetAttribute(k_agg_bins<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                           (int)sort_smem_bytes(RB));                                             \
-  if (e != cudaSuccess) return e;
+
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
   e = cudaFuncSetAttribute(k_sort_reduce_u64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_sort_reduce_u64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
   if (e != cudaSuccess) return e;
-#define CFGC(RB)                                                                                       \
-  e = cudaFuncSetAttribute(k_combine<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
+#define CFGC(RB)                                                                                             \
+  e = cudaFuncSetAttribute(k_combine<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem); \
+  if (e != cudaSuccess) return e;                                                                            \
+  e = cudaFuncSetAttribute(k_combine<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
   if (e != cudaSuccess) return e;
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
 #undef CFGC
@@ -967,14 +1127,9 @@ int launch_gen_zipf32(void* dst, uint64_t seed, uint64_t start, uint64_t n, cons
   k_gen_zipf32<<<stream_grid(n, 256, 8), 256, 0, s>>>((uint4*)dst, seed, start, n, d_table, V);
   return 1;
 }
-static inline dim3 source_grid(uint64_t n, const BinParams& bp) {
-  if (!bp.seg_counts) return dim3(stream_grid(n, 256, 8));
-  int x = (g_sm_count * 8 + (int)bp.nseg - 1) / (int)bp.nseg;
-  return dim3(x < 1 ? 1 : x, bp.nseg);
-}
 int launch_hist(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* hist, cudaStream_t s) {
   if (!n) return 0;
-  DISPATCH_RB(rb, (k_hist<RB><<<source_grid(n, bp), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
+  DISPATCH_RB(rb, (k_hist<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, hist)));
   return 1;
 }
 int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* out_copy, uint32_t* out_dense,
@@ -1007,19 +1162,26 @@ int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint3
   }
   return 1;
 }
-uint32_t combine_region_slack(int rb) { return (uint32_t)(kCombineSmem / rb) + kCombineThreads + 64; }
-int launch_combine(int rb, const void* recs, uint64_t n, void* out, uint32_t region_cap, uint32_t* seg_counts,
-                   uint32_t* hll, int sm_count, cudaStream_t s) {
+uint32_t gtab_log_slots(int rb, uint64_t bytes) {
+  uint32_t l = 5;
+  while (l < 28 && ((uint64_t)rb << (l + 1)) <= bytes) l++;
+  return l;
+}
+int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
+                   int sm_count, cudaStream_t s) {
   if (!n) return 0;
   uint32_t entries = (uint32_t)(kCombineSmem / rb);
-  DISPATCH_RB(rb, (k_combine<RB><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, (uint4*)out,
-                                                                                region_cap, seg_counts, entries, hll)));
+  if (checked) {
+    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, gtab, glog, flags)));
+  } else {
+    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, gtab, glog, flags)));
+  }
   return 1;
 }
-int launch_agg_bins(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count, cudaStream_t s) {
-  int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
-  if (grid < 1) grid = 1;
-  DISPATCH_RB(rb, (k_agg_bins<RB><<<grid, kSortThreads, sort_smem_bytes(RB), s>>>(b, B, cap)));
+int launch_gtab_compact(int rb, const uint32_t* gtab, uint32_t glog, void* out, uint32_t* count, cudaStream_t s) {
+  const uint32_t slots = 1u << glog;
+  int grid = (int)std::min<uint32_t>((slots + 255) / 256, (uint32_t)g_sm_count * 8);
+  DISPATCH_RB(rb, (k_gtab_compact<RB><<<grid, 256, 0, s>>>(gtab, glog, (uint4*)out, count)));
   return 1;
 }
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,
@@ -1047,7 +1209,7 @@ int launch_sample_u64(const void* recs, uint64_t n, uint32_t nsample, uint32_t* 
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                    cudaStream_t s) {
   if (!n) return 0;
-  DISPATCH_RB(rb, (k_scatter<RB><<<source_grid(n, bp), 256, 0, s>>>((const uint4*)recs, n, bp, cursor, (uint4*)mid)));
+  DISPATCH_RB(rb, (k_scatter<RB><<<stream_grid(n, 256, 8), 256, 0, s>>>((const uint4*)recs, n, bp, cursor, (uint4*)mid)));
   return 1;
 }
 // level 1 (source -> coarse regions, possibly on peers) and level 2 (coarse regions -> fine bins) of the split
@@ -1082,9 +1244,7 @@ int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, c
   a.capacity = (uint32_t)std::min<uint64_t>(pl.sub_stride, 0xffffffffull);
   a.nbins = pl.C1;
   a.level = 1;
-  dim3 grid(ctas);
-  if (bp.seg_counts) grid = dim3((ctas + bp.nseg - 1) / bp.nseg, bp.nseg);
-  DISPATCH_RB(rb, (k_split_tma<RB><<<grid, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
+  DISPATCH_RB(rb, (k_split_tma<RB><<<ctas, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
   return 1;
 }
 int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s) {

@@ -24,11 +24,6 @@ struct BinParams {
   uint32_t world;        // 1 = single GPU (slot == p)
   uint32_t wshift;       // log2(world) when world is a power of two, else 0xffffffff
   uint32_t pbase[9];
-  // segmented source (the combiner's per-CTA output regions): blockIdx.y selects segment y =
-  // seg_counts[y] records at recs + y * seg_stride records.  seg_counts == nullptr: one range.
-  const uint32_t* seg_counts;
-  uint64_t seg_stride;
-  uint32_t nseg;
   uint32_t rep_shift;    // few, heavily hit bins: 2^rep_shift counter copies per bin (copy = CTA id),
                          // i.e. bin b owns the consecutive virtual bins [b << rep_shift, (b+1) << rep_shift)
 };
@@ -37,7 +32,6 @@ MRHBM_HD inline uint32_t partition_slot(const BinParams& bp, uint32_t pid) {
   return bp.world > 1 ? bp.pbase[pid % bp.world] + pid / bp.world : pid;
 }
 
-constexpr uint32_t kHllRegs = 2048;
 constexpr int kCapBytes = 32 * 1024;  // record bytes one CTA sorts in shared memory (2 CTAs per SM)
 inline uint32_t cap_records(int rb) { return (uint32_t)(kCapBytes / rb); }
 
@@ -106,22 +100,21 @@ int launch_exscan(const uint32_t* in, uint32_t n, uint32_t* out_excl, uint32_t* 
 int launch_sample_u64(const void* recs, uint64_t n, uint32_t nsample, uint32_t* hist256, cudaStream_t s);
 int launch_scatter(int rb, const void* recs, uint64_t n, const BinParams& bp, uint32_t* cursor, void* mid,
                    cudaStream_t s);
-// map-side combine of one committed range into out (appends; *out_count is the running total)
 // device-side tokeniser: word starts per 256-byte block, then (after an exclusive scan of the
 // block counts) one record per word; *flags gets ERRF_KEYLEN when a word exceeds the key slot
 int launch_tok_count(const unsigned char* text, uint64_t len, uint32_t* block_counts, cudaStream_t s);
 int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint32_t* block_off, void* recs,
                     uint32_t* flags, cudaStream_t s);
 inline uint64_t tok_blocks(uint64_t len) { return (len + 255) / 256; }
-// map-side combine of one committed range: CTA y appends to its own region out + y * region_cap
-// (records), seg_counts[y] is its running fill level (no global atomics on the append path)
-int launch_combine(int rb, const void* recs, uint64_t n, void* out, uint32_t region_cap, uint32_t* seg_counts,
-                   uint32_t* hll, int sm_count, cudaStream_t s);
-uint32_t combine_region_slack(int rb);  // worst-case extra records one launch adds to a region
-// duplicate-heavy streams: per bin, aggregate through a shared-memory hash table, then sort the
-// distinct keys (bins are sized by distinct keys, not by records)
-int launch_agg_bins(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count, cudaStream_t s);
-inline uint32_t agg_table_entries(int rb) { return (uint32_t)((kCapBytes + (kCapBytes / rb) * 8) / rb); }
+// map-side combine of one committed range into the global table gtab (2^glog record-sized entries, zeroed by
+// the caller); flags[0] |= ERRF_SKEW when the table is full, ERRF_OVERFLOW when a u32 sum would wrap (checked
+// mode only: unchecked adds are fire-and-forget and the caller verifies afterwards that pairs x flags[2], the
+// largest value seen, stays below 2^32)
+int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
+                   int sm_count, cudaStream_t s);
+// one record per non-empty table entry appended to out; *count (zeroed by the caller) += entries
+int launch_gtab_compact(int rb, const uint32_t* gtab, uint32_t glog, void* out, uint32_t* count, cudaStream_t s);
+uint32_t gtab_log_slots(int rb, uint64_t bytes);  // largest power of two of rb-byte entries within `bytes`
 // tot[b] = sum over s < world of all[s * stride + base + b], b < n; *nover += bins (of all `stride`
 // bins) whose global total exceeds cap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,

@@ -767,129 +767,6 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
   }
 }
 
-// Duplicate-heavy input (a combiner is declared): a bin holds many records but few distinct keys.
-// Stream the bin through an open-addressing table in shared memory (one slot per distinct key,
-// value word = 1 + running sum), then sort the distinct keys and write the run.  The table
-// lives in the rec2 + cnt region, which the sort only needs afterwards.
-template <int RB>
-__global__ void __launch_bounds__(kSortThreads, 2) k_agg_bins(ShuffleBuffers b, uint32_t B, uint32_t cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_bin, s_n, s_fail;
-  using R = Rec<RB>;
-  constexpr int W = R::kWords, KW = R::kKeyWords;
-  constexpr uint32_t T = (uint32_t)((kCapBytes + (kCapBytes / RB) * 8) / RB);  // table entries
-  constexpr uint32_t kLock = 0xffffffffu;
-  SortSmem sm = carve(smem_raw, RB);
-  uint32_t* tab = (uint32_t*)sm.rec2;
-  const uint32_t tid = threadIdx.x;
-  for (;;) {
-    if (tid == 0) {
-      s_bin = atomicAdd(b.counters + CNT_TICKET, 1u);
-      s_n = 0;
-      s_fail = 0;
-    }
-    for (uint32_t i = tid; i < T * W; i += blockDim.x) tab[i] = 0;
-    __syncthreads();
-    uint32_t bin = s_bin;
-    if (bin >= B) break;
-    uint64_t off = bin_start(b, bin);
-    uint32_t cnt = bin_count(b, bin);
-    if (cnt == 0) {
-      if (tid == 0) b.ucount[bin] = 0;
-      __syncthreads();
-      continue;
-    }
-    const uint32_t nsegs = b.stride ? 1u : b.nseg;  // optimistic layout: the bin is one contiguous run
-    for (uint32_t sgm = 0; sgm < nsegs; sgm++) {
-      uint32_t so = 0, sc = cnt;
-      const uint4* src = (const uint4*)b.src + off * R::kVec;
-      if (!b.stride) {
-        so = b.seg_off[sgm][(size_t)bin << b.rep_shift];
-        sc = b.seg_off[sgm][(size_t)(bin + 1) << b.rep_shift] - so;
-        src = (const uint4*)b.src + (b.seg_base[sgm] + so) * R::kVec;
-      }
-      for (uint32_t i = tid; i < sc; i += blockDim.x) {
-        uint32_t w[W];
-#pragma unroll
-        for (int v = 0; v < R::kVec; v++) {
-          uint4 x = ldg_stream(src + (size_t)i * R::kVec + v);
-          w[4 * v] = x.x;
-          w[4 * v + 1] = x.y;
-          w[4 * v + 2] = x.z;
-          w[4 * v + 3] = x.w;
-        }
-        uint64_t val = rec_value<RB>(w);
-        if (val >= 0xfffffff0ull) {
-          atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_OVERFLOW);
-          continue;
-        }
-        uint32_t v32 = (uint32_t)val;
-        uint32_t slot = (uint32_t)__umul64hi(mix64(word_hash<RB>(w)), (uint64_t)T);
-        bool done = false;
-#pragma unroll 1
-        for (int probe = 0; probe < 24 && !done; probe++) {
-          uint32_t* stp = tab + (size_t)KW * T + slot;  // word-major table, see k_combine
-          uint32_t st = *(volatile uint32_t*)stp;
-          if (st == 0) {
-            if (atomicCAS(stp, 0u, kLock) == 0u) {
-#pragma unroll
-              for (int k = 0; k < KW; k++) tab[(size_t)k * T + slot] = w[k];
-              __threadfence_block();
-              atomicExch(stp, v32 + 1u);
-              done = true;
-              break;
-            }
-            st = *(volatile uint32_t*)stp;  // somebody else claimed it: look again
-          }
-          if (st == kLock) {  // being filled: wait for its key (the owner finishes without blocking)
-            probe--;
-            continue;
-          }
-          bool eq = true;
-#pragma unroll
-          for (int k = 0; k < KW; k++) eq &= (((volatile uint32_t*)tab)[(size_t)k * T + slot] == w[k]);
-          if (eq) {
-            uint32_t old = atomicAdd(stp, v32);
-            if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_OVERFLOW);
-            done = true;
-            break;
-          }
-          slot = slot + 1 == T ? 0 : slot + 1;
-        }
-        if (!done) s_fail = 1;  // more distinct keys than the table takes: the host widens S
-      }
-    }
-    __syncthreads();
-    // distinct keys -> sm.rec as records {key, sum}
-    for (uint32_t e = tid; e < T; e += blockDim.x) {
-      uint32_t st = tab[(size_t)KW * T + e];
-      if (!st) continue;
-      uint32_t pos = atomicAdd(&s_n, 1u);
-      if (pos < cap) {
-        uint32_t* d = (uint32_t*)sm.rec + (size_t)pos * W;
-#pragma unroll
-        for (int k = 0; k < KW; k++) d[k] = tab[(size_t)k * T + e];
-        d[KW] = st - 1u;
-        if constexpr (R::kU64) d[3] = 0u;
-      }
-    }
-    __syncthreads();
-    uint32_t n = s_n;
-    bool bad = s_fail || n > cap;
-    __syncthreads();
-    if (bad) {
-      if (tid == 0) {
-        atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_SKEW);
-        b.ucount[bin] = 0;
-      }
-      continue;
-    }
-    ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
-    uint32_t g = process_loaded<RB, MODE_FINAL>(sm, n, out);
-    if (tid == 0) b.ucount[bin] = g;
-  }
-}
-
 // One CTA per oversized bin (hot keys): chunk-wise in-place reduce until the bin fits.
 template <int RB>
 __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, uint32_t cap) {

@@ -312,9 +312,9 @@ def test_second_shuffle_after_overflow_skips_the_optimistic_layout():
             check_vs_oracle_u64(ctx, keys, vals, 4)
 
 
-def test_combiner_two_level_split_feeds_the_aggregation():
-    """duplicate-heavy strings with enough distinct keys for > 1024 bins: combine -> two-level split in the
-    optimistic layout -> k_agg_bins (the config 3 path), against the oracle"""
+def test_combiner_with_many_distinct_keys():
+    """duplicate-heavy strings, 2^20 possible keys: shared-memory tables + the L2-resident global table collapse the
+    stream to about one record per distinct key before the partition / sort / reduce stages (the config 3 path)"""
     n, P = 6_000_000, 15
     table = synth.zipf_table(1 << 20)
     recs = O.gen_zipf_rec32(SEED, 0, n, table).view(mrhbm.record_dtype(mrhbm.KEY_STR, 27)).reshape(-1)
@@ -323,8 +323,9 @@ def test_combiner_two_level_split_feeds_the_aggregation():
         m.gen_zipf(SEED, 0, n, table)
         m.commit()
         ctx.shuffle()
-        st = ctx.stats()
-        assert st["attempts"] == 1 and st["bins"] > 1024 and st["ms_hist"] < 0.05, st
+        st, info = ctx.stats(), ctx.result_info()
+        assert st["attempts"] == 1 and st["ms_combine"] > 0 and st["ms_hist"] < 0.05, st
+        assert info.groups <= info.pairs_recv <= info.groups + info.groups // 50  # (a key may own two table entries)
         check_vs_oracle_str(ctx, recs, P, O.PART_FNV_LUA)
 
 
@@ -343,16 +344,23 @@ def test_properties_at_10_pow_7():
         assert ctx.result_info().sorted == 1
 
 
-@pytest.mark.parametrize("kind", ["zipf", "u64dup"])
+@pytest.mark.parametrize("kind", ["zipf", "zipfbig", "u64dup"])
 def test_map_side_combiner_keeps_the_result(kind):
     """combinerfn == reducefn (job.lua:92-96,198-202): the map-side combine changes nothing"""
     n, P = 1_500_000, 15
-    if kind == "zipf":
+    if kind in ("zipf", "zipfbig"):
         table = synth.zipf_table(1 << 16)
         recs = O.gen_zipf_rec32(SEED, 0, n, table).view(mrhbm.record_dtype(mrhbm.KEY_STR, 27)).reshape(-1)
+        if kind == "zipfbig":  # pairs x largest value >= 2^32: the combiner must switch to checked adds; zeros and
+            recs = recs.copy()  # values > 0xffff bypass the shared-memory tables
+            recs["val"] = np.random.default_rng(3).integers(0, 3000, n).astype(np.uint32)
+            recs["val"][::97] = 70000
         with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, combiner=True) as ctx:
             m = ctx.map_begin(1)
-            m.gen_zipf(SEED, 0, n, table)
+            if kind == "zipf":
+                m.gen_zipf(SEED, 0, n, table)
+            else:
+                m.emit_batch(recs)
             m.commit()
             ctx.shuffle()
             st = ctx.stats()
