@@ -1,22 +1,33 @@
 #!/usr/bin/env python3
 """bench.py -- key-value pairs/s through shuffle + sort + reduce (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload u64|zipf32] [--pairs M]
-  python bench.py --impl reference ...   # the reference-shaped CPU path (oracle/) on host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W]              # the driver's call
+  python bench.py --impl reference ...                             # the reference-shaped CPU path (oracle/) on host cores
+  python bench.py --workload zipf32|u64|u64big|wordcount ...       # one workload only
 
-One "step" = one pass of the hot path (hash-partition + sort + segmented reduce) over one batch
-of synthetic pairs.  `value` times the step with the batch already resident in HBM; `e2e` times
-the same step through the public C-ABI calls a user makes, from pinned HOST buffers
-(emit_batch -> commit -> shuffle -> result_copy), host<->device copies inside the timed region.
-Workloads:
-  u64    : config 2, 10^8 uniform u64 keys / u32 values, 16 B records, 1024 partitions (default)
-  zipf32 : config 3, Zipf(1.1) words <= 27 B, 32 B records, value 1, 15 partitions
-Inputs are far larger than the 126 MB L2, so no flush is needed between iterations.
+One "step" = one pass of the hot path (map-side combine where declared, hash-partition, sort, segmented reduce)
+over one batch of synthetic pairs.  The headline line is BASELINE.json's largest single-GPU
+configuration, the one the north-star's %HBM target is quoted on:
+
+  zipf32 (headline) config 3: 10^9 Zipf(1.1) word keys <= 27 B, 32 B records, value 1, 15 partitions, FNV-in-doubles
+                    partitioner, combiner = reducer (the reference's headline setup); under torchrun every rank brings
+                    10^9 pairs of a disjoint counter range (weak scaling; config 5 is this shape on 8 GPUs)
+and these ride along in the same JSON line under "configs" (skipped with --workload / --only-headline):
+  u64               config 2: 10^8 uniform u64 keys / u32 values, 16 B records, 1024 partitions (one GPU)
+  u64big            config 4: 10^9 uniform u64 keys in total over the N GPUs (strong scaling), 1024 partitions
+  wordcount         config 1: 197 x 10k-line Europarl-shaped text through server.loop() with the device tokeniser,
+                    against the oracle engine (4 worker threads) on the same text -- identical sorted count/word lines
+
+`value` times K steps with the batch already resident in HBM; `e2e` times the same work through the public calls a
+user makes, from HOST buffers, host<->device copies inside the timed region (word count: text -> device tokeniser
+-> shuffle -> result arrays; u64: records -> emit_batch -> shuffle -> result arrays).  Every block carries
+`parity_vs_oracle`: the device result compared IN FULL with the CPU oracle on the same stream (bit-exact keys,
+sums and partition boundaries; at N > 1 every rank checks the partitions it owns).  Inputs are far larger than the
+126 MB L2, so no flush is needed between iterations.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,18 +43,17 @@ UNIT = "pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="u64", choices=["u64", "zipf32"])
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: config size)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "zipf32", "u64", "u64big", "wordcount"])
+    ap.add_argument("--only-headline", action="store_true", help="skip the ride-along configs")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: the config's size)")
     ap.add_argument("--partitions", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-serial", action="store_true", help="one worker, no overlap between steps")
-    ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="pairs in the CPU sample (default: 10^7 for cpu_baseline = ~10 s on 4 threads; "
-                         "2*10^6 per step for --impl reference)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in one CPU sample (default 10^7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full comparison with the oracle")
     return ap.parse_args()
 
 
@@ -58,57 +68,71 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons through NVML, sampled every 2 ms while the timed region runs."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.sm, self.reasons, self.mx, self.stop_flag, self.t = index, [], set(), None, False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as N
+            N.nvmlInit()
+            self.N, self.h = N, N.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.N = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+    def _loop(self):
+        N = self.N
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.002)
+
+    def start(self):
+        if self.N is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.N is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": "NVML, 2 ms period, timed region only"}
 
 
-def workload_params(a):
-    if a.workload == "u64":
-        return dict(name="config2: 1e8 uniform u64 keys / u32 values, 16 B records", rb=16,
-                    pairs=a.pairs or 100_000_000, P=a.partitions or 1024)
-    return dict(name="config3: Zipf(1.1) string keys <=27 B, 32 B records, value 1", rb=32,
-                pairs=a.pairs or 1_000_000_000, P=a.partitions or 15)
+# ---------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------
+def workload(name, a, world):
+    from lua_mapreduce_b200 import mrhbm
+    if name == "zipf32":
+        n = a.pairs or 1_000_000_000
+        return dict(key="zipf32", rb=32, pairs=n, P=a.partitions or 15, kind=mrhbm.KEY_STR, part=mrhbm.PART_FNV_LUA,
+                    combiner=True, scaling="weak", dtype="u8",
+                    name=("config3: 1e9 Zipf(1.1) word keys <=27 B, 32 B records, value 1, combiner = reducer" if world == 1 else
+                          "config5 shape: Zipf(1.1) word keys <=27 B, 32 B records, value 1, combiner = reducer, 1e9 pairs per GPU "
+                          "(weak-scaled config 3; config 5 names 4e9 pairs on 8 GPUs)"))
+    if name == "u64":
+        n = a.pairs or 100_000_000
+        return dict(key="u64", rb=16, pairs=n, P=a.partitions or 1024, kind=mrhbm.KEY_U64, part=mrhbm.PART_MULHASH,
+                    combiner=False, scaling="weak", dtype="u64",
+                    name="config2: 1e8 uniform u64 keys / u32 values, 16 B records" + ("" if world == 1 else " per GPU"))
+    if name == "u64big":
+        total = (a.pairs * world) if a.pairs else 1_000_000_000
+        return dict(key="u64big", rb=16, pairs=total // world, P=a.partitions or 1024, kind=mrhbm.KEY_U64,
+                    part=mrhbm.PART_MULHASH, combiner=False, scaling="strong", dtype="u64",
+                    name="config4: 1e9 uniform u64 keys in total, 1024 partitions, exchange over NVLink (%d GPU%s)"
+                         % (world, "" if world == 1 else "s"))
+    raise ValueError(name)
 
 
 def host_u64_records(seed, start, n, out):
@@ -119,63 +143,409 @@ def host_u64_records(seed, start, n, out):
         b = min(n, a + step)
         i = np.arange(start + a, start + b, dtype=np.uint64)
         out["key"][a:b] = splitmix64_np(np.uint64(seed) + i)
-        out["val"][a:b] = (splitmix64_np(np.uint64(seed) + np.uint64(1 << 40) + i) >> np.uint64(32)).astype(np.uint32)
-        out["pad"][a:b] = 0
+        out["val"][a:b] = splitmix64_np(np.uint64(seed) + np.uint64(1 << 40) + i) >> np.uint64(32)
 
 
-def cpu_baseline(a, wp, table, threads, sample):
-    """Reference-shaped CPU path (oracle engine: emit table, sort, text spill, heap merge,
-    sum) on a bounded sample of the same stream.  kind = "port" (the reference is Lua+MongoDB
-    and cannot run in this image)."""
+def oracle_mod():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    from lua_mapreduce_b200 import synth
+    return O
+
+
+def cpu_sample(wl, table, threads, sample):
+    """Reference-shaped CPU path (oracle engine: emit table, combiner, sort, text spill, heap merge, sum) on a bounded
+    sample of the same stream, `threads` worker threads.  kind = "port": the reference is Lua + MongoDB and cannot run
+    in this image.  Word count: the sample is TEXT (App. B), cut into one map job per "file" and tokenised by the
+    WordCount mapfn, like the reference's own run."""
+    O = oracle_mod()
+    from lua_mapreduce_b200 import mrhbm, synth
     njobs = max(threads, 8)
-    per = max(1, sample // njobs)
-    if a.workload == "u64":
-        eng = O.Engine(O.PART_MULHASH, wp["P"], combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
-        ms, rs = O.run_synthetic(eng, 0, synth.SEED, 0, per, njobs, threads)
+    if wl["key"] == "zipf32":
+        text = mrhbm.synth_zipf_text(synth.SEED, 0, sample, table)
+        eng = O.Engine(O.PART_FNV_LUA, wl["P"], combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
+        ms, rs = O.run_text(eng, text, njobs, threads)
+        what = "text of %d words of the same stream (%.0f MB)" % (sample, text.nbytes / 1e6)
+        n = sample
     else:
-        eng = O.Engine(O.PART_FNV_LUA, wp["P"], combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
-        ms, rs = O.run_synthetic(eng, 1, synth.SEED, 0, per, njobs, threads, table)
-    n = per * njobs
+        per = max(1, sample // njobs)
+        eng = O.Engine(O.PART_MULHASH, wl["P"], combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
+        ms, rs = O.run_synthetic(eng, 0, synth.SEED, 0, per, njobs, threads)
+        n = per * njobs
+        what = "%d pairs of the same stream" % n
     eng.close()
     return {"value": n / (ms + rs), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d pairs of the same stream as %d map jobs on %d worker threads "
-                      "(map %.2f s + reduce %.2f s)" % (n, njobs, threads, ms, rs)}
+            "sample": "%s as %d map jobs on %d worker threads (map %.2f s + reduce %.2f s)" % (what, njobs, threads, ms, rs)}
+
+
+def config_block(wl, world):
+    return {"workload": wl["name"], "pairs_per_gpu": wl["pairs"], "partitions": wl["P"], "record_bytes": wl["rb"],
+            "combiner": bool(wl["combiner"]), "n_gpus": world,
+            "l2": "inputs (%.1f GB per GPU) >> 126 MB L2, no flush needed" % (wl["pairs"] * wl["rb"] / 1e9)}
 
 
 def run_reference(a):
-    wp = workload_params(a)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import mrhbm_loader
     mrhbm_loader.load()
     from lua_mapreduce_b200 import synth
-    table = synth.zipf_table() if a.workload == "zipf32" else None
-    threads = os.cpu_count() or 1
-    vals = []
-    sample = a.cpu_sample or 2_000_000
-    for _ in range(a.warmup and 1):
-        cpu_baseline(a, wp, table, threads, sample)
+    world = max(1, a.gpus)
+    wl = workload("zipf32" if a.workload in ("auto", "wordcount") else a.workload, a, world)
+    table = synth.zipf_table() if wl["key"] == "zipf32" else None
+    threads = min(os.cpu_count() or 1, 64)
+    sample = a.cpu_sample or 10_000_000
+    for _ in range(a.warmup):
+        cpu_sample(wl, table, threads, sample)
+    vals, last = [], None
     t0 = time.perf_counter()
-    last = None
     for _ in range(max(1, a.steps)):
-        last = cpu_baseline(a, wp, table, threads, sample)
+        last = cpu_sample(wl, table, threads, sample)
         vals.append(last["value"])
     dt = time.perf_counter() - t0
     v = float(np.mean(vals))
     last["value"] = v
+    cfg = config_block(wl, world)
+    cfg["seed"] = hex(synth.SEED)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": max(1, a.steps), "warmup": a.warmup and 1, "ms_per_step": 1e3 * dt / max(1, a.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (Lua numbers) / bytes",
-        "data": "synthetic", "config": {"workload": wp["name"], "partitions": wp["P"],
-                                        "note": "reference-shaped CPU restatement (oracle/), not Lua+MongoDB"},
-        "cpu_baseline": last,
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / max(1, a.steps), "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "f64 (Lua numbers) / bytes", "data": "synthetic", "config": cfg,
+        "note": "reference-shaped CPU restatement (oracle/, kind 'port'), not Lua + MongoDB; every step is a bounded sample "
+                "of the workload (cpu_baseline.sample), input generation included in the step's wall time but not in value",
+        "cpu_baseline": last, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the product arm
+# ---------------------------------------------------------------------------------------------------------------
+class Job:
+    """torch.distributed plumbing of one bench process (rendezvous, barrier, max over ranks)."""
+
+    def __init__(self, a):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        torch.cuda.set_device(self.local)
+        if a.gpus > 1 or self.world > 1:
+            import datetime
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local), timeout=datetime.timedelta(seconds=600))
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        if self.dist is None:
+            return bool(ok)
+        t = self.torch.tensor([0 if ok else 1], device="cuda", dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return int(t.item()) == 0
+
+    def sum_u64(self, arr):
+        """element-wise sum of a uint64 array over the ranks (values < 2^62)"""
+        if self.dist is None:
+            return arr
+        t = self.torch.from_numpy(arr.astype(np.int64)).cuda()
+        self.dist.all_reduce(t)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def make_ctx(job, wl):
+    from lua_mapreduce_b200 import mrhbm
+    ctx = mrhbm.Ctx(wl["kind"], wl["P"], wl["part"], max_key_bytes=27, device=job.local, reserve_pairs=wl["pairs"],
+                    combiner=wl["combiner"])
+    if job.world > 1:
+        uid = [ctx.comm_unique_id() if job.rank == 0 else None]
+        job.dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], job.rank, job.world)
+    return ctx
+
+
+def parity_vs_oracle(job, ctx, wl, table):
+    """The device result of the last shuffle against the CPU oracle on the SAME stream, compared in full:
+    every rank compares the partitions it owns (keys ascending per partition, sums, partition boundaries)."""
+    O = oracle_mod()
+    from lua_mapreduce_b200 import synth
+    n, P, world, rank = wl["pairs"], wl["P"], job.world, job.rank
+    threads = max(1, min(128, os.cpu_count() or 1) // world)
+    t0 = time.perf_counter()
+    info = ctx.result_info()
+    keys, sums, po = ctx.result_copy()
+    part = np.repeat(np.arange(P, dtype=np.int64), np.diff(po.astype(np.int64)))
+    if not info.sorted:  # a partition is several ascending runs on the device (hash sub-bins): merge = sort by key
+        order = np.lexsort((keys, part))
+        keys, sums = keys[order], sums[order]
+    if wl["key"] == "zipf32":
+        counts = O.zipf_counts(synth.SEED, rank * n, n, table, nthreads=threads)  # this rank's pairs ...
+        counts = job.sum_u64(counts)                                             # ... of the whole job
+        okeys, osums, opo = O.wordcount_from_counts(counts, O.PART_FNV_LUA, P, world, rank)
+        okeys = okeys.view("S28").reshape(-1)
+        pairs_checked = int(counts.sum())
+    else:
+        total = n * world
+        okeys, osums, opo = O.groupby_u64_stream(synth.SEED, 0, total, O.PART_MULHASH, P, world, rank, nthreads=threads,
+                                                 max_groups=int(info.groups) + 16)
+        pairs_checked = total
+    ok = bool(okeys.shape[0] == keys.shape[0] and (opo == po).all() and (okeys == keys).all() and (osums == sums).all())
+    ok_all = job.all_ok(ok)
+    return {"ok": ok_all, "compared": "all groups of all partitions, keys + sums + partition boundaries, bit-exact"
+                                      + ("" if world == 1 else " (every rank its own partitions)"),
+            "pairs": pairs_checked, "groups_this_rank": int(keys.shape[0]), "oracle": "oracle/mr_oracle.c "
+            + ("mro_zipf_counts + mro_wordcount_from_counts" if wl["key"] == "zipf32" else "mro_groupby_u64_stream"),
+            "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def resident_run(job, a, wl, table, sample_clocks):
+    """W warm-up + K timed shuffles of a batch resident in HBM; returns the block's measurements (+ ctx)."""
+    from lua_mapreduce_b200 import synth
+    n, rank, world = wl["pairs"], job.rank, job.world
+    ctx = make_ctx(job, wl)
+    m = ctx.map_begin("resident")
+    if wl["key"] == "zipf32":
+        m.gen_zipf(synth.SEED, rank * n, n, table)
+    else:
+        m.gen_u64(synth.SEED, rank * n, n)
+    m.commit()
+    W = max(3, a.warmup)
+    for _ in range(W):
+        ctx.shuffle()
+    sampler = ClockSampler(job.local) if sample_clocks and rank == 0 else None
+    job.barrier()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    agg, launches = {}, 0
+    for _ in range(a.steps):
+        ctx.shuffle()
+        st = ctx.stats()
+        launches += st["launches"]
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                agg[k] = agg.get(k, 0.0) + v
+    job.barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    dt = job.max(dt)
+    st = ctx.stats()
+    info = ctx.result_info()
+    dev_ms = {k: v / a.steps for k, v in agg.items()}
+    return dict(ctx=ctx, dt=dt, ms_step=1e3 * dt / a.steps, value=world * n / (dt / a.steps), dev_ms=dev_ms, stats=st, info=info,
+                launches=launches, clocks=clocks, warmup=W)
+
+
+def roofline_of(wl, r):
+    """SURVEY 8d accounting: every logical stage is charged one read of its input and one write of its output.
+    combine N R + N' R | hash-partition N' R + N' R | sort N' R + N' R | segmented reduce N' R + U R
+    (N = pairs in, N' = pairs that leave the combiner (= N without one), U = groups, R = record bytes)."""
+    peak, peak_src = peaks()
+    R, n, ms = wl["rb"], wl["pairs"], r["dev_ms"]
+    g = int(r["info"].groups)
+    n2 = int(r["info"].pairs_recv) if wl["combiner"] else n  # N' (on several GPUs: the pairs this rank reduced)
+    kernels = {}
+    if wl["combiner"]:
+        kernels["k_combine (+ k_gtab_compact)"] = (n * R + n2 * R, ms["ms_combine"])
+    if ms["ms_scatter"] > 0.02:
+        kernels["k_split_tma level 1"] = (n2 * R, ms["ms_plan"])
+        kernels["k_split_tma level 2" + (" (pulls regions from peers over NVLink)" if r.get("world", 1) > 1 else "")] = (n2 * R, ms["ms_scatter"])
+    else:
+        kernels["k_split_tma (single level)"] = (2 * n2 * R, ms["ms_plan"])
+    if ms["ms_hist"] > 0.05:
+        kernels["k_hist (exact layout, overhead)"] = (0, ms["ms_hist"])
+    kernels["k_sort_reduce"] = (3 * n2 * R + g * R, ms["ms_sort_reduce"] + ms["ms_bigbins"])
+    pipe_bytes = sum(v[0] for v in kernels.values())
+    dom = max((k for k in kernels if kernels[k][0]), key=lambda k: kernels[k][1])
+    ach = kernels[dom][0] / (kernels[dom][1] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(wl["key"], {}).get(dom.split(" ")[0])
+    per_k = {k: {"algorithmic_bytes": b, "ms": t, "achieved": (b / (t * 1e-3) / 1e9) if t > 0 else None,
+                 "frac": (b / (t * 1e-3) / 1e9 / peak) if t > 0 else None} for k, (b, t) in kernels.items()}
+    return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "peak_source": peak_src, "algorithmic_bytes": kernels[dom][0], "kernel_ms": kernels[dom][1],
+            "pipeline": {"algorithmic_bytes": pipe_bytes, "ms": ms["ms_total"],
+                         "achieved": pipe_bytes / (ms["ms_total"] * 1e-3) / 1e9,
+                         "frac": pipe_bytes / (ms["ms_total"] * 1e-3) / 1e9 / peak},
+            "stages_ms": ms,
+            "fusion_headroom": {"lower_bound_bytes": n * R + g * R,
+                                "frac_of_peak": (n * R + g * R) / (ms["ms_total"] * 1e-3) / 1e9 / peak},
+            "kernels": per_k}
+
+
+def e2e_run(job, a, wl, table, ctx, groups_resident):
+    """The same work through the public calls a user makes, from pinned HOST buffers; every step's H2D and D2H inside
+    the timed region.  Word count: text -> mrhbm_map_wordcount (device tokeniser) -> shuffle -> result arrays.
+    u64: records -> mrhbm_emit_batch -> shuffle -> result arrays."""
+    from lua_mapreduce_b200 import mrhbm, synth
+    n, rank, rb = wl["pairs"], job.rank, wl["rb"]
+    ctx.reset()
+    info_groups = int(groups_resident)
+    cap_out = info_groups + info_groups // 8 + 4096
+    out_keys = ctx.pinned_array(cap_out, np.uint64 if wl["kind"] == mrhbm.KEY_U64 else "S%d" % (rb - 4))
+    out_sums = ctx.pinned_array(cap_out, np.uint64)
+    if wl["key"] == "zipf32":
+        need = mrhbm.synth_zipf_text(synth.SEED, rank * n, min(n, 1 << 16), table).nbytes * (n / min(n, 1 << 16))
+        buf = ctx.pinned_array(int(need * 1.02) + (1 << 20), np.uint8)
+        text = mrhbm.synth_zipf_text(synth.SEED, rank * n, n, table, out=buf)
+        # chunks end at line ends (a word never straddles two calls)
+        chunk, cuts, p = 256 << 20, [0], 0
+        while p + chunk < text.nbytes:
+            q = p + chunk
+            q += int(np.argmax(text[q:q + 4096] == 10)) + 1
+            cuts.append(q)
+            p = q
+        cuts.append(text.nbytes)
+        h2d = int(text.nbytes)
+
+        def emit(mm):
+            for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                mm.wordcount(text.ctypes.data + c0, c1 - c0)
+        how = "text (%.2f GB) -> mrhbm_map_wordcount in %d chunks -> commit -> shuffle -> result_copy" % (h2d / 1e9, len(cuts) - 1)
+    else:
+        host = ctx.pinned_array(n, mrhbm.record_dtype(wl["kind"], 27))
+        host_u64_records(synth.SEED, rank * n, n, host)
+        chunk = 1 << 22
+        h2d = n * rb
+
+        def emit(mm):
+            for s0 in range(0, n, chunk):
+                mm.emit_batch_ptr(host.ctypes.data + s0 * rb, min(chunk, n - s0))
+        how = "records -> mrhbm_emit_batch (4 Mi-record chunks) -> commit -> shuffle -> result_copy"
+
+    def one_step():
+        ctx.reset()  # every step is a fresh task iteration (server.lua:386-404)
+        mm = ctx.map_begin("e2e")
+        emit(mm)
+        mm.commit()  # returns when the host buffers have been read
+        ctx.shuffle()
+        ctx.result_copy(out_keys, out_sums)
+
+    dts = []
+    for it in range(a.e2e_steps + 1):  # the first one (allocations, first touch of the result buffers) is not timed
+        job.barrier()
+        t1 = time.perf_counter()
+        one_step()
+        job.barrier()
+        if it:
+            dts.append(time.perf_counter() - t1)
+    t = job.max(float(np.mean(dts)))
+    g2 = int(ctx.result_info().groups)
+    return {"value": job.world * n / t, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": g2 * ((rb - 4 + 8) if wl["kind"] == mrhbm.KEY_STR else 16) + 8 * (wl["P"] + 1),
+            "ms_per_step": 1e3 * t, "steps": a.e2e_steps, "groups_match": bool(g2 == info_groups), "mode": "one worker per GPU: " + how}
+
+
+def measure(job, a, name, table, headline):
+    """one workload: resident steps, parity, roofline, e2e (and the CPU sample when asked for)"""
+    wl = workload(name, a, job.world)
+    r = resident_run(job, a, wl, table, sample_clocks=headline)
+    r["world"] = job.world
+    ctx = r["ctx"]
+    try:
+        cin, cout = ctx.checksum_input(), ctx.checksum_result()
+        props_ok = True
+        if job.dist is not None:
+            box = [None] * job.world
+            job.dist.all_gather_object(box, (cin, cout))
+            cin = [sum(b[0][i] for b in box) % 2**64 for i in range(4)]
+            cout = [sum(b[1][i] for b in box) % 2**64 for i in range(6)]
+        props_ok = cin[:3] == cout[:3] and cout[4:] == [0, 0]
+        parity = None if a.no_parity else parity_vs_oracle(job, ctx, wl, table)
+        roof = roofline_of(wl, r)
+        groups = int(cout[3]) if job.dist is not None else int(r["info"].groups)
+        e2e = e2e_run(job, a, wl, table, ctx, r["info"].groups) if a.e2e_steps > 0 else None
+    finally:
+        ctx.close()
+    st = r["stats"]
+    cfg = config_block(wl, job.world)
+    block = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_step"], "steps": a.steps, "warmup": r["warmup"],
+             "scaling": wl["scaling"], "dtype": wl["dtype"], "config": cfg, "gpu_launches": int(r["launches"]),
+             "device_ms_per_step": r["dev_ms"]["ms_total"], "roofline": roof, "e2e": e2e,
+             "run": {"bins": st["bins"], "sub_bins": st["sub_bins"], "big_bins": st["big_bins"], "attempts": st["attempts"],
+                     "groups": groups, "pairs_after_combine": int(r["info"].pairs_recv) if wl["combiner"] else None,
+                     "bytes_exchanged_per_gpu": int(st["bytes_exchanged"]), "parity_properties_ok": bool(props_ok)},
+             "parity_vs_oracle": parity, "clocks": r["clocks"]}
+    return wl, block
+
+
+def wordcount_config1(job, a, table):
+    """config 1: the reference's published benchmark shape (README.md:43-75): 197 files x 10,000 lines x 25 words of
+    Europarl-shaped text through taskfn -> device mapfn -> partitionfn -> reducefn -> finalfn of the mirrored
+    server:loop(), against the oracle engine with 4 worker threads on the same files."""
+    import tempfile
+    O = oracle_mod()
+    from lua_mapreduce_b200 import mrhbm, synth
+    from lua_mapreduce_b200.mapreduce import server as mserver
+    files, lines, words = 197, 10_000, 25
+    per_file = lines * words
+    d = tempfile.mkdtemp(prefix="mrhbm_cfg1_")
+    paths, nbytes = [], 0
+    for f in range(files):
+        t = mrhbm.synth_zipf_text(synth.SEED, f * per_file, per_file, table, words_per_line=words)
+        p = os.path.join(d, "europarl_%03d.txt" % f)
+        t.tofile(p)
+        paths.append(p)
+        nbytes += t.nbytes
+    total = files * per_file
+    WC = "lua_mapreduce_b200.mapreduce.examples.WordCount"
+    from lua_mapreduce_b200.mapreduce.examples import WordCount
+
+    def run_once():
+        WordCount.RESULT.clear()
+        s = mserver.new("hbm://local", "bench_cfg1_%d" % len(paths))
+        s.configure(dict(taskfn="lua_mapreduce_b200.mapreduce.examples.WordCountBig.taskfn", mapfn=WC + ".mapfn_device",
+                         partitionfn=WC + ".partitionfn", reducefn=WC + ".reducefn", combinerfn=WC + ".reducefn",
+                         finalfn=WC + ".finalfn", init_args={"dir": d}, storage="hbm",
+                         hbm={"max_key_bytes": 27, "device": job.local}))
+        s.loop()
+        s.board.ctx.close()
+        return dict(WordCount.RESULT)
+
+    run_once()  # warm-up (allocations, page cache)
+    t0 = time.perf_counter()
+    result = run_once()
+    gpu_s = time.perf_counter() - t0
+    eng = O.Engine(O.PART_FNV_LUA, 15, combiner=O.RED_SUM, reducer=O.RED_SUM, aci=True)
+    text = np.concatenate([np.fromfile(p, dtype=np.uint8) for p in paths])  # (every file ends at a line end: one map job each)
+    ms, rs = O.run_text(eng, text, files, 4)
+    cpu_s = ms + rs
+    want = {k: int(v[0]) for _, k, v in eng.final_pairs()}
+    eng.close()
+    got = {k: int(v) for k, v in result.items()}
+    lines_got = sorted("%d %s" % (c, k.decode("latin1")) for k, c in got.items())
+    lines_want = sorted("%d %s" % (c, k.decode("latin1")) for k, c in want.items())
+    import hashlib
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return {"config": {"workload": "config1: word count of 197 x 10k-line Europarl-shaped text (App. B), 25 words per line",
+                       "files": files, "words": total, "text_bytes": nbytes, "partitions": 15},
+            "value": total / gpu_s, "unit": UNIT, "seconds": gpu_s,
+            "path": "server.loop(): taskfn -> hbm_mapfn wordcount_file (file read + H2D + device tokeniser) -> shuffle -> finalfn",
+            "parity_vs_oracle": {"ok": lines_got == lines_want, "distinct_words": len(want), "tokens": int(sum(want.values())),
+                                 "compared": "sorted 'count word' lines (test.sh:11), oracle engine = text spill + heap merge",
+                                 "sha256": hashlib.sha256("\n".join(lines_got).encode("latin1")).hexdigest()},
+            "cpu_baseline": {"value": total / cpu_s, "unit": UNIT, "cores": 4, "kind": "port",
+                             "sample": "the whole config (197 map jobs, 15 reduce jobs) on 4 worker threads: map %.2f s + reduce %.2f s; "
+                                       "the reference's README reports 49 s with 4 Lua workers + mongod on its own corpus" % (ms, rs)}}
 
 
 def main():
@@ -186,271 +556,39 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w")
     if a.impl == "reference":
         return run_reference(a)
-    import torch
     import mrhbm_loader
     mrhbm_loader.load()
-    from lua_mapreduce_b200 import mrhbm, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.gpus > 1 or world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
-                                timeout=datetime.timedelta(seconds=180))
-    else:
-        dist = None
-    torch.cuda.set_device(local)
-    wp = workload_params(a)
-    n, P, rb = wp["pairs"], wp["P"], wp["rb"]
-    table = synth.zipf_table() if a.workload == "zipf32" else None
-    kind = mrhbm.KEY_U64 if a.workload == "u64" else mrhbm.KEY_STR
-    part = mrhbm.PART_MULHASH if a.workload == "u64" else mrhbm.PART_FNV_LUA
-    ctx = mrhbm.Ctx(kind, P, part, max_key_bytes=27, device=local, reserve_pairs=n,
-                    combiner=(a.workload == "zipf32"))  # the reference's headline run uses combiner = reducer
-    if world > 1:
-        uid = [ctx.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident input (weak scaling: every GPU owns n pairs of disjoint counters)
-    m = ctx.map_begin("resident")
-    if a.workload == "u64":
-        m.gen_u64(synth.SEED, rank * n, n)
-    else:
-        m.gen_zipf(synth.SEED, rank * n, n, table)
-    m.commit()
-    for _ in range(max(3, a.warmup)):
-        ctx.shuffle()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(3):  # every rank (the shuffle is collective): lets nvidia-smi attach before the timed region
-        ctx.shuffle()
-    barrier()
-    t0 = time.perf_counter()
-    agg = {}
-    launches = 0
-    for _ in range(a.steps):
-        ctx.shuffle()
-        st = ctx.stats()
-        launches += st["launches"]
-        for k, v in st.items():
-            if k.startswith("ms_"):
-                agg[k] = agg.get(k, 0.0) + v
-    barrier()
-    dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    st = ctx.stats()
-    groups = ctx.result_info().groups
-    cin, cout = ctx.checksum_input(), ctx.checksum_result()
-    if dist is not None:  # the sum is linear over the whole job: add the per-rank digests mod 2^64
-        box = [None] * world
-        dist.all_gather_object(box, (cin, cout))
-        cin = [sum(b[0][i] for b in box) % 2**64 for i in range(4)]
-        cout = [sum(b[1][i] for b in box) % 2**64 for i in range(6)]
-        groups = cout[3]
-    parity_ok = cin[:3] == cout[:3] and cout[4:] == [0, 0]
-    ms_step = 1e3 * dt / a.steps
-    dev_ms = {k: v / a.steps for k, v in agg.items()}
-    value = world * n / (dt / a.steps)
-
-    # ---- roofline (SURVEY 8d accounting: one read of its input + one write of its output per stage)
-    peak, peak_src = peaks()
-    R = rb
-    info = ctx.result_info()
-    g_local = info.groups
-    combined = a.workload == "zipf32"  # ctx runs the map-side combiner for this workload
-    n2 = info.pairs_recv if combined else n  # N' = pairs that survive the combiner
-    # per GPU, SURVEY 8d: combine N R + N' R, hash-partition N' R + N' R, sort N' R + N' R, reduce N' R + U R.
-    # The hash-partition stage is one kernel (k_scatter) or, in the default single-GPU layout, the two
-    # levels of k_split, each charged half of the stage.
-    sort_name = "k_agg_bins" if combined else "k_sort_reduce"
-    split = world == 1 and not combined and dev_ms["ms_plan"] > 0.2
-    kernels = {}
-    if combined:
-        kernels["k_combine"] = (n * R + n2 * R, dev_ms["ms_combine"])
-    if split:
-        kernels["k_split_level1"] = (n2 * R, dev_ms["ms_plan"])
-        kernels["k_split_level2"] = (n2 * R, dev_ms["ms_scatter"])
-    else:
-        kernels["k_scatter"] = (2 * n2 * R, dev_ms["ms_scatter"])
-        if dev_ms["ms_hist"] > 0.05:
-            kernels["k_hist(overhead)"] = (0, dev_ms["ms_hist"])
-    kernels[sort_name] = (3 * n2 * R + g_local * R, dev_ms["ms_sort_reduce"] + dev_ms["ms_bigbins"])
-    stage_bytes = {k: v[0] for k, v in kernels.items()}
-    k_ms = {k: v[1] for k, v in kernels.items()}
-    pipe_bytes = sum(stage_bytes.values())
-    dom = max((k for k in k_ms if stage_bytes[k]), key=k_ms.get)
-    ach = stage_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tp) and world == 1 and a.workload == "u64" and n == 100_000_000:
-        traffic = json.load(open(tp)).get(dom)
-    roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": stage_bytes[dom],
-        "kernel_ms": k_ms[dom],
-        "pipeline": {"algorithmic_bytes": pipe_bytes, "ms": dev_ms["ms_total"],
-                     "achieved": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9,
-                     "frac": pipe_bytes / (dev_ms["ms_total"] * 1e-3) / 1e9 / peak},
-        "stages_ms": dev_ms,
-        # SURVEY 8d "fusion headroom": the strict end-to-end lower bound N R + U R_out of a single-pass hash
-        # aggregation over the step's time -- reported beside the graded fraction, not instead of it
-        "fusion_headroom": {"lower_bound_bytes": n * R + g_local * R,
-                            "frac_of_peak": (n * R + g_local * R) / (dev_ms["ms_total"] * 1e-3) / 1e9 / peak},
-        "kernels": {k: {"algorithmic_bytes": stage_bytes[k], "ms": k_ms[k],
-                        "achieved": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9) if k_ms[k] > 0 else None,
-                        "frac": (stage_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak) if k_ms[k] > 0 else None}
-                    for k in kernels},
-    }
-
-    # ---- e2e through the public API from pinned host buffers
-    e2e = None
-    if a.e2e_steps > 0:
-        ctx.reset()
-        rec_dt = mrhbm.record_dtype(kind, 27)
-        host = ctx.pinned_array(n, rec_dt)
-        if a.workload == "u64":
-            host_u64_records(synth.SEED, rank * n, n, host)
-        else:  # read the device-generated stream back once (outside the timed region)
-            mm = ctx.map_begin("g")
-            mm.gen_zipf(synth.SEED, rank * n, n, table)
-            mm.commit()
-            ctx.pool_read(0, n, host)
-            ctx.reset()
-        # a rank may own slightly more groups than the resident run showed (multi-GPU ownership)
-        cap_out = min(n + n // 16, int(g_local) * 2) + 4096
-        out_keys = ctx.pinned_array(cap_out, np.uint64 if kind == mrhbm.KEY_U64 else "S%d" % (rb - 4))
-        out_sums = ctx.pinned_array(cap_out, np.uint64)
-        chunk = 1 << 22
-
-        def one_step(cx, ok_, os_, h2d=None, d2h=None):
-            """one task iteration through the public API: emit from pinned host memory, shuffle, read the result"""
-            cx.reset()  # every step is a fresh task iteration (server.lua:386-404); frees the pool
-            if h2d:
-                h2d.acquire()
-            try:
-                mm = cx.map_begin("e2e")
-                for s0 in range(0, n, chunk):
-                    c = min(chunk, n - s0)
-                    mm.emit_batch_ptr(host.ctypes.data + s0 * rb, c)
-                mm.commit()  # returns when the host buffers have been read
-            finally:
-                if h2d:
-                    h2d.release()
-            cx.shuffle()
-            if d2h:
-                d2h.acquire()
-            try:
-                cx.result_copy(ok_, os_)
-            finally:
-                if d2h:
-                    d2h.release()
-
-        def run_serial():
-            dts = []
-            for it in range(a.e2e_steps + 1):
-                barrier()
-                t1 = time.perf_counter()
-                one_step(ctx, out_keys, out_sums)
-                barrier()
-                if it:
-                    dts.append(time.perf_counter() - t1)
-            return float(np.mean(dts)), ctx.result_info().groups, "one worker: emit -> shuffle -> result_copy, serial"
-
-        def run_duplex():
-            # Two worker threads, each with its own ctx and output buffers (the reference runs several workers per
-            # host), alternate steps.  One lock per PCIe direction keeps a single H2D and a single D2H in flight, so
-            # the upload of step k+1 overlaps the download of step k (full-duplex PCIe) and the device work of both.
-            import threading
-            ctx2 = mrhbm.Ctx(kind, P, part, max_key_bytes=27, device=local, reserve_pairs=n, combiner=False)
-            try:
-                outs = [(out_keys, out_sums),
-                        (ctx2.pinned_array(cap_out, out_keys.dtype), ctx2.pinned_array(cap_out, np.uint64))]
-                ctxs = [ctx, ctx2]
-                for w in range(2):  # warm-up: allocations, first-touch of the pinned result buffers
-                    one_step(ctxs[w], *outs[w])
-                h2d, d2h = threading.Lock(), threading.Lock()
-                total_steps = 2 * a.e2e_steps
-                errors = []
-
-                def work(w):
-                    try:
-                        torch.cuda.set_device(local)
-                        for _ in range(w, total_steps, 2):
-                            one_step(ctxs[w], *outs[w], h2d=h2d, d2h=d2h)
-                    except BaseException as e:  # noqa: surfaced below
-                        errors.append(e)
-
-                barrier()
-                t1 = time.perf_counter()
-                th = [threading.Thread(target=work, args=(w,), daemon=True) for w in range(2)]
-                for t in th:
-                    t.start()
-                for t in th:
-                    t.join()
-                barrier()
-                t_step = (time.perf_counter() - t1) / total_steps
-                if errors:
-                    raise errors[0]
-                g = ctx.result_info().groups
-                if ctx2.result_info().groups != g:
-                    raise RuntimeError("the two workers disagree on the number of groups")
-            finally:
-                ctx2.close()
-            return t_step, g, ("two worker threads x own ctx alternate steps; the H2D of one step overlaps the D2H of "
-                               "the previous one (full-duplex PCIe); %d steps timed as one region" % total_steps)
-
-        workers = 2 if (world == 1 and n * rb <= 4_000_000_000 and not a.e2e_serial) else 1
-        if workers == 2:
-            try:
-                e2e_t, g2, mode = run_duplex()
-            except Exception as ex:  # keep the bench line: fall back to the serial measurement and say so
-                sys.stderr.write("e2e: two-worker run failed (%r); falling back to the serial run\n" % (ex,))
-                workers = 1
-        if workers == 1:
-            e2e_t, g2, mode = run_serial()
-        if dist is not None:
-            t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_t = float(t.item())
-        e2e = {"value": world * n / e2e_t, "unit": UNIT, "h2d_bytes_per_step": n * rb,
-               "d2h_bytes_per_step": int(g2) * (rb - 4 + 8 if kind == mrhbm.KEY_STR else 16) + 8 * (P + 1),
-               "ms_per_step": 1e3 * e2e_t, "steps": a.e2e_steps * workers, "groups_match": bool(g2 == g_local),
-               "mode": mode}
-
+    from lua_mapreduce_b200 import synth
+    job = Job(a)
+    table = synth.zipf_table()
+    head = "zipf32" if a.workload in ("auto", "wordcount") else a.workload
+    extras = []
+    if a.workload == "auto" and not a.only_headline:
+        extras = (["u64", "u64big"] if job.world == 1 else ["u64big"])
+    wl, line = measure(job, a, head, table, headline=True)
+    configs = {}
+    for name in extras:
+        _, blk = measure(job, a, name, table, headline=False)
+        configs[{"u64": "config2_u64_1e8", "u64big": "config4_u64_1e9_total"}[name]] = blk
+    if (a.workload == "auto" and not a.only_headline and job.world == 1) or a.workload == "wordcount":
+        if job.rank == 0:
+            configs["config1_wordcount_197x10k"] = wordcount_config1(job, a, table)
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_baseline(a, wp, table, min(4, os.cpu_count() or 1), a.cpu_sample or 10_000_000)
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": max(3, a.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64" if a.workload == "u64" else "u8", "data": "synthetic",
-            "config": {"workload": wp["name"], "pairs_per_gpu": n, "partitions": P, "record_bytes": rb,
-                       "seed": hex(synth.SEED), "l2": "inputs (%.1f GB) >> 126 MB L2, no flush needed" % (n * rb / 1e9),
-                       "bins": st["bins"], "sub_bins": st["sub_bins"], "big_bins": st["big_bins"],
-                       "groups": int(groups), "pairs_after_combine": int(n2) if combined else None,
-                       "parity_properties_ok": bool(parity_ok)},
-            "gpu_launches": int(launches), "device_ms_per_step": dev_ms["ms_total"],
-            "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-        }))
-    ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    if job.rank == 0 and job.world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_sample(wl, table, min(4, os.cpu_count() or 1), a.cpu_sample or 10_000_000)
+    if job.rank == 0:
+        cfg = line.pop("config")
+        cfg["seed"] = hex(synth.SEED)
+        out = {"metric": METRIC, "value": line.pop("value"), "unit": UNIT, "n_gpus": job.world, "steps": a.steps,
+               "warmup": line.pop("warmup"), "ms_per_step": line.pop("ms_per_step"), "higher_is_better": True,
+               "scaling": line.pop("scaling"), "vs_baseline": None, "dtype": line.pop("dtype"), "data": "synthetic", "config": cfg}
+        line.pop("unit")
+        line.pop("steps")
+        out.update(line)
+        out["cpu_baseline"] = cpu
+        out["configs"] = configs
+        print(json.dumps(out))
+    job.close()
 
 
 if __name__ == "__main__":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MRHBM_ABI_VERSION 1
+#define MRHBM_ABI_VERSION 2
 
 enum { /* error codes */
   MRHBM_OK = 0,
@@ -86,7 +86,7 @@ typedef struct mrhbm_config {
 #define MRHBM_F_NO_OPTIMISTIC 4u /* always run the exact two-pass (histogram) partition layout */
 
 /* record layouts (little endian) moved by emit_batch / gen / result_copy:
- *   U64 : { uint64_t key; uint32_t value; uint32_t zero; }              16 B
+ *   U64 : { uint64_t key; uint64_t value; }                             16 B
  *   STR : { uint8_t key[RB-4] zero padded, no NUL inside; uint32_t value; }  RB = 32/64/128 */
 uint32_t mrhbm_record_bytes(const mrhbm_ctx *);
 
@@ -104,7 +104,7 @@ void mrhbm_host_free(mrhbm_ctx *, void *);
 int mrhbm_map_begin(mrhbm_ctx *, const char *map_job_id, mrhbm_map **out);
 /* key bytes are copied before return (Lua strings may be collected) */
 int mrhbm_emit_str(mrhbm_map *, const void *key, size_t klen, uint32_t value);
-int mrhbm_emit_u64(mrhbm_map *, uint64_t key, uint32_t value);
+int mrhbm_emit_u64(mrhbm_map *, uint64_t key, uint64_t value); /* value < 2^53 keeps Lua-number sums exact */
 /* n records in the ctx layout.  Pageable memory is consumed before return; memory from
  * mrhbm_host_alloc() is read asynchronously and must stay untouched until commit/abort. */
 int mrhbm_emit_batch(mrhbm_map *, const void *records, size_t n);
@@ -122,6 +122,12 @@ int mrhbm_map_gen_zipf(mrhbm_map *, uint64_t seed, uint64_t start, uint64_t n,
  * isspace (' ' \t \n \v \f \r), i.e. Lua's "[^%s]+".  A word that does not fit the ctx record
  * class fails with MRHBM_E_KEY and emits nothing.  *words (optional) receives the token count. */
 int mrhbm_map_wordcount(mrhbm_map *, const void *text, size_t len, uint64_t *words);
+/* host-side generator of the synthetic word-count text of SURVEY App. B (bench + tests; needs no ctx):
+ * words first .. first+n-1 of the Zipf(table) word stream, one space between words, '\n' after every
+ * words_per_line-th word.  *len receives the bytes the text needs; MRHBM_E_INVAL (nothing usable written) if
+ * that exceeds cap.  Call with cap = 0 to size the buffer. */
+int mrhbm_synth_zipf_text(uint64_t seed, uint64_t first, uint64_t n, uint32_t words_per_line,
+                          const uint64_t *table, uint64_t V, void *out, size_t cap, size_t *len, int threads);
 /* copies n committed pairs starting at pair index `first` (commit order) back to host
  * memory in the record layout (bench + tests: checks the device generators) */
 int mrhbm_pool_read(mrhbm_ctx *, uint64_t first, uint64_t n, void *host_out);

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mrhbm.h"
@@ -398,6 +399,7 @@ int mrhbm_init(const mrhbm_config* cfg, mrhbm_ctx** out) {
   CU(c, cudaMalloc((void**)&c->d_sample, 256 * sizeof(uint32_t)));
   CU(c, cudaHostAlloc((void**)&c->h_sample, 256 * sizeof(uint32_t), cudaHostAllocDefault));
   if (const char* e = getenv("MRHBM_TUNE")) c->tune = (uint32_t)strtoul(e, nullptr, 0);  // measurement hooks, read once
+  kernels_set_tune(c->tune);
   if (cfg->reserve_pairs) {
     uint64_t off;
     int rc = pool_reserve(c, cfg->reserve_pairs, &off);
@@ -486,7 +488,7 @@ int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
   return MRHBM_OK;
 }
 
-int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint32_t value) {
+int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint64_t value) {
   if (!m) return MRHBM_E_INVAL;
   mrhbm_ctx* c = m->ctx;
   Entry g(c);
@@ -494,10 +496,8 @@ int mrhbm_emit_u64(mrhbm_map* m, uint64_t key, uint32_t value) {
   unsigned char* slot;
   int rc = stage_slot(m, &slot);
   if (rc) return rc;
-  uint32_t zero = 0;
   memcpy(slot, &key, 8);
-  memcpy(slot + 8, &value, 4);
-  memcpy(slot + 12, &zero, 4);
+  memcpy(slot + 8, &value, 8);
   return MRHBM_OK;
 }
 
@@ -635,6 +635,82 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
   }
   if (rc) return rc;
   if (words) *words = total;
+  return MRHBM_OK;
+}
+
+// ---- synthetic word-count text, host side: the input of the end-to-end word-count measurements
+namespace {
+inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+inline int synth_rank_to_key(uint64_t rank, char* out) {  // bijective base 26 prefix + hashed upper-case suffix
+  char tmp[16];
+  int n = 0, o = 0;
+  for (uint64_t r = rank; r > 0; r /= 26) {
+    r -= 1;
+    tmp[n++] = (char)('a' + (r % 26));
+  }
+  while (n > 0) out[o++] = tmp[--n];
+  const uint64_t h = splitmix64(rank ^ 0xA5A5A5A5A5A5A5A5ull);
+  unsigned l = (unsigned)(h % 8);
+  if (((h >> 8) % 64) == 0) l = 8 + (unsigned)((h >> 16) % 15);
+  for (unsigned j = 0; j < l; j++) out[o++] = (char)('A' + (splitmix64(h + j) % 26));
+  return o;
+}
+inline uint64_t synth_zipf_rank(const uint64_t* T, uint64_t V, uint64_t u) {
+  uint64_t lo = 0, hi = V;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (T[mid] < u) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo + 1 > V ? V : lo + 1;
+}
+}  // namespace
+
+int mrhbm_synth_zipf_text(uint64_t seed, uint64_t first, uint64_t n, uint32_t words_per_line, const uint64_t* table,
+                          uint64_t V, void* out, size_t cap, size_t* len, int threads) {
+  if (!table || !V || !len || !words_per_line || (!out && cap)) return MRHBM_E_INVAL;
+  threads = std::max(1, std::min(threads, 256));
+  const uint64_t lines = (n + words_per_line - 1) / words_per_line;
+  std::vector<uint64_t> bytes((size_t)threads + 1, 0);
+  auto span = [&](int t, uint64_t* l0, uint64_t* l1) {
+    *l0 = lines / threads * t;
+    *l1 = t + 1 == threads ? lines : lines / threads * (t + 1);
+  };
+  auto run = [&](int t, char* dst) -> uint64_t {  // dst == nullptr: only measure
+    uint64_t l0, l1, total = 0;
+    span(t, &l0, &l1);
+    char key[32];
+    for (uint64_t l = l0; l < l1; l++) {
+      const uint64_t w0 = l * words_per_line, w1 = std::min<uint64_t>(n, w0 + words_per_line);
+      for (uint64_t w = w0; w < w1; w++) {
+        const uint64_t u = splitmix64(seed + (1ull << 41) + first + w);
+        const int kl = synth_rank_to_key(synth_zipf_rank(table, V, u), key);
+        if (dst) {
+          memcpy(dst + total, key, (size_t)kl);
+          dst[total + kl] = w + 1 == w1 ? '\n' : ' ';
+        }
+        total += (uint64_t)kl + 1;
+      }
+    }
+    return total;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back([&, t] { bytes[(size_t)t + 1] = run(t, nullptr); });
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < threads; t++) bytes[(size_t)t + 1] += bytes[(size_t)t];
+  *len = (size_t)bytes[(size_t)threads];
+  if (*len > cap) return MRHBM_E_INVAL;
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back([&, t] { run(t, (char*)out + bytes[(size_t)t]); });
+  for (auto& x : th) x.join();
   return MRHBM_OK;
 }
 

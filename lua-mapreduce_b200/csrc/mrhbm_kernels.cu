@@ -18,6 +18,7 @@
 namespace mrhbm {
 
 static int g_sm_count = 148;
+static uint32_t g_tune = 0;  // MRHBM_TUNE measurement hooks (set once by kernels_set_tune)
 
 // ============================================================================
 // synthetic device-side mapfn
@@ -394,8 +395,10 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
         uint32_t dest;
         const uint32_t fine = bin_of<RB>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr, &dest);
         if (a.level == 1) {
-          const uint32_t d = a.ndest > 1 ? dest : 0u;
-          sub[k] = s_rbase[d] + ((fine - s_fbase[d]) >> a.logF);
+          if (a.ndest > 1)
+            sub[k] = s_rbase[dest] + ((fine - s_fbase[dest]) >> a.logF);
+          else
+            sub[k] = fine >> a.logF;
         } else {
           sub[k] = (fine - fine_base) & (a.F - 1u);
         }
@@ -642,28 +645,74 @@ __device__ __forceinline__ uint32_t slot_hash(const uint32_t* w) {
   h *= 0xC2B2AE35u;
   return h ^ (h >> 13);
 }
-__device__ __forceinline__ uint32_t ldv_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// L2 residency: the global table (64 MB) only stays in the 126 MB L2 if the 32 GB of pairs streaming through the
+// same L2 do not push it out (ncu, before: L2 hit rate 38 %, the table walk waiting ~10 us per round).  The pair
+// stream is read with an evict_first policy, every table access carries evict_last.  Table reads are relaxed
+// gpu-scope loads (L2 is the point of coherence; `volatile` would compile to system-scope loads).
+struct L2Policy {
+  uint64_t stream, keep;
+};
+__device__ __forceinline__ L2Policy l2_policies() {
+  L2Policy p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  return p;
 }
-__device__ __forceinline__ unsigned long long ldv_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint4 ldv_v4(const uint4* p) {
+__device__ __forceinline__ uint4 ldg_stream_hint(const uint4* p, uint64_t pol) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
   return v;
+}
+__device__ __forceinline__ uint32_t ldv_u32(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ldv_u64(const unsigned long long* p, uint64_t pol) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldv_v4(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stv_v4(uint4* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(pol)
+               : "memory");
 }
 
-__device__ __forceinline__ void stv_v4(uint4* p, const uint4& v) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+template <int RB>
+__device__ __forceinline__ void load_rec_hint(const uint4* p, uint32_t* w, uint64_t pol) {
+#pragma unroll
+  for (int v = 0; v < Rec<RB>::kVec; v++) {
+    uint4 x = ldg_stream_hint(p + v, pol);
+    w[4 * v + 0] = x.x;
+    w[4 * v + 1] = x.y;
+    w[4 * v + 2] = x.z;
+    w[4 * v + 3] = x.w;
+  }
 }
 
 // adds (key of w, v) to the global table.  Entry = one record slot: strings {key words, u32 state}, state =
 // 0 empty / kCombineLock being written / sum + 1; u64 keys {u64 key, u64 state} with the same encoding.
+// WARP-COLLECTIVE: all 32 lanes call it (active = this lane has a pair) and walk the probe sequence together --
+// lanes that are done idle inside the loop instead of leaving it, because fragments of a warp that left a
+// data-dependent loop at different trips do not reconverge and every fragment would run the walk, a chain of
+// L2 round trips, on its own.
 // CHECKED: use the returned old value to catch a u32 sum about to wrap (otherwise the add is fire-and-forget
 // and the caller has bounded the sums: pairs x largest value < 2^32).
 // Entries of 16 / 32 bytes are read with ONE round of independent 16-byte loads (state included).  Such a
@@ -671,8 +720,8 @@ __device__ __forceinline__ void stv_v4(uint4* p, const uint4& v) {
 // like a match for a key whose leading 16 bytes are all zero, so those keys take the two-step path (state,
 // then key) that the larger record classes always take.
 template <int RB, bool CHECKED>
-__device__ __forceinline__ void gtab_add(uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint64_t v, uint32_t h,
-                                         uint32_t* __restrict__ flags) {
+__device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint64_t v,
+                                         uint32_t h, uint32_t* __restrict__ flags, uint64_t pol) {
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
   uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
@@ -681,192 +730,215 @@ __device__ __forceinline__ void gtab_add(uint32_t* __restrict__ gtab, uint32_t g
   g ^= g >> 15;
   const uint32_t mask = (1u << glog) - 1u;
   uint32_t slot = g >> (32 - glog);
+  bool done = !active;
   if constexpr (R::kU64) {
     const unsigned long long key = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32), lock = ~0ull;
 #pragma unroll 1
     for (int probe = 0; probe < kGtabMaxProbes; probe++) {
-      unsigned long long* e = (unsigned long long*)gtab + 2 * (size_t)slot;
-      unsigned long long st, k;
-      if (key != 0) {  // one 16-byte load: key and state
-        const uint4 x = ldv_v4((const uint4*)e);
-        k = (unsigned long long)x.x | ((unsigned long long)x.y << 32);
-        st = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
-      } else {
-        st = ldv_u64(e + 1);
-        k = 0;
-      }
-      if (st == 0) {
-        const unsigned long long old = atomicCAS(e + 1, 0ull, lock);
-        if (old == 0) {
-          *(volatile unsigned long long*)e = key;
-          __threadfence();
-          atomicExch(e + 1, v + 1ull);
-          return;
+      if (__all_sync(0xffffffffu, done)) break;
+      if (!done) {
+        unsigned long long* e = (unsigned long long*)gtab + 2 * (size_t)slot;
+        unsigned long long st, k;
+        {  // one 16-byte load: key and state (issued before anything looks at the record, which may still be in flight)
+          const uint4 x = ldv_v4((const uint4*)e, pol);
+          k = (unsigned long long)x.x | ((unsigned long long)x.y << 32);
+          st = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
         }
-        st = old;
+        if (st == 0) {
+          const unsigned long long old = atomicCAS(e + 1, 0ull, lock);
+          if (old == 0) {
+            *(volatile unsigned long long*)e = key;
+            __threadfence();
+            atomicExch(e + 1, v + 1ull);
+            done = true;
+          }
+          st = old;
+        }
+        if (!done) {
+          if (st == lock || key == 0) {  // published meanwhile (or the zero key): read the key after the state
+            while (st == lock) st = ldv_u64(e + 1, pol);
+            k = ldv_u64(e, pol);
+          }
+          if (k == key) {
+            if (v) red_add_u64(e + 1, (unsigned long long)v, pol);
+            done = true;
+          }
+        }
+        slot = (slot + 1) & mask;
       }
-      if (st == lock || key == 0) {  // published meanwhile (or the zero key): read the key after the state
-        while (st == lock) st = ldv_u64(e + 1);
-        k = ldv_u64(e);
-      }
-      if (k == key) {
-        if (v) atomicAdd(e + 1, (unsigned long long)v);
-        return;
-      }
-      slot = (slot + 1) & mask;
     }
   } else {
-    if (v >= 0xfffffff0ull) {
+    if (!done && v >= 0xfffffff0ull) {
       atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
-      return;
+      done = true;
     }
     const uint32_t v32 = (uint32_t)v;
     const bool snapshot_ok = RB == 32 && (w[0] | w[1] | w[2] | w[3]) != 0;
 #pragma unroll 1
     for (int probe = 0; probe < kGtabMaxProbes; probe++) {
-      uint32_t* e = gtab + (size_t)slot * W;
-      uint4 x[R::kVec];
-      uint32_t st;
-      if (snapshot_ok) {
+      if (__all_sync(0xffffffffu, done)) break;
+      if (!done) {
+        uint32_t* e = gtab + (size_t)slot * W;
+        uint4 x[R::kVec];
+        uint32_t st;
+        if (RB == 32) {  // (issued before anything looks at w: the record itself may still be in flight)
 #pragma unroll
-        for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i);
-        st = x[R::kVec - 1].w;
-      } else {
-        st = ldv_u32(e + KW);
-      }
-      if (st == 0) {
-        const uint32_t old = atomicCAS(e + KW, 0u, kCombineLock);
-        if (old == 0) {
-#pragma unroll
-          for (int i = 0; i < R::kVec; i++)  // the last vector rewrites the lock word with itself
-            stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]));
-          __threadfence();
-          atomicExch(e + KW, v32 + 1u);
-          return;
+          for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i, pol);
+          st = x[R::kVec - 1].w;
+        } else {
+          st = ldv_u32(e + KW, pol);
         }
-        st = old;
-      }
-      if (st == kCombineLock || !snapshot_ok) {  // read the key after the (published) state
-        while (st == kCombineLock) st = ldv_u32(e + KW);
+        if (st == 0) {
+          const uint32_t old = atomicCAS(e + KW, 0u, kCombineLock);
+          if (old == 0) {
 #pragma unroll
-        for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i);
-      }
-      bool eq = true;
+            for (int i = 0; i < R::kVec; i++)  // the last vector rewrites the lock word with itself
+              stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]), pol);
+            __threadfence();
+            atomicExch(e + KW, v32 + 1u);
+            done = true;
+          }
+          st = old;
+        }
+        if (!done) {
+          if (st == kCombineLock || !snapshot_ok) {  // read the key after the (published) state
+            while (st == kCombineLock) st = ldv_u32(e + KW, pol);
 #pragma unroll
-      for (int i = 0; i < R::kVec; i++)
-        eq = eq && x[i].x == w[4 * i] && x[i].y == w[4 * i + 1] && x[i].z == w[4 * i + 2] && (4 * i + 3 == KW || x[i].w == w[4 * i + 3]);
-      if (eq) {
-        if (v32) {
-          if (CHECKED) {
-            const uint32_t old = atomicAdd(e + KW, v32);
-            if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
-          } else {
-            atomicAdd(e + KW, v32);
+            for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i, pol);
+          }
+          bool eq = true;
+#pragma unroll
+          for (int i = 0; i < R::kVec; i++)
+            eq = eq && x[i].x == w[4 * i] && x[i].y == w[4 * i + 1] && x[i].z == w[4 * i + 2] && (4 * i + 3 == KW || x[i].w == w[4 * i + 3]);
+          if (eq) {
+            if (v32) {
+              if (CHECKED) {
+                const uint32_t old = atomicAdd(e + KW, v32);
+                if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+              } else {
+                red_add_u32(e + KW, v32, pol);
+              }
+            }
+            done = true;
           }
         }
-        return;
+        slot = (slot + 1) & mask;
       }
-      slot = (slot + 1) & mask;
     }
   }
-  atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
+  if (!done) atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
 }
 
-// flags[0] |= ERRF_*, flags[2] = max over the values seen (saturated to u32)
+// flags[0] |= ERRF_*, flags[2] = max over the values seen (saturated to u32).
+// vcap: largest value the shared table accepts -- chosen by the host so that one CTA's sum of such values cannot
+// wrap 32 bits (pairs per CTA x vcap < 2^32), which keeps saturation tests out of the per-pair path.
 template <int RB, bool CHECKED>
 __global__ void __launch_bounds__(kCombineThreads, 1)
-    k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t entries, uint32_t* __restrict__ gtab, uint32_t glog,
-              uint32_t* __restrict__ flags) {
+    k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t entries, uint32_t vcap, uint32_t* __restrict__ gtab,
+              uint32_t glog, uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
-  // shared table, WORD-MAJOR: word k of entry e at tab[k * entries + e] (k = KW: 0 empty, lock, else the u32 partial
-  // sum), so that 32 lanes probing 32 random entries hit 32 random banks instead of the four a record stride allows
-  uint32_t* tab = (uint32_t*)smem_raw;
-  uint32_t* state = tab + (size_t)KW * entries;
+  constexpr int KC = KW < 3 ? KW : 3;  // key words a hit verifies at once (keys < 12 bytes end inside them)
+  // Shared table, ARRAY PER FIELD (32 lanes probing 32 random entries hit 32 random banks, not the four a record
+  // stride allows): tag[e] = 0 empty / 1 being written / the key's 32-bit hash with bit 1 set; val[e] = u32 partial
+  // sum; key[k][e] = key word k.  A probe reads two neighbouring tags; only a tag hit touches the key words.
+  uint32_t* tag = (uint32_t*)smem_raw;
+  uint32_t* val = tag + entries;
+  uint32_t* key = val + entries;
   // pairs that found no place in the shared table wait in a per-warp queue (record indices) until 32 of them are
   // there: the global-table walk, a chain of L2 round trips, then runs with all lanes busy instead of the ~30 %
   // that miss in one batch
-  __shared__ uint32_t queue[kCombineThreads / 32][64];
+  __shared__ uint2 queue[kCombineThreads / 32][64];  // (record index, key hash): the walk starts without the record
   const uint32_t tid = threadIdx.x, lane = tid & 31;
-  uint32_t* q = queue[tid >> 5];
+  const L2Policy pol = l2_policies();
+  uint2* q = queue[tid >> 5];
   uint32_t qn = 0, vmax = 0;
-  for (uint32_t i = tid; i < entries * (KW + 1); i += blockDim.x) tab[i] = 0;
+  for (uint32_t i = tid; i < entries * (KW + 2); i += blockDim.x) tag[i] = 0;
   __syncthreads();
-  auto to_gtab = [&](uint32_t idx) {
+  auto to_gtab = [&](bool active, uint2 qe) {
     uint32_t w[W];
-    load_rec<RB>(recs + (size_t)idx * R::kVec, w);
-    gtab_add<RB, CHECKED>(gtab, glog, w, rec_value<RB>(w), slot_hash<RB>(w), flags);
+#pragma unroll
+    for (int k = 0; k < W; k++) w[k] = 0;
+    if (active) load_rec_hint<RB>(recs + (size_t)qe.x * R::kVec, w, pol.stream);  // (an L2 hit, in flight with the first probe)
+    gtab_add<RB, CHECKED>(active, gtab, glog, w, rec_value<RB>(w), qe.y, flags, pol.keep);
   };
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t n_round = (n + 31) / 32 * 32;
+  // The pair of the NEXT trip is requested before this one is processed: with 32 warps per SM (the table takes the
+  // shared memory, the register file caps the CTA at 1024 threads) the DRAM latency is otherwise exposed between
+  // every two pairs of a thread (ncu: half of the stall samples waited for these loads).
+  uint32_t wn[W];
+  {
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + tid;
+    if (i0 < n) load_rec_hint<RB>(recs + i0 * R::kVec, wn, pol.stream);
+  }
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n_round; i += stride) {
-    bool need = false;
-    if (i < n) {
-      uint32_t w[W];
-      load_rec<RB>(recs + i * R::kVec, w);
-      const uint64_t v = rec_value<RB>(w);
-      vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
-      need = true;
-      if (v != 0 && v <= 0xffffull) {  // (a zero cannot live in the shared table: its state word would read "empty")
-        uint32_t slot = __umulhi(slot_hash<RB>(w), entries);
-#pragma unroll 1
-        for (int probe = 0; probe < 4; probe++) {
-          const uint32_t st = *(volatile uint32_t*)(state + slot);
-          if (st == 0) {
-            if (atomicCAS(state + slot, 0u, kCombineLock) == 0u) {
+    uint32_t w[W];
+    bool need = i < n;
 #pragma unroll
-              for (int k = 0; k < KW; k++) tab[(size_t)k * entries + slot] = w[k];
-              __threadfence_block();
-              atomicExch(state + slot, (uint32_t)v);
-              need = false;
-              break;
-            }
-          } else if (st != kCombineLock && st <= 0x7fffffffu) {
-            bool eq = true;
+    for (int k = 0; k < W; k++) w[k] = wn[k];
+    if (i + stride < n) load_rec_hint<RB>(recs + (i + stride) * R::kVec, wn, pol.stream);
+    const uint64_t v = need ? rec_value<RB>(w) : 0ull;
+    vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
+    // Straight-line, predicated code: a probe loop that lanes leave at different trips falls apart into fragments
+    // that do not reconverge inside it, and every fragment then waits for shared memory on its own.
+    const uint32_t h = slot_hash<RB>(w);
+    if (need && v != 0 && v <= vcap) {  // (a zero would still have to create its key: left to the global table)
+      const uint32_t tg = h | 2u;
+      const uint32_t s0 = __umulhi(h, entries), s1 = s0 + 1 == entries ? 0u : s0 + 1;
+      const uint32_t t0 = ((volatile uint32_t*)tag)[s0], t1 = ((volatile uint32_t*)tag)[s1];
+      if (t0 == tg || t1 == tg) {
+        const uint32_t sl = t0 == tg ? s0 : s1;
+        uint32_t x[KC];
 #pragma unroll
-            for (int k = 0; k < KW; k++) {
-              const uint32_t x = ((volatile uint32_t*)tab)[(size_t)k * entries + slot];
-              if (x != w[k]) {
-                eq = false;
-                break;
-              }
-              if (!R::kU64 && x == 0) break;  // both keys end here (zero padded, no NUL inside)
-            }
-            if (eq) {
-              atomicAdd(state + slot, (uint32_t)v);  // <= 0x7fffffff + 0xffff: never wraps, never looks empty or locked
-              need = false;
-              break;
-            }
-          }
-          slot = slot + 1 == entries ? 0 : slot + 1;
+        for (int k = 0; k < KC; k++) x[k] = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl];
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < KC; k++) eq = eq && x[k] == w[k];
+        if (KW > KC && eq && (w[KC - 1] >> 24) != 0) {  // 12 bytes or longer (rare): the remaining words, one by one
+#pragma unroll
+          for (int k = KC; k < KW; k++)  // (unrolled: a run-time index into w[] would move the record to local memory)
+            if (eq) eq = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl] == w[k];
+        }
+        if (eq) {
+          atomicAdd(val + sl, (uint32_t)v);
+          need = false;
+        }  // (same hash, other key: the pair goes to the global table, which is allowed to hold a key twice)
+      } else if (t0 == 0 || t1 == 0) {  // claim the empty slot (the table fills early in the kernel's life; then rare)
+        const uint32_t sl = t0 == 0 ? s0 : s1;
+        if (atomicCAS(tag + sl, 0u, 1u) == 0u) {
+#pragma unroll
+          for (int k = 0; k < KW; k++) key[(uint32_t)k * entries + sl] = w[k];
+          val[sl] = (uint32_t)v;
+          __threadfence_block();
+          atomicExch(tag + sl, tg);
+          need = false;
         }
       }
     }
     const uint32_t m = __ballot_sync(0xffffffffu, need);
     if (m) {
-      if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+      if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, h);
       qn += __popc(m);
       __syncwarp();
       if (qn >= 32) {
         qn -= 32;
-        to_gtab(q[qn + lane]);
+        to_gtab(true, q[qn + lane]);
         __syncwarp();
       }
     }
   }
-  if (lane < qn) to_gtab(q[lane]);
+  to_gtab(lane < qn, lane < qn ? q[lane] : make_uint2(0u, 0u));
   __syncthreads();
   // flush the shared table into the global one
-  for (uint32_t e = tid; e < entries; e += blockDim.x) {
-    const uint32_t st = state[e];
-    if (!st) continue;
+  const uint32_t e_round = (entries + 31) / 32 * 32;
+  for (uint32_t e = tid; e < e_round; e += blockDim.x) {
+    const bool has = e < entries && tag[e] > 1u;
     uint32_t w[W];
 #pragma unroll
-    for (int k = 0; k < KW; k++) w[k] = tab[(size_t)k * entries + e];
-#pragma unroll
-    for (int k = KW; k < W; k++) w[k] = 0;
-    gtab_add<RB, CHECKED>(gtab, glog, w, (uint64_t)st, slot_hash<RB>(w), flags);
+    for (int k = 0; k < W; k++) w[k] = (k < KW && has) ? key[(uint32_t)k * entries + e] : 0u;
+    gtab_add<RB, CHECKED>(has, gtab, glog, w, has ? (uint64_t)val[e] : 0ull, slot_hash<RB>(w), flags, pol.keep);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -1071,6 +1143,8 @@ static inline int stream_grid(uint64_t n, int threads, int ctas_per_sm) {
   return (int)(need < cap ? (need ? need : 1) : cap);
 }
 
+void kernels_set_tune(uint32_t bits) { g_tune = bits; }
+
 cudaError_t kernels_configure() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -1093,12 +1167,12 @@ cudaError_t kernels_configure() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_sort_reduce_u64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
   if (e != cudaSuccess) return e;
-#define CFGC(RB)                                                                                             \
-  e = cudaFuncSetAttribute(k_combine<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem); \
-  if (e != cudaSuccess) return e;                                                                            \
-  e = cudaFuncSetAttribute(k_combine<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
+#define CFGC1(RB, CH)                                                                                      \
+  e = cudaFuncSetAttribute(k_combine<RB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
   if (e != cudaSuccess) return e;
+#define CFGC(RB) CFGC1(RB, false) CFGC1(RB, true)
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
+#undef CFGC1
 #undef CFGC
 #define CFGT(RB)                                                                                         \
   e = cudaFuncSetAttribute(k_split_tma<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(RB)); \
@@ -1170,11 +1244,14 @@ uint32_t gtab_log_slots(int rb, uint64_t bytes) {
 int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
                    int sm_count, cudaStream_t s) {
   if (!n) return 0;
-  uint32_t entries = (uint32_t)(kCombineSmem / rb);
+  uint32_t entries = (uint32_t)(kCombineSmem / (rb + 4));  // key words + value, + the tag
+  // the shared table only takes values whose per-CTA sum cannot wrap 32 bits
+  const uint64_t per_cta = (n + sm_count - 1) / sm_count + kCombineThreads;
+  const uint32_t vcap = (uint32_t)std::min<uint64_t>(0xffffull, 0xffffffffull / per_cta);
   if (checked) {
-    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, gtab, glog, flags)));
+    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags)));
   } else {
-    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, gtab, glog, flags)));
+    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags)));
   }
   return 1;
 }

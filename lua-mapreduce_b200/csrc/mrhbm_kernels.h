@@ -160,6 +160,7 @@ int launch_compact(int rb, const ShuffleBuffers& b, uint32_t B, void* dst_keys, 
 int launch_checksum_in(int rb, const void* recs, uint64_t n, uint64_t* acc4, cudaStream_t s);
 int launch_checksum_out(int rb, const ShuffleBuffers& b, uint32_t B, const BinParams& bp, uint32_t bin_base,
                         uint64_t* acc6, cudaStream_t s);
+void kernels_set_tune(uint32_t bits);  // measurement hooks (MRHBM_TUNE), read once at mrhbm_init
 cudaError_t kernels_configure();  // opt-in shared memory sizes; call once per device
 
 }  // namespace mrhbm

@@ -15,6 +15,7 @@ local hbm = { _VERSION = "0.1", _NAME = "mapreduce.hbm" }
 --   partitionfn module: hbm_partitionfn = "fnv_lua" | "wordhash" | "mulhash", NUM_REDUCERS = n
 --   reducefn / combinerfn module: hbm_reducefn = "sum"
 local ctx -- one context per worker process (job.lua keeps `funcs`/`initialized` per process too)
+local tuple_keys = false -- hbm.configure(..., { key_kind = "tuple" }); an upvalue of configure, map_job and groups
 
 function hbm.configure(partition_mod, reduce_mod, combiner_mod, opts)
   -- hbm_reducefn = "sum": reduced on the device.  No declaration: general reducer -- the device
@@ -48,12 +49,44 @@ end
 --                big-endian 7-bit groups each OR 0x80
 -- Bytewise order = length first, then component-wise: a linear extension of tuple.lua:183-195.
 local tuple = require "mapreduce.tuple"
-local spack, sunpack = string.pack, string.unpack -- Lua >= 5.3; on 5.2 use struct.pack(">d") from lua-struct
+-- IEEE-754 binary64 <-> two 32-bit words (big end first) with math.frexp / math.ldexp: Lua 5.2 has no
+-- string.pack.  Mirrored 1:1 (and checked against struct.pack) in tests/test_lua_sources.py.
+local function double_to_words(x)
+  if x == 0 then return 0, 0 end
+  local sign = 0
+  if x < 0 then sign, x = 0x80000000, -x end
+  if x == math.huge then return sign + 0x7FF00000, 0 end
+  local m, e = math.frexp(x) -- x = m * 2^e, 0.5 <= m < 1
+  e = e + 1022               -- biased exponent of the 1.f form
+  local mant
+  if e <= 0 then             -- subnormal: 0.f * 2^-1022
+    mant, e = m * 2 ^ (52 + e), 0
+  else
+    mant = (m * 2 - 1) * 2 ^ 52
+  end
+  local hi_m = math.floor(mant / 2 ^ 32)
+  return sign + e * 2 ^ 20 + hi_m, mant - hi_m * 2 ^ 32
+end
+local function words_to_double(hi, lo)
+  local neg = hi >= 0x80000000
+  if neg then hi = hi - 0x80000000 end
+  local e = math.floor(hi / 2 ^ 20)
+  local mant = (hi - e * 2 ^ 20) * 2 ^ 32 + lo
+  local x
+  if e == 0 then
+    x = math.ldexp(mant, -1074)
+  elseif e == 2047 then
+    x = math.huge -- (NaN is rejected by enc_num, so only infinities arrive here)
+  else
+    x = math.ldexp(mant + 2 ^ 52, e - 1075)
+  end
+  return neg and -x or x
+end
 
 local function enc_num(x, out)
   assert(x == x, "NaN cannot be a key")
   if x == 0 then x = 0 end -- -0 and 0 are the same table key
-  local hi, lo = sunpack(">I4I4", spack(">d", x))
+  local hi, lo = double_to_words(x)
   if hi >= 0x80000000 then hi, lo = 0xFFFFFFFF - hi, 0xFFFFFFFF - lo else hi = hi + 0x80000000 end
   -- 64 bits -> groups of 1,7,7,...,7 bits
   local bits = {}
@@ -114,7 +147,7 @@ local function dec_component(s, i)
       end
     end
     if hi >= 0x80000000 then hi = hi - 0x80000000 else hi, lo = 0xFFFFFFFF - hi, 0xFFFFFFFF - lo end
-    return (sunpack(">d", spack(">I4I4", hi, lo))), i + 11
+    return words_to_double(hi, lo), i + 11
   elseif tag == 32 then
     local j = s:find("\1", i + 1, true)
     return s:sub(i + 1, j - 1), j + 1
@@ -133,8 +166,6 @@ dec_key = function(s, i)
   return tuple(t), i
 end
 function hbm.decode_key(s) return (dec_key(s, 1)) end
-
-local tuple_keys = false -- hbm.configure(..., { key_kind = "tuple" })
 
 -- job_prepare_map (job.lua:154-228): returns the emit closure and the finisher
 function hbm.map_job(map_key)

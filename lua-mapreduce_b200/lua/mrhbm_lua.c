@@ -13,6 +13,7 @@
  */
 #include <lauxlib.h>
 #include <lua.h>
+#include <math.h>
 #include <string.h>
 
 #include "mrhbm.h"
@@ -85,6 +86,11 @@ static int ctx_map_begin(lua_State *L) {
   m->h = NULL;
   m->ctx = u->h;
   luaL_setmetatable(L, MAP_MT);
+  /* the map keeps its ctx alive (Lua 5.2 user values are tables): commit / abort / __gc dereference it */
+  lua_createtable(L, 1, 0);
+  lua_pushvalue(L, 1);
+  lua_rawseti(L, -2, 1);
+  lua_setuservalue(L, -2);
   if (mrhbm_map_begin(u->h, id, &m->h) != MRHBM_OK) return fail(L, u->h);
   return 1;
 }
@@ -93,19 +99,34 @@ static int ctx_map_begin(lua_State *L) {
 static int map_emit(lua_State *L) {
   lmap *m = (lmap *)luaL_checkudata(L, 1, MAP_MT);
   int rc;
-  uint32_t v = (uint32_t)luaL_optnumber(L, 3, 1);
+  lua_Number vn = luaL_optnumber(L, 3, 1);
+  int u64 = m->h && mrhbm_record_bytes(m->ctx) == 16;
   if (!m->h) return fail(L, NULL);
+  /* values are unsigned integers: < 2^32 in string records, < 2^53 (exact Lua numbers) with u64 keys.  Anything
+   * else is refused here -- a C cast of an out-of-range double is undefined behaviour, not a wrap-around. */
+  if (!(vn >= 0 && vn == floor(vn) && vn < (u64 ? 9007199254740992.0 : 4294967296.0))) {
+    lua_pushnil(L);
+    lua_pushstring(L, u64 ? "mrhbm: value must be an integer in [0, 2^53)" : "mrhbm: value must be an integer in [0, 2^32)");
+    return 2;
+  }
+  uint64_t v = (uint64_t)vn;
   if (lua_type(L, 2) == LUA_TNUMBER) {
-    rc = mrhbm_emit_u64(m->h, (uint64_t)lua_tonumber(L, 2), v);
+    lua_Number kn = lua_tonumber(L, 2);
+    if (!u64 || !(kn >= 0 && kn == floor(kn) && kn < 9007199254740992.0)) {
+      lua_pushnil(L);
+      lua_pushstring(L, "mrhbm: number keys need key_kind = 'u64' and an integer in [0, 2^53)");
+      return 2;
+    }
+    rc = mrhbm_emit_u64(m->h, (uint64_t)kn, v);
   } else {
     size_t len;
     const char *k = luaL_checklstring(L, 2, &len);
-    if (mrhbm_record_bytes(m->ctx) == 16 && len == 8) {
+    if (u64 && len == 8) {
       uint64_t x = 0;
       for (int i = 0; i < 8; i++) x = (x << 8) | (unsigned char)k[i];
       rc = mrhbm_emit_u64(m->h, x, v);
     } else
-      rc = mrhbm_emit_str(m->h, k, len, v);
+      rc = mrhbm_emit_str(m->h, k, len, (uint32_t)v);
   }
   if (rc != MRHBM_OK) return fail(L, m->ctx);
   lua_pushboolean(L, 1);
@@ -195,7 +216,8 @@ static int ctx_groups(lua_State *L) {
   it->h = NULL;
   luaL_setmetatable(L, ITER_MT);
   if (mrhbm_groups_open(u->h, p, &it->h) != MRHBM_OK) return fail(L, u->h);
-  lua_pushcclosure(L, iter_next, 1);
+  lua_pushvalue(L, 1); /* second upvalue: the ctx stays alive as long as the iterator function does */
+  lua_pushcclosure(L, iter_next, 2);
   return 1;
 }
 

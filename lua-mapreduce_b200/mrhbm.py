@@ -52,7 +52,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "mrhbm_abi_version", "mrhbm_init", "mrhbm_destroy", "mrhbm_last_error", "mrhbm_record_bytes",
     "mrhbm_host_alloc", "mrhbm_host_free", "mrhbm_map_begin", "mrhbm_emit_str", "mrhbm_emit_u64",
-    "mrhbm_emit_batch", "mrhbm_emit_device", "mrhbm_map_gen_u64", "mrhbm_map_gen_zipf", "mrhbm_map_wordcount", "mrhbm_pool_read", "mrhbm_map_commit",
+    "mrhbm_emit_batch", "mrhbm_emit_device", "mrhbm_map_gen_u64", "mrhbm_map_gen_zipf", "mrhbm_map_wordcount", "mrhbm_synth_zipf_text", "mrhbm_pool_read", "mrhbm_map_commit",
     "mrhbm_map_abort", "mrhbm_shuffle", "mrhbm_partitions", "mrhbm_groups_open", "mrhbm_groups_next",
     "mrhbm_groups_close", "mrhbm_result_info_get", "mrhbm_result_copy", "mrhbm_checksum_input",
     "mrhbm_checksum_result", "mrhbm_stats_get", "mrhbm_reset", "mrhbm_comm_unique_id", "mrhbm_comm_init",
@@ -92,12 +92,13 @@ def load(build_if_missing=True):
     sig("mrhbm_host_free", None, vp, vp)
     sig("mrhbm_map_begin", i, vp, C.c_char_p, C.POINTER(vp))
     sig("mrhbm_emit_str", i, vp, C.c_char_p, sz, u32)
-    sig("mrhbm_emit_u64", i, vp, u64, u32)
+    sig("mrhbm_emit_u64", i, vp, u64, u64)
     sig("mrhbm_emit_batch", i, vp, vp, sz)
     sig("mrhbm_emit_device", i, vp, vp, sz)
     sig("mrhbm_map_gen_u64", i, vp, u64, u64, u64)
     sig("mrhbm_map_gen_zipf", i, vp, u64, u64, u64, vp, u64)
-    sig("mrhbm_map_wordcount", i, vp, C.c_char_p, sz, C.POINTER(u64))
+    sig("mrhbm_map_wordcount", i, vp, vp, sz, C.POINTER(u64))
+    sig("mrhbm_synth_zipf_text", i, u64, u64, u64, u32, vp, u64, vp, sz, C.POINTER(sz), i)
     sig("mrhbm_pool_read", i, vp, u64, u64, vp)
     sig("mrhbm_map_commit", i, vp)
     sig("mrhbm_map_abort", None, vp)
@@ -118,10 +119,27 @@ def load(build_if_missing=True):
     return L
 
 
+def synth_zipf_text(seed, first, n, table, words_per_line=25, out=None, threads=None):
+    """SURVEY App. B word-count text of words [first, first+n) of the Zipf word stream (host side generator in
+    libmrhbm).  Returns a uint8 array (a view of `out` when given)."""
+    L = load()
+    t = np.ascontiguousarray(table, dtype=np.uint64)
+    threads = threads or min(os.cpu_count() or 1, 128)
+    need = C.c_size_t()
+    if out is None:
+        L.mrhbm_synth_zipf_text(seed, first, n, words_per_line, t.ctypes.data, t.size, None, 0, C.byref(need), threads)
+        out = np.empty(need.value, dtype=np.uint8)
+    rc = L.mrhbm_synth_zipf_text(seed, first, n, words_per_line, t.ctypes.data, t.size, out.ctypes.data, out.nbytes,
+                                 C.byref(need), threads)
+    if rc != 0:
+        raise MrhbmError(rc, "synth_zipf_text: the text needs %d bytes, the buffer holds %d" % (need.value, out.nbytes))
+    return out[:need.value]
+
+
 def record_dtype(key_kind, max_key_bytes=27):
     """numpy dtype of one emit_batch record."""
     if key_kind == KEY_U64:
-        return np.dtype([("key", "<u8"), ("val", "<u4"), ("pad", "<u4")])
+        return np.dtype([("key", "<u8"), ("val", "<u8")])
     rb = 32 if max_key_bytes <= 27 else 64 if max_key_bytes <= 59 else 128
     return np.dtype([("key", "S%d" % (rb - 4)), ("val", "<u4")])
 
@@ -134,10 +152,15 @@ class Map:
         ctx._chk(ctx.L.mrhbm_map_begin(ctx.h, str(job_id).encode(), C.byref(self.h)))
 
     def emit(self, key, value=1):
-        if isinstance(key, int):
-            rc = self.ctx.L.mrhbm_emit_u64(self.h, key, value)
+        # values are unsigned integers: < 2^32 in string records, < 2^53 (exact Lua numbers) with u64 keys;
+        # ctypes would silently wrap or truncate anything else
+        u64 = isinstance(key, int)
+        if not (isinstance(value, (int, np.integer)) or float(value).is_integer()) or not 0 <= value < (1 << 53 if u64 else 1 << 32):
+            raise MrhbmError(-1, "value must be an integer in [0, 2^%d), got %r" % (53 if u64 else 32, value))
+        if u64:
+            rc = self.ctx.L.mrhbm_emit_u64(self.h, key, int(value))
         else:
-            rc = self.ctx.L.mrhbm_emit_str(self.h, key, len(key), value)
+            rc = self.ctx.L.mrhbm_emit_str(self.h, key, len(key), int(value))
         self.ctx._chk(rc)
 
     def emit_batch(self, recs):
@@ -158,10 +181,18 @@ class Map:
         t = np.ascontiguousarray(table, dtype=np.uint64)
         self.ctx._chk(self.ctx.L.mrhbm_map_gen_zipf(self.h, seed, start, n, t.ctypes.data, t.size))
 
-    def wordcount(self, text: bytes):
-        """device-side WordCount mapfn over a text buffer; returns the number of words emitted"""
+    def wordcount(self, text, nbytes=None):
+        """device-side WordCount mapfn over a text buffer (bytes, a uint8 numpy array, or an address with
+        nbytes); returns the number of words emitted"""
         n = C.c_uint64()
-        self.ctx._chk(self.ctx.L.mrhbm_map_wordcount(self.h, text, len(text), C.byref(n)))
+        if isinstance(text, (bytes, bytearray)):
+            keep = C.create_string_buffer(bytes(text), len(text)) if isinstance(text, bytearray) else text
+            ptr, nbytes = C.cast(C.c_char_p(keep), C.c_void_p), len(text)
+        elif isinstance(text, np.ndarray):
+            ptr, nbytes = C.c_void_p(text.ctypes.data), text.nbytes
+        else:
+            ptr = C.c_void_p(int(text))
+        self.ctx._chk(self.ctx.L.mrhbm_map_wordcount(self.h, ptr, nbytes, C.byref(n)))
         return n.value
 
     def commit(self):

@@ -981,7 +981,7 @@ void mro_gen_zipf_rec32(uint64_t seed, uint64_t start, size_t n, const uint64_t 
 /* ======================================================================== */
 typedef struct {
   uint32_t part;
-  uint32_t val;
+  uint64_t val;
   uint64_t key;
 } flat64_t;
 static int flat64_cmp(const void *a, const void *b) {
@@ -989,13 +989,12 @@ static int flat64_cmp(const void *a, const void *b) {
   if (x->part != y->part) return x->part < y->part ? -1 : 1;
   return (x->key > y->key) - (x->key < y->key);
 }
-size_t mro_groupby_u64(const uint64_t *keys, const uint32_t *vals, size_t n, int partitioner,
-                       uint32_t nparts, uint64_t *out_keys, uint64_t *out_sums,
-                       uint64_t *part_off) {
+static size_t groupby_u64_any(const uint64_t *keys, const void *vals, int val_bytes, size_t n, int partitioner,
+                              uint32_t nparts, uint64_t *out_keys, uint64_t *out_sums, uint64_t *part_off) {
   flat64_t *a = (flat64_t *)malloc((n ? n : 1) * sizeof *a);
   for (size_t i = 0; i < n; i++) {
     a[i].key = keys[i];
-    a[i].val = vals[i];
+    a[i].val = val_bytes == 8 ? ((const uint64_t *)vals)[i] : ((const uint32_t *)vals)[i];
     if (partitioner == MRO_PART_MULHASH)
       a[i].part = mro_part_mulhash(keys[i], nparts);
     else {
@@ -1025,6 +1024,16 @@ size_t mro_groupby_u64(const uint64_t *keys, const uint32_t *vals, size_t n, int
   for (uint32_t p = 0; p < nparts; p++) part_off[p + 1] += part_off[p];
   free(a);
   return g;
+}
+size_t mro_groupby_u64(const uint64_t *keys, const uint32_t *vals, size_t n, int partitioner,
+                       uint32_t nparts, uint64_t *out_keys, uint64_t *out_sums,
+                       uint64_t *part_off) {
+  return groupby_u64_any(keys, vals, 4, n, partitioner, nparts, out_keys, out_sums, part_off);
+}
+size_t mro_groupby_u64_v64(const uint64_t *keys, const uint64_t *vals, size_t n, int partitioner,
+                           uint32_t nparts, uint64_t *out_keys, uint64_t *out_sums,
+                           uint64_t *part_off) {
+  return groupby_u64_any(keys, vals, 8, n, partitioner, nparts, out_keys, out_sums, part_off);
 }
 static uint32_t g_rec_bytes;
 typedef struct {
@@ -1380,3 +1389,56 @@ int mro_run_synthetic(mro_t *o, int kind, uint64_t seed, uint64_t start, uint64_
   *reduce_seconds = t2 - t1;
   return r < 0 ? -1 : 0;
 }
+
+/* the same runner over a TEXT: njobs map jobs = the text cut at line ends into njobs slices (one "file" per
+ * job, examples/WordCountBig/taskfn.lua:6-12), mapfn = examples/WordCount/mapfn.lua:3-9 */
+typedef struct {
+  mro_t *o;
+  const char *text;
+  const size_t *cut; /* njobs+1 slice boundaries */
+  uint32_t njobs, next;
+  pthread_mutex_t mu;
+} tctx_t;
+static void *text_worker(void *arg) {
+  tctx_t *c = (tctx_t *)arg;
+  for (;;) {
+    pthread_mutex_lock(&c->mu);
+    uint32_t j = c->next++;
+    pthread_mutex_unlock(&c->mu);
+    if (j >= c->njobs) break;
+    char name[32];
+    snprintf(name, sizeof name, "%u", j + 1);
+    mro_map_t *m = mro_map_begin(c->o, name);
+    mro_map_wordcount(m, c->text + c->cut[j], c->cut[j + 1] - c->cut[j]);
+    mro_map_commit(m);
+  }
+  return NULL;
+}
+int mro_run_text(mro_t *o, const void *textv, size_t len, uint32_t njobs, int nthreads, double *map_seconds,
+                 double *reduce_seconds) {
+  const char *text = (const char *)textv;
+  if (njobs < 1) njobs = 1;
+  size_t *cut = (size_t *)calloc(njobs + 1, sizeof(size_t));
+  for (uint32_t j = 1; j < njobs; j++) {
+    size_t p = len / njobs * j;
+    if (p < cut[j - 1]) p = cut[j - 1];
+    while (p < len && p > 0 && text[p - 1] != '\n') p++; /* next line start */
+    cut[j] = p;
+  }
+  cut[njobs] = len;
+  tctx_t c = {o, text, cut, njobs, 0, PTHREAD_MUTEX_INITIALIZER};
+  pthread_t th[64];
+  if (nthreads > 64) nthreads = 64;
+  if (nthreads < 1) nthreads = 1;
+  double t0 = now_s();
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, text_worker, &c);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  double t1 = now_s();
+  int r = mro_reduce_all(o, nthreads);
+  double t2 = now_s();
+  free(cut);
+  *map_seconds = t1 - t0;
+  *reduce_seconds = t2 - t1;
+  return r < 0 ? -1 : 0;
+}
+

@@ -83,10 +83,12 @@ def lib():
     sig("mro_gen_u64", None, u64, u64, sz, vp, vp)
     sig("mro_gen_zipf_rec32", None, u64, u64, sz, vp, u64, vp)
     sig("mro_groupby_u64", sz, vp, vp, sz, i, u32, vp, vp, vp)
+    sig("mro_groupby_u64_v64", sz, vp, vp, sz, i, u32, vp, vp, vp)
     sig("mro_groupby_rec", sz, vp, sz, u32, i, u32, vp, vp, vp)
     sig("mro_groupby_u64_stream", sz, u64, u64, sz, i, u32, u32, u32, i, vp, vp, sz, vp)
     sig("mro_zipf_counts", i, u64, u64, sz, vp, u64, i, vp)
     sig("mro_wordcount_from_counts", sz, vp, u64, i, u32, u32, u32, vp, vp, vp)
+    sig("mro_run_text", i, vp, vp, sz, u32, i, C.POINTER(dbl), C.POINTER(dbl))
     sig("mro_run_synthetic", i, vp, i, u64, u64, u64, u32, i, vp, u64, C.POINTER(dbl), C.POINTER(dbl))
     _lib = L
     return L
@@ -248,13 +250,14 @@ def gen_zipf_rec32(seed, start, n, table):
 
 def groupby_u64(keys, vals, partitioner, nparts):
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
-    vals = np.ascontiguousarray(vals, dtype=np.uint32)
+    wide = np.asarray(vals).dtype.itemsize == 8  # 64-bit values (u64-key records carry them since ABI 2)
+    vals = np.ascontiguousarray(vals, dtype=np.uint64 if wide else np.uint32)
     n = keys.size
     ok = np.empty(max(n, 1), dtype=np.uint64)
     os_ = np.empty(max(n, 1), dtype=np.uint64)
     po = np.empty(nparts + 1, dtype=np.uint64)
-    g = lib().mro_groupby_u64(keys.ctypes.data, vals.ctypes.data, n, partitioner, nparts,
-                              ok.ctypes.data, os_.ctypes.data, po.ctypes.data)
+    fn = lib().mro_groupby_u64_v64 if wide else lib().mro_groupby_u64
+    g = fn(keys.ctypes.data, vals.ctypes.data, n, partitioner, nparts, ok.ctypes.data, os_.ctypes.data, po.ctypes.data)
     return ok[:g].copy(), os_[:g].copy(), po
 
 
@@ -314,5 +317,15 @@ def run_synthetic(engine, kind, seed, start, pairs_per_job, njobs, nthreads, tab
                                 t.ctypes.data if t is not None else None, t.size if t is not None else 0,
                                 C.byref(ms), C.byref(rs))
     if r != 0:
+        raise RuntimeError(lib().mro_error(engine.h).decode())
+    return ms.value, rs.value
+
+
+def run_text(engine, text, njobs, nthreads):
+    """word count of a text (bytes or uint8 array) as njobs map jobs + all reduce jobs on nthreads workers.
+    Returns (map_seconds, reduce_seconds)."""
+    a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+    ms, rs = C.c_double(), C.c_double()
+    if lib().mro_run_text(engine.h, a.ctypes.data, a.size, njobs, nthreads, C.byref(ms), C.byref(rs)) != 0:
         raise RuntimeError(lib().mro_error(engine.h).decode())
     return ms.value, rs.value

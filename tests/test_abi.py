@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libmrhbm.so does not export %s" % n
     assert sorted(mrhbm.EXPORTS) == names
-    assert L.mrhbm_abi_version() == 1
+    assert L.mrhbm_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

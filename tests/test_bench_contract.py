@@ -25,7 +25,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "config2" in d["config"]["workload"]
+    assert "config3" in d["config"]["workload"] and d["warmup"] == 1
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -53,9 +53,13 @@ def test_bench_main_dry_run_assembles_the_contract_line():
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "gpu_launches", "clocks", "e2e", "roofline", "cpu_baseline"):
+              "vs_baseline", "dtype", "data", "config", "gpu_launches", "clocks", "e2e", "roofline", "cpu_baseline",
+              "parity_vs_oracle", "configs", "run"):
         assert k in d, k
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernels", "pipeline", "fusion_headroom"}
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
-    assert d["config"]["workload"].startswith("config2") and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("config3") and d["vs_baseline"] is None
+    assert set(d["configs"]) == {"config2_u64_1e8", "config4_u64_1e9_total", "config1_wordcount_197x10k"}
+    for blk in (d["configs"]["config2_u64_1e8"], d["configs"]["config4_u64_1e9_total"]):
+        assert set(blk) >= {"value", "ms_per_step", "roofline", "e2e", "config", "parity_vs_oracle"}

@@ -114,6 +114,30 @@ def test_u64_sparse_duplicates_inside_key_ordered_bins():
             check_vs_oracle_u64(ctx, keys, vals, P)
 
 
+@pytest.mark.parametrize("combiner", [False, True])
+def test_u64_values_wider_than_32_bits(combiner):
+    """u64-key records carry 64-bit values (ABI 2): any integer-valued Lua number < 2^53 (job.lua:83-97 emits
+    arbitrary values; reducefn.lua:1-5 adds doubles).  Sums here pass 2^32 many times over."""
+    n, P = 1_200_000 if combiner else 300_000, 16
+    rng = np.random.default_rng(21)
+    keys = O.gen_u64(SEED, 99, 4000)[0][rng.integers(0, 4000, n)]
+    vals = rng.integers(0, 1 << 40, n).astype(np.uint64)
+    vals[::7] = rng.integers(0, 60000, vals[::7].size).astype(np.uint64)  # small ones go through the shared-memory tables
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, combiner=combiner) as ctx:
+        m = ctx.map_begin("wide")
+        m.emit_batch(u64_records(keys[: n - 3], vals[: n - 3]))
+        for k, v in zip(keys[n - 3:].tolist(), vals[n - 3:].tolist()):
+            m.emit(k, v)
+        with pytest.raises(mrhbm.MrhbmError):
+            m.emit(5, 1 << 53)
+        with pytest.raises(mrhbm.MrhbmError):
+            m.emit(5, -1)
+        m.commit()
+        ctx.shuffle()
+        check_vs_oracle_u64(ctx, keys, vals, P)
+        assert int(ctx.result_copy()[1].max()) > 1 << 40
+
+
 def test_u64_clustered_keys_fall_back_to_runs():
     """sequential integers: top key bits are constant, so key-ordered sub-bins cannot balance"""
     n, P = 300_000, 4
