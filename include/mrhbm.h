@@ -33,7 +33,7 @@ enum { /* error codes */
   MRHBM_E_INVAL = -1,     /* bad argument / bad state */
   MRHBM_E_CUDA = -2,      /* CUDA runtime error (message has the CUDA string) */
   MRHBM_E_NOMEM = -3,     /* host or device allocation failed */
-  MRHBM_E_KEY = -4,       /* key does not fit the ctx record layout (too long / embedded NUL) */
+  MRHBM_E_KEY = -4,       /* key does not fit the ctx record layout (too long) */
   MRHBM_E_SKEW = -5,      /* a bin holds more distinct keys than one SM can sort */
   MRHBM_E_OVERFLOW = -6,  /* u32 partial sum overflow while combining string-keyed records */
   MRHBM_E_NCCL = -7,      /* NCCL missing or failed */
@@ -87,7 +87,7 @@ typedef struct mrhbm_config {
 
 /* record layouts (little endian) moved by emit_batch / gen / result_copy:
  *   U64 : { uint64_t key; uint64_t value; }                             16 B
- *   STR : { uint8_t key[RB-4] zero padded, no NUL inside; uint32_t value; }  RB = 32/64/128 */
+ *   STR : { uint8_t key[RB-4] zero padded, no NUL inside (see mrhbm_emit_str); uint32_t value; }  RB = 32/64/128 */
 uint32_t mrhbm_record_bytes(const mrhbm_ctx *);
 
 /* ---- lifecycle (replaces cnn(...) + fs.router(...), mapreduce/fs.lua:185-208) ---- */
@@ -102,7 +102,10 @@ void mrhbm_host_free(mrhbm_ctx *, void *);
 
 /* ---- map side: job.lua:83-97 (emit) + job.lua:186-227 (sort/partition/spill) ---- */
 int mrhbm_map_begin(mrhbm_ctx *, const char *map_job_id, mrhbm_map **out);
-/* key bytes are copied before return (Lua strings may be collected) */
+/* key bytes are copied before return (Lua strings may be collected).  Any byte string is a key: bytes 0x00 and
+ * 0x01 are stored escaped (01 01 / 01 02, order preserving; each costs one more byte of the key slot), hashed by
+ * the built-in partitioners as the original bytes and handed back unescaped by mrhbm_groups_next.  Key slots in
+ * emit_batch records and in mrhbm_result_copy are in the stored (escaped) form. */
 int mrhbm_emit_str(mrhbm_map *, const void *key, size_t klen, uint32_t value);
 int mrhbm_emit_u64(mrhbm_map *, uint64_t key, uint64_t value); /* value < 2^53 keeps Lua-number sums exact */
 /* n records in the ctx layout.  Pageable memory is consumed before return; memory from

@@ -72,6 +72,10 @@ struct mrhbm_ctx {
   bool no_ordered = false;     // sticky: key-ordered sub-bins overflowed once (clustered keys)
   void* l1buf = nullptr;  // coarse regions of the two-level split
   uint64_t l1_cap = 0;
+  // device tokeniser scratch (mrhbm_map_wordcount)
+  unsigned char* d_tok_text = nullptr;
+  uint32_t *d_tok_cnt = nullptr, *d_tok_off = nullptr;
+  uint64_t tok_text_cap = 0, tok_blocks_cap = 0;
   // map-side combiner: the global (L2 resident) hash table and the records compacted out of it
   void *comb = nullptr, *gtab = nullptr;
   uint64_t comb_cap = 0, gtab_cap = 0;  // records
@@ -116,6 +120,7 @@ struct RunCursor {
 struct mrhbm_iter {
   mrhbm_ctx* ctx;
   std::vector<uint64_t> valbuf;  // group-only mode: the values of the current key
+  std::vector<unsigned char> unesc;  // the current key with its 0x00 / 0x01 bytes restored
   std::vector<unsigned char> keys;
   std::vector<uint64_t> sums;
   std::vector<RunCursor> runs;
@@ -425,7 +430,8 @@ void mrhbm_destroy(mrhbm_ctx* c) {
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
                    c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
-                   c->gtab,        c->l1buf,       c->regions,    c->d_l1all,     c->d_sample};
+                   c->gtab,        c->l1buf,       c->regions,    c->d_l1all,     c->d_sample,   c->d_tok_text,
+                   c->d_tok_cnt,   c->d_tok_off};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -476,14 +482,31 @@ int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
   mrhbm_ctx* c = m->ctx;
   Entry g(c);
   if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "ctx holds u64 keys");
-  if (klen >= (size_t)c->kb)
-    return fail(c, MRHBM_E_KEY, "key of %zu bytes does not fit the %d-byte record class", klen, c->rb);
-  if (klen && memchr(key, 0, klen)) return fail(c, MRHBM_E_KEY, "keys with embedded NUL are not supported");
+  // Key slots are zero padded, so a key byte 0x00 cannot be stored as such.  Bytes 0x00 and 0x01 travel escaped --
+  // 0x00 -> 01 01, 0x01 -> 01 02 -- which keeps the bytewise order of the keys ("a" < "a\0" < "a\1" < "ab")
+  // and is the identity for text.  The device partitioner hashes the unescaped bytes, the iterator unescapes.
+  const unsigned char* k = (const unsigned char*)key;
+  size_t extra = 0;
+  for (size_t i = 0; i < klen; i++) extra += k[i] <= 1;
+  if (klen + extra >= (size_t)c->kb)
+    return fail(c, MRHBM_E_KEY, "key of %zu bytes does not fit the %d-byte record class", klen + extra, c->rb);
   unsigned char* slot;
   int rc = stage_slot(m, &slot);
   if (rc) return rc;
-  memcpy(slot, key, klen);
-  memset(slot + klen, 0, c->kb - klen);
+  if (!extra) {
+    memcpy(slot, key, klen);
+  } else {
+    size_t o = 0;
+    for (size_t i = 0; i < klen; i++) {
+      if (k[i] <= 1) {
+        slot[o++] = 1;
+        slot[o++] = (unsigned char)(k[i] + 1);
+      } else {
+        slot[o++] = k[i];
+      }
+    }
+  }
+  memset(slot + klen + extra, 0, c->kb - (klen + extra));
   memcpy(slot + c->kb, &value, 4);
   return MRHBM_OK;
 }
@@ -589,28 +612,37 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
   int rc = stage_flush(m);
   if (rc) return rc;
   const uint64_t nb = tok_blocks(len);
-  unsigned char* d_text = nullptr;
-  uint32_t *d_cnt = nullptr, *d_off = nullptr;
-  CU(c, cudaMalloc((void**)&d_text, len));
-  cudaError_t e = cudaMalloc((void**)&d_cnt, nb * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, (nb + 1) * 4);
-  auto cleanup = [&]() {
-    cudaFree(d_text);
-    cudaFree(d_cnt);
-    cudaFree(d_off);
-  };
-  if (e != cudaSuccess) {
-    cleanup();
-    cudaGetLastError();
-    return fail(c, MRHBM_E_NOMEM, "wordcount: %s", cudaGetErrorString(e));
+  // scratch of the tokeniser (text + per-block word counts and offsets) lives with the ctx and only grows: a
+  // cudaMalloc / cudaFree pair per call would synchronise the device every time
+  if (len > c->tok_text_cap || nb + 1 > c->tok_blocks_cap) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (void** p : {(void**)&c->d_tok_text, (void**)&c->d_tok_cnt, (void**)&c->d_tok_off}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
+    c->tok_text_cap = c->tok_blocks_cap = 0;
+    const uint64_t tcap = len + len / 8 + 4096, bcap = tok_blocks(tcap) + 1;
+    cudaError_t ea = cudaMalloc((void**)&c->d_tok_text, tcap);
+    if (ea == cudaSuccess) ea = cudaMalloc((void**)&c->d_tok_cnt, bcap * 4);
+    if (ea == cudaSuccess) ea = cudaMalloc((void**)&c->d_tok_off, (bcap + 1) * 4);
+    if (ea != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, MRHBM_E_NOMEM, "wordcount: %s", cudaGetErrorString(ea));
+    }
+    c->tok_text_cap = tcap;
+    c->tok_blocks_cap = bcap;
   }
+  unsigned char* d_text = c->d_tok_text;
+  uint32_t *d_cnt = c->d_tok_cnt, *d_off = c->d_tok_off;
+  cudaError_t e = cudaSuccess;
   uint64_t total = 0, off = 0;
   do {
     if ((e = cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
     if ((e = cudaMemsetAsync(c->sb.counters ? c->sb.counters : c->d_small, 0, 4, c->stream)) != cudaSuccess) break;
     launch_tok_count(d_text, len, d_cnt, c->stream);
     // exclusive scan of the block counts (chunks of at most 2^30 blocks is far beyond any text here)
-    launch_exscan(d_cnt, (uint32_t)nb, d_off, nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small, 0, c->stream);
+    launch_exscan(d_cnt, (uint32_t)nb, d_off, nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small, 0, c->stream,
+                  c->d_small + 64);
     if ((e = cudaMemcpyAsync(c->h_small, c->d_small, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
     total = c->h_small[0];
@@ -628,7 +660,6 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
     }
     add_range(m, off, total);
   } while (0);
-  cleanup();
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail(c, MRHBM_E_CUDA, "wordcount: %s", cudaGetErrorString(e));
@@ -978,8 +1009,8 @@ struct Src {
   const char* p;
   uint64_t n;
 };
-constexpr uint64_t kGtabL2Bytes = 64ull << 20;  // global combiner table sized to stay resident in the 126 MB L2
-constexpr uint32_t kGtabMaxExtra = 4;           // ... grown up to 16x (1 GB) when the keys do not fit
+constexpr uint32_t kGtabLog = 21;       // global combiner table: 2^21 16-byte entries = 32 MB, resident in the 126 MB L2
+constexpr uint32_t kGtabMaxExtra = 5;   // ... grown up to 32x (1 GB) when the keys do not fit
 
 // The pairs the shuffle partitions: the committed pool ranges, or -- with a combiner declared
 // (job.lua:92-96,198-202) and enough pairs to pay for it -- one record per distinct key of this rank's pairs
@@ -997,13 +1028,14 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
   cudaStream_t s = c->stream;
   bool checked = c->combine_checked;
   for (;;) {
-    const uint32_t glog = gtab_log_slots(c->rb, kGtabL2Bytes) + c->gtab_extra;
-    const uint64_t slots = 1ull << glog;
-    int rc = ensure_records(c, &c->gtab, &c->gtab_cap, slots);
+    const uint32_t glog = kGtabLog + c->gtab_extra;
+    const uint64_t tab_bytes = gtab_bytes_host(c->rb, glog);
+    const uint64_t slots = (1ull << glog) + (c->rb == 16 ? 0 : 1ull << (glog - 4));  // records the compaction can emit
+    int rc = ensure_records(c, &c->gtab, &c->gtab_cap, (tab_bytes + c->rb - 1) / c->rb);
     if (rc) return rc;
     rc = ensure_records(c, &c->comb, &c->comb_cap, slots);
     if (rc) return rc;
-    CU(c, cudaMemsetAsync(c->gtab, 0, slots * c->rb, s));
+    CU(c, cudaMemsetAsync(c->gtab, 0, tab_bytes, s));
     CU(c, cudaMemsetAsync(c->d_small, 0, 3 * sizeof(uint32_t), s));  // [0] flags, [1] records out, [2] largest value
     for (auto& sr : srcs)
       st.launches += launch_combine(c->rb, sr.p, sr.n, (uint32_t*)c->gtab, glog, c->d_small, checked, c->sm_count, s);
@@ -1014,7 +1046,7 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
     const uint32_t ef = c->h_small[0];
     if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
     if (ef & ERRF_SKEW) {  // the table filled up: more distinct keys than it takes
-      if (c->gtab_extra < kGtabMaxExtra && (slots << 1) * c->rb <= (4ull << 30)) {
+      if (c->gtab_extra < kGtabMaxExtra) {
         c->gtab_extra++;
         continue;
       }
@@ -1787,8 +1819,20 @@ int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint
     *key = it->keybuf;
     *klen = 8;
   } else {
+    size_t len = strnlen((const char*)k, c->kb);
+    if (memchr(k, 1, len)) {  // escaped 0x00 / 0x01 bytes (see mrhbm_emit_str)
+      it->unesc.clear();
+      for (size_t i = 0; i < len; i++) {
+        if (k[i] == 1 && i + 1 < len)
+          it->unesc.push_back((unsigned char)(k[++i] - 1));
+        else
+          it->unesc.push_back(k[i]);
+      }
+      k = it->unesc.data();
+      len = it->unesc.size();
+    }
     *key = k;
-    *klen = strnlen((const char*)k, c->kb);
+    *klen = len;
   }
   *values = gathered ? it->valbuf.data() : &it->sums[i];
   *nvalues = nv;

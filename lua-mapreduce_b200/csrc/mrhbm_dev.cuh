@@ -122,14 +122,24 @@ __device__ __forceinline__ uint32_t fnv_lua_hash(const uint32_t* r) {
   } else {
     // The word loop is unrolled (the record lives in registers), the byte loop is NOT: fully unrolled,
     // 4 records x 28 bytes of fnv_lua_step overflowed the instruction cache (ncu on k_hist<32>: 43 % of
-    // the stall samples were "no instruction").
+    // the stall samples were "no instruction").  Key bytes 0x00 / 0x01 are stored escaped (01 01 / 01 02,
+    // mrhbm_emit_str); the reference's partitionfn sees the original bytes, so they are restored here.
+    bool esc = false;
 #pragma unroll
     for (int i = 0; i < Rec<RB>::kKeyWords; i++) {
       uint32_t w = r[i];
       if (w == 0) break;  // keys hold no NUL: a zero word is past the end (short keys leave early)
 #pragma unroll 1
       do {
-        h = fnv_lua_step(h, w & 0xffu);
+        const uint32_t b = w & 0xffu;
+        if (esc) {
+          h = fnv_lua_step(h, b - 1u);
+          esc = false;
+        } else if (b == 1u) {
+          esc = true;
+        } else {
+          h = fnv_lua_step(h, b);
+        }
         w >>= 8;
       } while (w);
       if ((r[i] >> 24) == 0) break;

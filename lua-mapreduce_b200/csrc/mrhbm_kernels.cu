@@ -121,12 +121,19 @@ __global__ void __launch_bounds__(256) k_tok_emit(const unsigned char* __restric
     } rec;
 #pragma unroll
     for (int v = 0; v < RB / 16; v++) rec.v[v] = make_uint4(0, 0, 0, 0);
-    int l = 0;
-    while (i + l < len && !tok_space(t[i + l]) && l < KB) {
-      rec.b[l] = t[i + l];
-      l++;
+    int l = 0;  // bytes written to the key slot
+    uint64_t p = i;
+    while (p < len && !tok_space(t[p]) && l < KB) {
+      const unsigned char ch = t[p++];
+      if (ch <= 1) {  // 0x00 / 0x01 inside a word travel escaped, like mrhbm_emit_str does it
+        rec.b[l++] = 1;
+        if (l < KB) rec.b[l++] = (unsigned char)(ch + 1);
+        else l = KB + 1;
+      } else {
+        rec.b[l++] = ch;
+      }
     }
-    if (l >= KB || (i + l < len && !tok_space(t[i + l]))) {  // does not fit (one zero byte must remain)
+    if (l >= KB || (p < len && !tok_space(t[p]))) {  // does not fit (one zero byte must remain)
       atomicOr(flags, (uint32_t)ERRF_KEYLEN);
       l = KB - 1;
       rec.b[KB - 1] = 0;
@@ -332,6 +339,8 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
                                                        // bin's run (0: the run does not fit, nothing is stored)
   __shared__ uint32_t wsum[THREADS / 32];
   __shared__ uint32_t s_rbase[9], s_fbase[9];  // (kernel-parameter arrays indexed by a register would be copied to local memory)
+  __shared__ unsigned long long s_src[8];      // byte address and length (records) of the tile streams of this CTA
+  __shared__ uint32_t s_n[8];
   __shared__ __align__(8) uint64_t mbar[2];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -350,25 +359,31 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       uint32_t o0 = a.base_off[(size_t)f0 << a.rep_shift], o1 = a.base_off[(size_t)f1 << a.rep_shift];
       src += (size_t)o0 * R::kVec;
       n = o1 - o0;
-    } else {
-      unsigned long long base = a.peer[0];
+    }
+  }
+  // The tile streams this CTA splits: one (the source range) or, for optimistic level 2, region `coarse` as every
+  // rank filled it -- ndest streams, the remote ones read over NVLink.  The CTA takes tiles x, x + gridDim.x, ... of
+  // EVERY stream, round-robin over the streams, so that its remote bulk copies fly while it splits local tiles
+  // (with one CTA per source the ranks first did all their local tiles, then sat on the link: level 2 took
+  // local time + link time).
+  const uint32_t nsrc = (a.level == 2 && !a.base_off) ? a.ndest : 1u;
 #pragma unroll
-      for (int z = 1; z < 8; z++)
-        if (blockIdx.z == (uint32_t)z) base = a.peer[z];
-      src = (const uint4*)(uintptr_t)base + (size_t)(a.region_first + coarse) * a.seg_stride * R::kVec;
-      uint32_t c = a.seg_counts[(size_t)blockIdx.z * a.seg_zstride + ((size_t)(a.region_first + coarse) << a.ctr_shift)];
-      n = c < a.seg_stride ? c : a.seg_stride;
+  for (int z = 0; z < 8; z++) {
+    if (tid == (uint32_t)z && (uint32_t)z < nsrc) {
+      if (nsrc == 1 && !(a.level == 2 && !a.base_off)) {
+        s_src[0] = (unsigned long long)(uintptr_t)src;
+        s_n[0] = (uint32_t)n;
+      } else {
+        s_src[z] = a.peer[z] + (unsigned long long)(a.region_first + coarse) * a.seg_stride * RB;
+        const uint32_t c = a.seg_counts[(size_t)z * a.seg_zstride + ((size_t)(a.region_first + coarse) << a.ctr_shift)];
+        s_n[z] = c < a.seg_stride ? c : (uint32_t)a.seg_stride;
+      }
     }
   }
   uint32_t fine_base = a.fbase[0];  // first fine bin of this rank
 #pragma unroll
   for (int z = 1; z < 8; z++)
     if (a.me == (uint32_t)z) fine_base = a.fbase[z];
-  const uint64_t ntiles = (n + T - 1) / T;
-  auto tile_len = [&](uint64_t tile) -> uint32_t {
-    uint64_t t0 = tile * T;
-    return (uint32_t)((n - t0) < (uint64_t)T ? (n - t0) : (uint64_t)T);
-  };
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -376,16 +391,38 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   }
   for (uint32_t b = tid; b < kSplitMaxBins; b += THREADS) scnt[b] = 0;
   __syncthreads();
-  if (tid == 0 && blockIdx.x < ntiles)
-    bulk_load(raw0, src + (uint64_t)blockIdx.x * T * R::kVec, tile_len(blockIdx.x) * RB, &mbar[0]);
+  uint32_t ntmax = 0;
+  for (uint32_t z = 0; z < nsrc; z++) ntmax = max(ntmax, (s_n[z] + T - 1) / T);
+  // a CTA takes a CONTIGUOUS range of tiles of every stream (tiles x, x + gridDim.x, ... would walk it through a
+  // new 2 MB page per tile, 296 CTAs x 12 MB apart: beyond the TLB reach)
+  const uint32_t rounds = (ntmax + gridDim.x - 1) / gridDim.x;
+  const uint32_t ksteps = rounds * nsrc;
+  // step k of this CTA: round k / nsrc, stream (k % nsrc + blockIdx.x + me) % nsrc, tile blockIdx.x * rounds + round
+  auto step = [&](uint32_t k, const uint4*& p) -> uint32_t {
+    const uint32_t r = k / nsrc, z = (k - r * nsrc + blockIdx.x + a.me) % nsrc;
+    const uint64_t t0 = (uint64_t)(blockIdx.x * rounds + r) * T;
+    const uint32_t nz = s_n[z];
+    p = (const uint4*)(uintptr_t)s_src[z] + t0 * R::kVec;
+    return t0 < nz ? (uint32_t)((nz - t0) < (uint64_t)T ? (nz - t0) : (uint64_t)T) : 0u;
+  };
+  auto next_valid = [&](uint32_t k, const uint4*& p, uint32_t& len) -> uint32_t {
+    for (; k < ksteps; k++)
+      if ((len = step(k, p)) != 0) return k;
+    len = 0;
+    return ksteps;
+  };
+  const uint4* cur_p = nullptr;
+  uint32_t cur_len = 0;
+  uint32_t k = next_valid(0, cur_p, cur_len);
+  if (tid == 0 && k < ksteps) bulk_load(raw0, cur_p, cur_len * RB, &mbar[0]);
   uint32_t it = 0;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-    const uint32_t tn = tile_len(tile);
+  for (; k < ksteps; it++) {
+    const uint32_t tn = cur_len;
     const uint4* raw = (it & 1) ? raw1 : raw0;
     // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
-    const uint64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles)
-      bulk_load((it & 1) ? raw0 : raw1, src + next * T * R::kVec, tile_len(next) * RB, &mbar[(it & 1) ^ 1]);
+    const uint32_t knext = next_valid(k + 1, cur_p, cur_len);
+    if (tid == 0 && knext < ksteps) bulk_load((it & 1) ? raw0 : raw1, cur_p, cur_len * RB, &mbar[(it & 1) ^ 1]);
+    k = knext;
     mbar_wait(&mbar[it & 1], (it >> 1) & 1);
     uint32_t sub[U], rk[U];
 #pragma unroll
@@ -621,7 +658,7 @@ __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict
 //  * Every CTA keeps an open-addressing table in SHARED memory for its lifetime: hot keys (Zipf) are summed
 //    there with shared-memory atomics and never travel further.
 //  * Whatever does not find a place there -- the long tail -- is added to ONE open-addressing table in GLOBAL
-//    memory sized to stay resident in the 126 MB L2 (2^21 32-byte entries = 64 MB): one L2 atomic per pair
+//    memory sized to stay resident in the 126 MB L2 (2^21 16-byte entries = 32 MB): one L2 atomic per pair
 //    instead of a partition pass, a sort pass and a reduce pass over that pair.  At its end every CTA flushes
 //    its shared table into the global one; k_gtab_compact then emits one record per table entry.
 // The result (one record per distinct key, in the common case) is what the partition/sort/reduce stages see.
@@ -707,18 +744,25 @@ __device__ __forceinline__ void load_rec_hint(const uint4* p, uint32_t* w, uint6
   }
 }
 
-// adds (key of w, v) to the global table.  Entry = one record slot: strings {key words, u32 state}, state =
-// 0 empty / kCombineLock being written / sum + 1; u64 keys {u64 key, u64 state} with the same encoding.
-// WARP-COLLECTIVE: all 32 lanes call it (active = this lane has a pair) and walk the probe sequence together --
-// lanes that are done idle inside the loop instead of leaving it, because fragments of a warp that left a
-// data-dependent loop at different trips do not reconverge and every fragment would run the walk, a chain of
-// L2 round trips, on its own.
-// CHECKED: use the returned old value to catch a u32 sum about to wrap (otherwise the add is fire-and-forget
-// and the caller has bounded the sums: pairs x largest value < 2^32).
-// Entries of 16 / 32 bytes are read with ONE round of independent 16-byte loads (state included).  Such a
-// snapshot may pair a published state with key words from before the publication (zeros): that can only look
-// like a match for a key whose leading 16 bytes are all zero, so those keys take the two-step path (state,
-// then key) that the larger record classes always take.
+// ---- the global table --------------------------------------------------------------------------------------
+// 2^glog SHORT entries of 16 bytes in buckets of four (one 64-byte, two-sector read probes a whole bucket):
+//   string keys of up to 12 bytes: {key word 0, 1, 2, u32 state}        u64 keys: {u64 key, u64 state}
+// state = 0 empty / all ones being written / sum + 1.  An entry is one aligned 16-byte vector: it is claimed with
+// a CAS on the state, written (key + lock) with one vector store, published with an exchange of the state after a
+// fence, and read with one vector load -- a reader that sees a published state sees its key.
+// String keys longer than 12 bytes (rare in word counts) go to 2^(glog-4) LONG entries of one record slot each
+// behind the short ones, walked entry by entry (state first, then the key).
+// A warp walks the table TOGETHER (all 32 lanes call, active = this lane has a pair; lanes that are done idle
+// inside the loop): fragments of a warp that leave a data-dependent loop at different trips do not reconverge,
+// and each would pay its chain of L2 round trips alone.  With one-entry probes the walk took as long as its
+// unluckiest lane (5-6 round trips at load 0.5); a four-entry bucket almost always settles in the first.
+// CHECKED: use the returned old value to catch a u32 sum about to wrap (otherwise the add is fire-and-forget and
+// the caller has bounded the sums: pairs x largest value < 2^32).
+__host__ __device__ inline uint64_t gtab_bytes(int rb, uint32_t glog) {
+  return ((uint64_t)16 << glog) + (rb == 16 ? 0ull : ((uint64_t)rb << (glog - 4)));
+}
+constexpr int kGtabMaxBuckets = 32;
+
 template <int RB, bool CHECKED>
 __device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint64_t v,
                                          uint32_t h, uint32_t* __restrict__ flags, uint64_t pol) {
@@ -728,66 +772,117 @@ __device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gta
   g ^= g >> 12;
   g *= 0x297A2D39u;
   g ^= g >> 15;
-  const uint32_t mask = (1u << glog) - 1u;
-  uint32_t slot = g >> (32 - glog);
+  const uint32_t bmask = (1u << (glog - 2)) - 1u;
+  uint32_t b = g >> (32 - (glog - 2));
   bool done = !active;
   if constexpr (R::kU64) {
     const unsigned long long key = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32), lock = ~0ull;
 #pragma unroll 1
-    for (int probe = 0; probe < kGtabMaxProbes; probe++) {
+    for (int probe = 0; probe < kGtabMaxBuckets; probe++) {
       if (__all_sync(0xffffffffu, done)) break;
       if (!done) {
-        unsigned long long* e = (unsigned long long*)gtab + 2 * (size_t)slot;
-        unsigned long long st, k;
-        {  // one 16-byte load: key and state (issued before anything looks at the record, which may still be in flight)
-          const uint4 x = ldv_v4((const uint4*)e, pol);
-          k = (unsigned long long)x.x | ((unsigned long long)x.y << 32);
-          st = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
-        }
-        if (st == 0) {
-          const unsigned long long old = atomicCAS(e + 1, 0ull, lock);
-          if (old == 0) {
-            *(volatile unsigned long long*)e = key;
-            __threadfence();
-            atomicExch(e + 1, v + 1ull);
-            done = true;
+        uint4* e = (uint4*)gtab + 4 * (size_t)b;
+        uint4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[i] = ldv_v4(e + i, pol);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (!done) {
+            unsigned long long* st_p = (unsigned long long*)(e + i) + 1;
+            unsigned long long st = (unsigned long long)x[i].z | ((unsigned long long)x[i].w << 32);
+            unsigned long long k = (unsigned long long)x[i].x | ((unsigned long long)x[i].y << 32);
+            if (st == 0) {
+              const unsigned long long old = atomicCAS(st_p, 0ull, lock);
+              if (old == 0) {
+                stv_v4(e + i, make_uint4(w[0], w[1], 0xffffffffu, 0xffffffffu), pol);
+                __threadfence();
+                atomicExch(st_p, v + 1ull);
+                done = true;
+              }
+              st = lock;  // (somebody else's: look at it again)
+            }
+            if (!done) {
+              while (st == lock) {
+                const uint4 y = ldv_v4(e + i, pol);
+                k = (unsigned long long)y.x | ((unsigned long long)y.y << 32);
+                st = (unsigned long long)y.z | ((unsigned long long)y.w << 32);
+              }
+              if (k == key) {
+                if (v) red_add_u64(st_p, (unsigned long long)v, pol);
+                done = true;
+              }
+            }
           }
-          st = old;
         }
-        if (!done) {
-          if (st == lock || key == 0) {  // published meanwhile (or the zero key): read the key after the state
-            while (st == lock) st = ldv_u64(e + 1, pol);
-            k = ldv_u64(e, pol);
-          }
-          if (k == key) {
-            if (v) red_add_u64(e + 1, (unsigned long long)v, pol);
-            done = true;
-          }
-        }
-        slot = (slot + 1) & mask;
+        b = (b + 1) & bmask;
       }
     }
   } else {
+    bool is_short = true;
+#pragma unroll
+    for (int k = 3; k < KW; k++) is_short = is_short && w[k] == 0;
     if (!done && v >= 0xfffffff0ull) {
       atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
       done = true;
     }
     const uint32_t v32 = (uint32_t)v;
-    const bool snapshot_ok = RB == 32 && (w[0] | w[1] | w[2] | w[3]) != 0;
+    auto add = [&](uint32_t* st_p) {
+      if (!v32) return;
+      if (CHECKED) {
+        const uint32_t old = atomicAdd(st_p, v32);
+        if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+      } else {
+        red_add_u32(st_p, v32, pol);
+      }
+    };
+    bool sdone = done || !is_short;
 #pragma unroll 1
-    for (int probe = 0; probe < kGtabMaxProbes; probe++) {
-      if (__all_sync(0xffffffffu, done)) break;
-      if (!done) {
-        uint32_t* e = gtab + (size_t)slot * W;
-        uint4 x[R::kVec];
-        uint32_t st;
-        if (RB == 32) {  // (issued before anything looks at w: the record itself may still be in flight)
+    for (int probe = 0; probe < kGtabMaxBuckets; probe++) {
+      if (__all_sync(0xffffffffu, sdone)) break;
+      if (!sdone) {
+        uint4* e = (uint4*)gtab + 4 * (size_t)b;
+        uint4 x[4];
 #pragma unroll
-          for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i, pol);
-          st = x[R::kVec - 1].w;
-        } else {
-          st = ldv_u32(e + KW, pol);
+        for (int i = 0; i < 4; i++) x[i] = ldv_v4(e + i, pol);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (!sdone) {
+            uint32_t* st_p = (uint32_t*)(e + i) + 3;
+            uint4 y = x[i];
+            if (y.w == 0) {
+              const uint32_t old = atomicCAS(st_p, 0u, kCombineLock);
+              if (old == 0) {
+                stv_v4(e + i, make_uint4(w[0], w[1], w[2], kCombineLock), pol);
+                __threadfence();
+                atomicExch(st_p, v32 + 1u);
+                sdone = true;
+              }
+              y.w = kCombineLock;  // (somebody else's: look at it again)
+            }
+            if (!sdone) {
+              while (y.w == kCombineLock) y = ldv_v4(e + i, pol);
+              if (y.x == w[0] && y.y == w[1] && y.z == w[2]) {
+                add(st_p);
+                sdone = true;
+              }
+            }
+          }
         }
+        b = (b + 1) & bmask;
+      }
+    }
+    if (is_short && !sdone) atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
+    // long keys: one record slot per entry, state first, then the key
+    uint32_t* ltab = gtab + ((size_t)4 << glog);
+    const uint32_t lmask = (1u << (glog - 4)) - 1u;
+    uint32_t slot = g >> (32 - (glog - 4));
+    bool ldone = done || is_short;
+#pragma unroll 1
+    for (int probe = 0; probe < 4 * kGtabMaxBuckets; probe++) {
+      if (__all_sync(0xffffffffu, ldone)) break;
+      if (!ldone) {
+        uint32_t* e = ltab + (size_t)slot * W;
+        uint32_t st = ldv_u32(e + KW, pol);
         if (st == 0) {
           const uint32_t old = atomicCAS(e + KW, 0u, kCombineLock);
           if (old == 0) {
@@ -796,35 +891,28 @@ __device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gta
               stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]), pol);
             __threadfence();
             atomicExch(e + KW, v32 + 1u);
-            done = true;
+            ldone = true;
           }
-          st = old;
+          st = kCombineLock;
         }
-        if (!done) {
-          if (st == kCombineLock || !snapshot_ok) {  // read the key after the (published) state
-            while (st == kCombineLock) st = ldv_u32(e + KW, pol);
-#pragma unroll
-            for (int i = 0; i < R::kVec; i++) x[i] = ldv_v4((const uint4*)e + i, pol);
-          }
+        if (!ldone) {
+          while (st == kCombineLock) st = ldv_u32(e + KW, pol);
           bool eq = true;
 #pragma unroll
-          for (int i = 0; i < R::kVec; i++)
-            eq = eq && x[i].x == w[4 * i] && x[i].y == w[4 * i + 1] && x[i].z == w[4 * i + 2] && (4 * i + 3 == KW || x[i].w == w[4 * i + 3]);
+          for (int i = 0; i < R::kVec; i++) {
+            const uint4 y = ldv_v4((const uint4*)e + i, pol);
+            eq = eq && y.x == w[4 * i] && y.y == w[4 * i + 1] && y.z == w[4 * i + 2] && (4 * i + 3 == KW || y.w == w[4 * i + 3]);
+          }
           if (eq) {
-            if (v32) {
-              if (CHECKED) {
-                const uint32_t old = atomicAdd(e + KW, v32);
-                if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
-              } else {
-                red_add_u32(e + KW, v32, pol);
-              }
-            }
-            done = true;
+            add(e + KW);
+            ldone = true;
           }
         }
-        slot = (slot + 1) & mask;
+        slot = (slot + 1) & lmask;
       }
     }
+    if (!is_short && !ldone) atomicOr(flags, (uint32_t)ERRF_SKEW);
+    return;
   }
   if (!done) atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
 }
@@ -863,69 +951,90 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
     if (active) load_rec_hint<RB>(recs + (size_t)qe.x * R::kVec, w, pol.stream);  // (an L2 hit, in flight with the first probe)
     gtab_add<RB, CHECKED>(active, gtab, glog, w, rec_value<RB>(w), qe.y, flags, pol.keep);
   };
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t n_round = (n + 31) / 32 * 32;
-  // The pair of the NEXT trip is requested before this one is processed: with 32 warps per SM (the table takes the
-  // shared memory, the register file caps the CTA at 1024 threads) the DRAM latency is otherwise exposed between
-  // every two pairs of a thread (ncu: half of the stall samples waited for these loads).
-  uint32_t wn[W];
-  {
-    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + tid;
-    if (i0 < n) load_rec_hint<RB>(recs + i0 * R::kVec, wn, pol.stream);
-  }
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n_round; i += stride) {
-    uint32_t w[W];
-    bool need = i < n;
+  // every CTA streams ONE contiguous slice of the pairs (a grid-wide stride would walk each CTA through a new
+  // 2 MB page every trip: 148 CTAs x 4.8 MB apart, far beyond the TLB reach)
+  const uint64_t stride = blockDim.x;
+  const uint64_t slice = ((n + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+  const uint64_t slice_lo = slice * blockIdx.x < n ? slice * blockIdx.x : n;
+  const uint64_t slice_hi = slice_lo + slice < n ? slice_lo + slice : n;  // (this CTA's pairs: [slice_lo, slice_hi))
+  // TWO pairs per thread and trip, phase by phase (loads, tags, key words, adds): with 32 warps per SM -- the table
+  // takes the shared memory, the register file caps the CTA at 1024 threads -- every dependent wait (DRAM, then
+  // shared memory twice) is otherwise exposed; two independent chains per thread halve that (ncu: 25 % issue
+  // utilisation, 70 % of the stall samples on scoreboards, before).  All of it is straight-line, predicated code: a
+  // probe loop that lanes leave at different trips falls apart into fragments that do not reconverge inside it.
+  constexpr int J = RB <= 32 ? 2 : 1;  // (two 64- or 128-byte records do not fit the 64 registers a 1024-thread CTA leaves)
+  const uint64_t n_round2 = slice_lo + (slice_hi - slice_lo + 31) / 32 * 32;  // (lanes of a warp stay together: ballots inside)
+  for (uint64_t i = slice_lo + tid; i < n_round2; i += J * stride) {
+    uint32_t w[J][W], h[J], t0[J], t1[J], s0[J], s1[J];
+    uint64_t v[J];
+    bool need[J], live[J], hit[J];
 #pragma unroll
-    for (int k = 0; k < W; k++) w[k] = wn[k];
-    if (i + stride < n) load_rec_hint<RB>(recs + (i + stride) * R::kVec, wn, pol.stream);
-    const uint64_t v = need ? rec_value<RB>(w) : 0ull;
-    vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
-    // Straight-line, predicated code: a probe loop that lanes leave at different trips falls apart into fragments
-    // that do not reconverge inside it, and every fragment then waits for shared memory on its own.
-    const uint32_t h = slot_hash<RB>(w);
-    if (need && v != 0 && v <= vcap) {  // (a zero would still have to create its key: left to the global table)
-      const uint32_t tg = h | 2u;
-      const uint32_t s0 = __umulhi(h, entries), s1 = s0 + 1 == entries ? 0u : s0 + 1;
-      const uint32_t t0 = ((volatile uint32_t*)tag)[s0], t1 = ((volatile uint32_t*)tag)[s1];
-      if (t0 == tg || t1 == tg) {
-        const uint32_t sl = t0 == tg ? s0 : s1;
-        uint32_t x[KC];
+    for (int j = 0; j < J; j++) {
+      need[j] = i + j * stride < slice_hi;
+      if (need[j]) load_rec_hint<RB>(recs + (i + j * stride) * R::kVec, w[j], pol.stream);
+    }
 #pragma unroll
-        for (int k = 0; k < KC; k++) x[k] = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl];
+    for (int j = 0; j < J; j++) {
+      v[j] = need[j] ? rec_value<RB>(w[j]) : 0ull;
+      vmax = max(vmax, (uint32_t)(v[j] > 0xffffffffull ? 0xffffffffull : v[j]));
+      h[j] = slot_hash<RB>(w[j]);
+      live[j] = need[j] && v[j] != 0 && v[j] <= vcap;  // (a zero would still have to create its key: left to the global table)
+      s0[j] = __umulhi(h[j], entries);
+      s1[j] = s0[j] + 1 == entries ? 0u : s0[j] + 1;
+    }
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      t0[j] = live[j] ? ((volatile uint32_t*)tag)[s0[j]] : 1u;
+      t1[j] = live[j] ? ((volatile uint32_t*)tag)[s1[j]] : 1u;
+    }
+    uint32_t x[J][KC], sl[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const uint32_t tg = h[j] | 2u;
+      hit[j] = live[j] && (t0[j] == tg || t1[j] == tg);
+      sl[j] = t0[j] == tg ? s0[j] : s1[j];
+#pragma unroll
+      for (int k = 0; k < KC; k++) x[j][k] = hit[j] ? ((volatile uint32_t*)key)[(uint32_t)k * entries + sl[j]] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      if (hit[j]) {
         bool eq = true;
 #pragma unroll
-        for (int k = 0; k < KC; k++) eq = eq && x[k] == w[k];
-        if (KW > KC && eq && (w[KC - 1] >> 24) != 0) {  // 12 bytes or longer (rare): the remaining words, one by one
+        for (int k = 0; k < KC; k++) eq = eq && x[j][k] == w[j][k];
+        if (KW > KC && eq && (w[j][KC - 1] >> 24) != 0) {  // 12 bytes or longer (rare): the remaining words, one by one
 #pragma unroll
           for (int k = KC; k < KW; k++)  // (unrolled: a run-time index into w[] would move the record to local memory)
-            if (eq) eq = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl] == w[k];
+            if (eq) eq = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl[j]] == w[j][k];
         }
         if (eq) {
-          atomicAdd(val + sl, (uint32_t)v);
-          need = false;
+          atomicAdd(val + sl[j], (uint32_t)v[j]);
+          need[j] = false;
         }  // (same hash, other key: the pair goes to the global table, which is allowed to hold a key twice)
-      } else if (t0 == 0 || t1 == 0) {  // claim the empty slot (the table fills early in the kernel's life; then rare)
-        const uint32_t sl = t0 == 0 ? s0 : s1;
-        if (atomicCAS(tag + sl, 0u, 1u) == 0u) {
+      } else if (live[j] && (t0[j] == 0 || t1[j] == 0)) {  // claim the empty slot (the table fills early; then rare)
+        const uint32_t se = t0[j] == 0 ? s0[j] : s1[j];
+        if (atomicCAS(tag + se, 0u, 1u) == 0u) {
 #pragma unroll
-          for (int k = 0; k < KW; k++) key[(uint32_t)k * entries + sl] = w[k];
-          val[sl] = (uint32_t)v;
+          for (int k = 0; k < KW; k++) key[(uint32_t)k * entries + se] = w[j][k];
+          val[se] = (uint32_t)v[j];
           __threadfence_block();
-          atomicExch(tag + sl, tg);
-          need = false;
+          atomicExch(tag + se, h[j] | 2u);
+          need[j] = false;
         }
       }
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, need);
-    if (m) {
-      if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, h);
-      qn += __popc(m);
-      __syncwarp();
-      if (qn >= 32) {
-        qn -= 32;
-        to_gtab(true, q[qn + lane]);
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, need[j]);
+      if (m) {
+        if (need[j]) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(i + j * stride), h[j]);
+        qn += __popc(m);
         __syncwarp();
+        if (qn >= 32) {
+          qn -= 32;
+          to_gtab(true, q[qn + lane]);
+          __syncwarp();
+        }
       }
     }
   }
@@ -945,33 +1054,47 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   if (lane == 0 && vmax) atomicMax(flags + 2, vmax);
 }
 
-// one record per non-empty entry of the global table, appended to out (order unspecified)
+// one record per non-empty entry of the global table (short entries first, then the long ones), appended to out
 template <int RB>
 __global__ void __launch_bounds__(256) k_gtab_compact(const uint32_t* __restrict__ gtab, uint32_t glog, uint4* __restrict__ out,
                                                       uint32_t* __restrict__ count) {
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
-  const uint32_t slots = 1u << glog, lane = threadIdx.x & 31;
-  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < slots; base += gridDim.x * blockDim.x) {
-    const uint32_t s = base + lane;
+  const uint32_t nshort = 1u << glog, nlong = R::kU64 ? 0u : 1u << (glog - 4), lane = threadIdx.x & 31;
+  const uint32_t* ltab = gtab + ((size_t)4 << glog);
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < nshort + nlong; base += gridDim.x * blockDim.x) {
+    const uint32_t s = base + lane;  // (nshort and nlong are multiples of 32: a warp never straddles the two tables)
     uint32_t w[W];
-    const uint4* e = (const uint4*)(gtab + (size_t)s * W);
 #pragma unroll
-    for (int i = 0; i < R::kVec; i++) {
-      const uint4 x = e[i];
-      w[4 * i] = x.x;
-      w[4 * i + 1] = x.y;
-      w[4 * i + 2] = x.z;
-      w[4 * i + 3] = x.w;
-    }
+    for (int k = 0; k < W; k++) w[k] = 0;
     bool has;
-    if constexpr (R::kU64) {
-      unsigned long long st = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
-      has = st != 0;
-      st -= 1ull;
-      w[2] = (uint32_t)st;
-      w[3] = (uint32_t)(st >> 32);
+    if (s < nshort) {
+      const uint4 x = ((const uint4*)gtab)[s];
+      if constexpr (R::kU64) {
+        unsigned long long st = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
+        has = st != 0;
+        st -= 1ull;
+        w[0] = x.x;
+        w[1] = x.y;
+        w[2] = (uint32_t)st;
+        w[3] = (uint32_t)(st >> 32);
+      } else {
+        has = x.w != 0;
+        w[0] = x.x;
+        w[1] = x.y;
+        w[2] = x.z;
+        w[KW] = x.w - 1u;
+      }
     } else {
+      const uint4* e = (const uint4*)(ltab + (size_t)(s - nshort) * W);
+#pragma unroll
+      for (int i = 0; i < R::kVec; i++) {
+        const uint4 x = e[i];
+        w[4 * i] = x.x;
+        w[4 * i + 1] = x.y;
+        w[4 * i + 2] = x.z;
+        w[4 * i + 3] = x.w;
+      }
       has = w[KW] != 0;
       w[KW] -= 1u;
     }
@@ -1236,11 +1359,7 @@ int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint3
   }
   return 1;
 }
-uint32_t gtab_log_slots(int rb, uint64_t bytes) {
-  uint32_t l = 5;
-  while (l < 28 && ((uint64_t)rb << (l + 1)) <= bytes) l++;
-  return l;
-}
+uint64_t gtab_bytes_host(int rb, uint32_t glog) { return gtab_bytes(rb, glog); }
 int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
                    int sm_count, cudaStream_t s) {
   if (!n) return 0;
@@ -1256,7 +1375,7 @@ int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_
   return 1;
 }
 int launch_gtab_compact(int rb, const uint32_t* gtab, uint32_t glog, void* out, uint32_t* count, cudaStream_t s) {
-  const uint32_t slots = 1u << glog;
+  const uint32_t slots = (1u << glog) + (rb == 16 ? 0u : 1u << (glog - 4));
   int grid = (int)std::min<uint32_t>((slots + 255) / 256, (uint32_t)g_sm_count * 8);
   DISPATCH_RB(rb, (k_gtab_compact<RB><<<grid, 256, 0, s>>>(gtab, glog, (uint4*)out, count)));
   return 1;
@@ -1341,21 +1460,21 @@ int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream
   a.capacity = pl.cap;
   a.nbins = pl.F;
   a.level = 2;
-  // x CTAs per (region, sub-region), chosen so that all CTAs fill whole waves of `ctas` resident CTAs
+  // x CTAs per region (each takes every x-th tile of all the region's streams), chosen so that all CTAs fill whole waves of `ctas` resident CTAs
   // (C1 = 220, x = 2 ran 440 CTAs = 1.49 waves on 296 slots: 26 % of the second wave idle)
   int x = 1;
   double best = 0;
   const uint64_t region_recs = pl.base_off ? (uint64_t)pl.F * pl.cap : pl.sub_stride;
-  const uint64_t tiles = (region_recs * rb + kTmaTileBytes - 1) / kTmaTileBytes;
+  const uint64_t tiles = nsub * ((region_recs * rb + kTmaTileBytes - 1) / kTmaTileBytes);
   for (int cand = 1; cand <= 16 && (uint64_t)cand <= std::max<uint64_t>(1, tiles / 4); cand++) {
-    uint64_t total = (uint64_t)cand * regions * nsub, waves = (total + ctas - 1) / ctas;
+    uint64_t total = (uint64_t)cand * regions, waves = (total + ctas - 1) / ctas;
     double eff = (double)total / (double)(waves * ctas);
     if (eff > best + 0.02) {
       best = eff;
       x = cand;
     }
   }
-  DISPATCH_RB(rb, (k_split_tma<RB><<<dim3(x, regions, nsub), kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
+  DISPATCH_RB(rb, (k_split_tma<RB><<<dim3(x, regions), kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,

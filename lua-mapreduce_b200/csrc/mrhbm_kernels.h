@@ -106,15 +106,15 @@ int launch_tok_count(const unsigned char* text, uint64_t len, uint32_t* block_co
 int launch_tok_emit(int rb, const unsigned char* text, uint64_t len, const uint32_t* block_off, void* recs,
                     uint32_t* flags, cudaStream_t s);
 inline uint64_t tok_blocks(uint64_t len) { return (len + 255) / 256; }
-// map-side combine of one committed range into the global table gtab (2^glog record-sized entries, zeroed by
-// the caller); flags[0] |= ERRF_SKEW when the table is full, ERRF_OVERFLOW when a u32 sum would wrap (checked
+// map-side combine of one committed range into the global table gtab (2^glog 16-byte short entries + 2^(glog-4)
+// record-sized long ones = gtab_bytes_host(rb, glog) bytes, zeroed by the caller); flags[0] |= ERRF_SKEW when the table is full, ERRF_OVERFLOW when a u32 sum would wrap (checked
 // mode only: unchecked adds are fire-and-forget and the caller verifies afterwards that pairs x flags[2], the
 // largest value seen, stays below 2^32)
 int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
                    int sm_count, cudaStream_t s);
 // one record per non-empty table entry appended to out; *count (zeroed by the caller) += entries
 int launch_gtab_compact(int rb, const uint32_t* gtab, uint32_t glog, void* out, uint32_t* count, cudaStream_t s);
-uint32_t gtab_log_slots(int rb, uint64_t bytes);  // largest power of two of rb-byte entries within `bytes`
+uint64_t gtab_bytes_host(int rb, uint32_t glog);
 // tot[b] = sum over s < world of all[s * stride + base + b], b < n; *nover += bins (of all `stride`
 // bins) whose global total exceeds cap
 int launch_sum_src(const uint32_t* all, uint32_t world, uint32_t stride, uint32_t base, uint32_t n,

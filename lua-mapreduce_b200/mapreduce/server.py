@@ -56,8 +56,15 @@ class server:
             raise NotImplementedError("unknown hbm_reducefn %r (built-ins: 'sum')" % (builtin_red,))
         # no declaration = general reducer: the device partitions, sorts and groups, reducefn runs
         # on the host per group (job.lua:264-284); values are unsigned integers < 2^32
-        if "combinerfn" in mods and (builtin_red != "sum" or getattr(mods["combinerfn"], "hbm_reducefn", None) != "sum"):
-            raise NotImplementedError("a combinerfn runs on the device: it (and the reducefn) must declare hbm_reducefn = 'sum'")
+        # A combinerfn only ever runs on the device, as the declared built-in (it must equal the reducefn there).
+        # Any other combinerfn is SKIPPED: the reference's contract for it (job.lua:92-96,198-202) is that reducing
+        # combined values equals reducing the raw ones, so the reducefn -- on the device if it is the built-in, per
+        # group on the host otherwise -- sees the raw values and produces the same result, just without the saving.
+        device_combiner = "combinerfn" in mods and builtin_red == "sum" and \
+            getattr(mods["combinerfn"], "hbm_reducefn", None) == "sum"
+        if "combinerfn" in mods and not device_combiner:
+            sys.stderr.write("# WARNING: combinerfn %s is not a device built-in (hbm_reducefn = 'sum'); it is skipped, "
+                             "the reducefn sees the uncombined values\n" % params["combinerfn"])
         pname = getattr(part, "hbm_partitionfn", None)
         if pname not in _BUILTIN_PART:
             raise NotImplementedError("partitionfn module must declare hbm_partitionfn in %s" % sorted(_BUILTIN_PART))
@@ -65,7 +72,7 @@ class server:
         assert isinstance(nparts, int) and nparts >= 1, "partitionfn module must expose NUM_REDUCERS"
         hbm = dict(key_kind="str", max_key_bytes=123, device=-1)
         hbm.update(params.get("hbm") or {})
-        hbm.update(partitioner=_BUILTIN_PART[pname], num_partitions=nparts, combiner="combinerfn" in mods,
+        hbm.update(partitioner=_BUILTIN_PART[pname], num_partitions=nparts, combiner=device_combiner,
                    reducer=0 if builtin_red == "sum" else 1)
         self.config = dict(mapfn=params["mapfn"], reducefn=params["reducefn"], partitionfn=params["partitionfn"],
                            combinerfn=params.get("combinerfn"), init_args=self.init_args,

@@ -52,7 +52,19 @@ class worker:
             job_done = True
 
     def execute(self):
-        """worker.lua:112-138"""
+        """worker.lua:112-138.  The worker registers itself on the board for the time it runs: the server only
+        executes jobs inline while no worker is attached, so the two never drive the shared ctx at once (the C
+        handle additionally serialises its callers with a per-ctx lock)."""
+        with self.board.cv:
+            self.board.workers += 1
+        try:
+            self._execute_with_retries()
+        finally:
+            with self.board.cv:
+                self.board.workers -= 1
+                self.board.cv.notify_all()
+
+    def _execute_with_retries(self):
         failed = set()
         while True:
             try:

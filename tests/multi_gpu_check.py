@@ -1,6 +1,7 @@
 """Launched by torchrun (one rank per GPU) from tests/test_gpu_multi.py and profiles/*.sh:
-the sharded shuffle (count all-gather + NCCL all-to-all + per-rank sort/reduce) must give the
-oracle's result for the union of all ranks' pairs, with partition p living on rank p % world."""
+the sharded shuffle (level-1 split into rank-aligned regions, level 2 of the owner pulling its regions from every
+peer over NVLink, per-rank sort/reduce; the exact-layout NCCL path for skewed keys) must give the oracle's result
+for the union of all ranks' pairs, with partition p living on rank p % world."""
 import os
 import sys
 
@@ -79,15 +80,15 @@ def run_u64(rank, world, n_per, P, flags=0, dup=False):
             want = [(int(np.searchsorted(po, i, side="right")) - 1, int(ok[i]).to_bytes(8, "big"), [int(osum[i])])
                     for i in range(ok.size)]
             check("finalfn order over all ranks", pairs == want)
-        print("u64 world=%d n/rank=%d P=%d dup=%s ok: groups=%d sorted=%s big_bins=%s exch=%.3f ms %.1f MB"
+        print("u64 world=%d n/rank=%d P=%d dup=%s ok: groups=%d sorted=%s big_bins=%s attempts=%s bins=%d pulled %.1f MB"
               % (world, n_per, P, dup, ok.size, [b[5] for b in box], [b[7]["big_bins"] for b in box],
-                 box[0][7]["ms_exchange"], box[0][7]["bytes_exchanged"] / 1e6), flush=True)
+                 [b[7]["attempts"] for b in box], box[0][7]["bins"], box[0][7]["bytes_exchanged"] / 1e6), flush=True)
 
 
-def run_zipf(rank, world, n_per, P):
+def run_zipf(rank, world, n_per, P, combiner=False):
     import oracle as O
     table = synth.zipf_table(1 << 14)
-    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, device=int(os.environ["LOCAL_RANK"])) as ctx:
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, device=int(os.environ["LOCAL_RANK"]), combiner=combiner) as ctx:
         parallel.init_comm(ctx, dist)
         m = ctx.map_begin("r%d" % rank)
         m.gen_zipf(synth.SEED, rank * n_per, n_per, table)
@@ -102,8 +103,8 @@ def run_zipf(rank, world, n_per, P):
         want = [(int(np.searchsorted(po, i, side="right")) - 1, bytes(okeys[i]).rstrip(b"\0"), [int(osum[i])])
                 for i in range(osum.size)]
         check("zipf word count over all ranks", pairs == want)
-        print("zipf world=%d n/rank=%d P=%d ok: groups=%d big_bins(rank0)=%d" % (world, n_per, P, osum.size, st["big_bins"]),
-              flush=True)
+        print("zipf world=%d n/rank=%d P=%d combiner=%s ok: groups=%d big_bins(rank0)=%d attempts=%d"
+              % (world, n_per, P, combiner, osum.size, st["big_bins"], st["attempts"]), flush=True)
 
 
 def main():
@@ -114,9 +115,11 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     run_u64(rank, world, 100_000, 16)
     run_u64(rank, world, 1_000_000, 1024)
+    run_u64(rank, world, 6_000_000, 1024)                # several tiles per (region, source): the level-2 pulls in earnest
     run_u64(rank, world, 200_000, 7, dup=True)           # P not a multiple of world, hot key
     run_u64(rank, world, 150_000, 3, flags=mrhbm.F_FORCE_RUNS)
     run_zipf(rank, world, 200_000, 15)
+    run_zipf(rank, world, 1_500_000, 15, combiner=True)  # local combine (global table) on every rank, then the exchange
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world=%d" % world, flush=True)

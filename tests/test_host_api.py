@@ -3,6 +3,7 @@ lua-mapreduce_b200/mapreduce: test.sh's four plugin configurations against misc/
 answer (the golden word count).  CPU tests run the host logic over a stand-in ctx (tests only);
 the gpu-marked tests run the same scripts over the CUDA path."""
 import threading
+import time
 
 import pytest
 
@@ -94,9 +95,13 @@ def run_config(name, dbname, ctx_factory=None, with_worker=False):
     if with_worker:
         w = worker.new("hbm://local", dbname)
         w.configure({"max_iter": 2000, "max_tasks": 1})
-        s.board.workers += 1
         th = threading.Thread(target=w.execute, daemon=True)
         th.start()
+        for _ in range(2000):  # the worker registers itself on the board (worker.execute); wait for that
+            if s.board.workers > 0:
+                break
+            time.sleep(0.001)
+        assert s.board.workers == 1
     s.loop()
     if th:
         th.join(timeout=60)
@@ -214,6 +219,25 @@ def test_general_reducer_runs_on_the_host_over_device_groups(corpus, golden_word
     s.loop()
     assert got == {k: [1, sum(c)] for k, _, c in golden_wordcount}
     s.board.ctx.close()
+
+
+def test_undeclared_combinerfn_is_skipped_not_refused(corpus, golden_wordcount):
+    """a combinerfn that is not the device built-in (no hbm_reducefn = 'sum'): configure() no longer raises; the
+    combiner -- an optimisation whose contract is "reduce(combined) == reduce(raw)" (job.lua:92-96,198-202) -- is
+    skipped and the reducefn sees the raw values"""
+    import sys
+    import types
+    mod = types.ModuleType("my_combinerfn")
+    mod.init = lambda a=None: None
+    mod.combinerfn = lambda key, values, emit: emit(sum(values))
+    sys.modules["my_combinerfn"] = mod
+    s = server.new("hbm://local", "cpu-undeclared-combiner")
+    s.ctx_factory = StandInCtx
+    s.configure(dict(taskfn=WC + ".taskfn", mapfn=WC + ".mapfn", partitionfn=WC + ".partitionfn", reducefn=WC + ".reducefn",
+                     combinerfn="my_combinerfn", finalfn=WC + ".finalfn", storage="hbm"))
+    assert s.config["hbm"]["combiner"] is False and s.config["hbm"]["reducer"] == 0
+    s.loop()
+    assert WordCount.RESULT == {k: sum(c) for k, _, c in golden_wordcount}
 
 
 def test_exported_result_files_equal_the_oracles(corpus, golden_wordcount, tmp_path):

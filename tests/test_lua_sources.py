@@ -136,3 +136,14 @@ def test_double_codec_edge_values():
         hi, lo = double_to_words(x)
         assert (int(hi), int(lo)) == struct.unpack(">II", struct.pack(">d", x)), x
         assert words_to_double(int(hi), int(lo)) == x
+
+
+def test_lua_c_module_type_checks_against_lua52_prototypes():
+    """mrhbm_lua.c cannot be built here (no lua.h).  With DECLARATIONS of the Lua 5.2 C API subset it uses
+    (tests/native/lua_stub, written from the reference manual) gcc -fsyntax-only checks every call against
+    include/mrhbm.h and the Lua prototypes: argument counts, types, undeclared names."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-std=gnu99",
+                        "-I" + os.path.join(ROOT, "tests", "native", "lua_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(LUA_DIR, "mrhbm_lua.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
