@@ -393,14 +393,13 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   __syncthreads();
   uint32_t ntmax = 0;
   for (uint32_t z = 0; z < nsrc; z++) ntmax = max(ntmax, (s_n[z] + T - 1) / T);
-  // a CTA takes a CONTIGUOUS range of tiles of every stream (tiles x, x + gridDim.x, ... would walk it through a
-  // new 2 MB page per tile, 296 CTAs x 12 MB apart: beyond the TLB reach)
-  const uint32_t rounds = (ntmax + gridDim.x - 1) / gridDim.x;
+  // (tiles x, x + gridDim.x, ...: a contiguous range of tiles per CTA measured 4 % slower)
+  const uint32_t rounds = ntmax > blockIdx.x ? (ntmax - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
   const uint32_t ksteps = rounds * nsrc;
-  // step k of this CTA: round k / nsrc, stream (k % nsrc + blockIdx.x + me) % nsrc, tile blockIdx.x * rounds + round
+  // step k of this CTA: round k / nsrc, stream (k % nsrc + blockIdx.x + me) % nsrc, tile blockIdx.x + round * gridDim.x
   auto step = [&](uint32_t k, const uint4*& p) -> uint32_t {
     const uint32_t r = k / nsrc, z = (k - r * nsrc + blockIdx.x + a.me) % nsrc;
-    const uint64_t t0 = (uint64_t)(blockIdx.x * rounds + r) * T;
+    const uint64_t t0 = (uint64_t)(blockIdx.x + r * gridDim.x) * T;
     const uint32_t nz = s_n[z];
     p = (const uint4*)(uintptr_t)s_src[z] + t0 * R::kVec;
     return t0 < nz ? (uint32_t)((nz - t0) < (uint64_t)T ? (nz - t0) : (uint64_t)T) : 0u;
@@ -668,8 +667,7 @@ __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict
 // the combiner; a u32 sum about to wrap raises ERRF_OVERFLOW (string records carry u32 values).
 constexpr uint32_t kCombineLock = 0xffffffffu;
 constexpr int kCombineThreads = 1024;
-constexpr int kCombineSmem = 200 * 1024;
-constexpr int kGtabMaxProbes = 96;
+constexpr int kCombineSmem = 190 * 1024;  // (+ 32 KB of per-warp miss queues = 222 of the 227 KB)
 
 // cheap 32-bit hash of the key words (one IMAD per word); the shared table takes its top bits, the global
 // table a remix of it
@@ -702,6 +700,11 @@ __device__ __forceinline__ uint4 ldg_stream_hint(const uint4* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
+}
+constexpr int kPrefetchTrips = 6;
+constexpr uint32_t kEpochTrips = 256;  // shared-table clean-up period: 256 trips = 262,144 pairs per CTA
 __device__ __forceinline__ uint32_t ldv_u32(const uint32_t* p, uint64_t pol) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
@@ -745,176 +748,133 @@ __device__ __forceinline__ void load_rec_hint(const uint4* p, uint32_t* w, uint6
 }
 
 // ---- the global table --------------------------------------------------------------------------------------
-// 2^glog SHORT entries of 16 bytes in buckets of four (one 64-byte, two-sector read probes a whole bucket):
+// 2^glog SHORT entries of 16 bytes, open addressing with linear probing, ONE entry per probe:
 //   string keys of up to 12 bytes: {key word 0, 1, 2, u32 state}        u64 keys: {u64 key, u64 state}
 // state = 0 empty / all ones being written / sum + 1.  An entry is one aligned 16-byte vector: it is claimed with
 // a CAS on the state, written (key + lock) with one vector store, published with an exchange of the state after a
 // fence, and read with one vector load -- a reader that sees a published state sees its key.
 // String keys longer than 12 bytes (rare in word counts) go to 2^(glog-4) LONG entries of one record slot each
-// behind the short ones, walked entry by entry (state first, then the key).
-// A warp walks the table TOGETHER (all 32 lanes call, active = this lane has a pair; lanes that are done idle
-// inside the loop): fragments of a warp that leave a data-dependent loop at different trips do not reconverge,
-// and each would pay its chain of L2 round trips alone.  With one-entry probes the walk took as long as its
-// unluckiest lane (5-6 round trips at load 0.5); a four-entry bucket almost always settles in the first.
+// behind the short ones, walked entry by entry by the whole warp (state first, then the key).
+// Why one 16-byte entry per probe: a random L2 read costs the SM per REQUEST, not per byte
+// (profiles/microbench/gather_l2.cu: 143 G 16-byte reads/s, 72 G 32-byte, 36 G 64-byte reads/s on the chip), and
+// a probe is never waited for: it is issued when 32 pairs have queued up and looked at when the next 32 have.
 // CHECKED: use the returned old value to catch a u32 sum about to wrap (otherwise the add is fire-and-forget and
 // the caller has bounded the sums: pairs x largest value < 2^32).
 __host__ __device__ inline uint64_t gtab_bytes(int rb, uint32_t glog) {
   return ((uint64_t)16 << glog) + (rb == 16 ? 0ull : ((uint64_t)rb << (glog - 4)));
 }
-constexpr int kGtabMaxBuckets = 32;
+constexpr uint32_t kGtabMaxProbes = 192;  // linear probes before the table counts as full
+constexpr int kGtabMaxLongProbes = 128;
 
-template <int RB, bool CHECKED>
-__device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint64_t v,
-                                         uint32_t h, uint32_t* __restrict__ flags, uint64_t pol) {
-  using R = Rec<RB>;
-  constexpr int W = R::kWords, KW = R::kKeyWords;
-  uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
-  g ^= g >> 12;
-  g *= 0x297A2D39u;
+// A pair on its way to the global table, 16 bytes: strings of up to 12 bytes {key word 0, 1, 2, u32 value},
+// u64 keys {key lo, key hi, value lo, value hi} -- also the layout of a short table entry (value -> state).
+template <int RB>
+__device__ __forceinline__ uint32_t gtab_slot(const uint4& E, uint32_t glog) {
+  uint32_t g = (E.x ^ 0x9E3779B9u) * 0x85EBCA6Bu;
+  g = (g ^ (g >> 15) ^ E.y) * 0x2C1B3C6Du;
+  if (!Rec<RB>::kU64) g = (g ^ (g >> 13) ^ E.z) * 0x297A2D39u;
+  g ^= g >> 16;
+  g *= 0xC2B2AE35u;
   g ^= g >> 15;
-  const uint32_t bmask = (1u << (glog - 2)) - 1u;
-  uint32_t b = g >> (32 - (glog - 2));
-  bool done = !active;
-  if constexpr (R::kU64) {
-    const unsigned long long key = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32), lock = ~0ull;
-#pragma unroll 1
-    for (int probe = 0; probe < kGtabMaxBuckets; probe++) {
-      if (__all_sync(0xffffffffu, done)) break;
-      if (!done) {
-        uint4* e = (uint4*)gtab + 4 * (size_t)b;
-        uint4 x[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) x[i] = ldv_v4(e + i, pol);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (!done) {
-            unsigned long long* st_p = (unsigned long long*)(e + i) + 1;
-            unsigned long long st = (unsigned long long)x[i].z | ((unsigned long long)x[i].w << 32);
-            unsigned long long k = (unsigned long long)x[i].x | ((unsigned long long)x[i].y << 32);
-            if (st == 0) {
-              const unsigned long long old = atomicCAS(st_p, 0ull, lock);
-              if (old == 0) {
-                stv_v4(e + i, make_uint4(w[0], w[1], 0xffffffffu, 0xffffffffu), pol);
-                __threadfence();
-                atomicExch(st_p, v + 1ull);
-                done = true;
-              }
-              st = lock;  // (somebody else's: look at it again)
-            }
-            if (!done) {
-              while (st == lock) {
-                const uint4 y = ldv_v4(e + i, pol);
-                k = (unsigned long long)y.x | ((unsigned long long)y.y << 32);
-                st = (unsigned long long)y.z | ((unsigned long long)y.w << 32);
-              }
-              if (k == key) {
-                if (v) red_add_u64(st_p, (unsigned long long)v, pol);
-                done = true;
-              }
-            }
-          }
-        }
-        b = (b + 1) & bmask;
-      }
+  return g >> (32 - glog);
+}
+// One probe of the short table: entry `e` as read into x.  Returns 0 = the pair is settled (added, or inserted into
+// the empty entry), 1 = the entry holds another key (probe the next one), 2 = the entry is being written (look again).
+template <int RB, bool CHECKED>
+__device__ __forceinline__ int gtab_probe(uint4* e, const uint4& x, const uint4& E, uint32_t* __restrict__ flags, uint64_t pol) {
+  if constexpr (Rec<RB>::kU64) {
+    unsigned long long* st_p = (unsigned long long*)e + 1;
+    const unsigned long long st = (unsigned long long)x.z | ((unsigned long long)x.w << 32), lock = ~0ull;
+    const unsigned long long v = (unsigned long long)E.z | ((unsigned long long)E.w << 32);
+    if (st == 0) {
+      if (atomicCAS(st_p, 0ull, lock) != 0ull) return 2;
+      stv_v4(e, make_uint4(E.x, E.y, 0xffffffffu, 0xffffffffu), pol);
+      __threadfence();
+      atomicExch(st_p, v + 1ull);
+      return 0;
     }
+    if (st == lock) return 2;
+    if (x.x != E.x || x.y != E.y) return 1;
+    if (v) red_add_u64(st_p, v, pol);
+    return 0;
   } else {
-    bool is_short = true;
-#pragma unroll
-    for (int k = 3; k < KW; k++) is_short = is_short && w[k] == 0;
-    if (!done && v >= 0xfffffff0ull) {
-      atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
-      done = true;
+    uint32_t* st_p = (uint32_t*)e + 3;
+    const uint32_t v32 = E.w;
+    if (x.w == 0) {
+      if (atomicCAS(st_p, 0u, kCombineLock) != 0u) return 2;
+      stv_v4(e, make_uint4(E.x, E.y, E.z, kCombineLock), pol);
+      __threadfence();
+      atomicExch(st_p, v32 + 1u);
+      return 0;
     }
-    const uint32_t v32 = (uint32_t)v;
-    auto add = [&](uint32_t* st_p) {
-      if (!v32) return;
+    if (x.w == kCombineLock) return 2;
+    if (x.x != E.x || x.y != E.y || x.z != E.z) return 1;
+    if (v32) {
       if (CHECKED) {
         const uint32_t old = atomicAdd(st_p, v32);
         if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
       } else {
         red_add_u32(st_p, v32, pol);
       }
-    };
-    bool sdone = done || !is_short;
-#pragma unroll 1
-    for (int probe = 0; probe < kGtabMaxBuckets; probe++) {
-      if (__all_sync(0xffffffffu, sdone)) break;
-      if (!sdone) {
-        uint4* e = (uint4*)gtab + 4 * (size_t)b;
-        uint4 x[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) x[i] = ldv_v4(e + i, pol);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (!sdone) {
-            uint32_t* st_p = (uint32_t*)(e + i) + 3;
-            uint4 y = x[i];
-            if (y.w == 0) {
-              const uint32_t old = atomicCAS(st_p, 0u, kCombineLock);
-              if (old == 0) {
-                stv_v4(e + i, make_uint4(w[0], w[1], w[2], kCombineLock), pol);
-                __threadfence();
-                atomicExch(st_p, v32 + 1u);
-                sdone = true;
-              }
-              y.w = kCombineLock;  // (somebody else's: look at it again)
-            }
-            if (!sdone) {
-              while (y.w == kCombineLock) y = ldv_v4(e + i, pol);
-              if (y.x == w[0] && y.y == w[1] && y.z == w[2]) {
-                add(st_p);
-                sdone = true;
-              }
-            }
-          }
-        }
-        b = (b + 1) & bmask;
-      }
     }
-    if (is_short && !sdone) atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
-    // long keys: one record slot per entry, state first, then the key
-    uint32_t* ltab = gtab + ((size_t)4 << glog);
-    const uint32_t lmask = (1u << (glog - 4)) - 1u;
-    uint32_t slot = g >> (32 - (glog - 4));
-    bool ldone = done || is_short;
-#pragma unroll 1
-    for (int probe = 0; probe < 4 * kGtabMaxBuckets; probe++) {
-      if (__all_sync(0xffffffffu, ldone)) break;
-      if (!ldone) {
-        uint32_t* e = ltab + (size_t)slot * W;
-        uint32_t st = ldv_u32(e + KW, pol);
-        if (st == 0) {
-          const uint32_t old = atomicCAS(e + KW, 0u, kCombineLock);
-          if (old == 0) {
-#pragma unroll
-            for (int i = 0; i < R::kVec; i++)  // the last vector rewrites the lock word with itself
-              stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]), pol);
-            __threadfence();
-            atomicExch(e + KW, v32 + 1u);
-            ldone = true;
-          }
-          st = kCombineLock;
-        }
-        if (!ldone) {
-          while (st == kCombineLock) st = ldv_u32(e + KW, pol);
-          bool eq = true;
-#pragma unroll
-          for (int i = 0; i < R::kVec; i++) {
-            const uint4 y = ldv_v4((const uint4*)e + i, pol);
-            eq = eq && y.x == w[4 * i] && y.y == w[4 * i + 1] && y.z == w[4 * i + 2] && (4 * i + 3 == KW || y.w == w[4 * i + 3]);
-          }
-          if (eq) {
-            add(e + KW);
-            ldone = true;
-          }
-        }
-        slot = (slot + 1) & lmask;
-      }
-    }
-    if (!is_short && !ldone) atomicOr(flags, (uint32_t)ERRF_SKEW);
-    return;
+    return 0;
   }
-  if (!done) atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
+}
+// WARP-COLLECTIVE: string keys longer than 12 bytes, one record slot per entry, state first, then the key
+template <int RB, bool CHECKED>
+__device__ __forceinline__ void gtab_add_long(bool active, uint32_t* __restrict__ gtab, uint32_t glog, const uint32_t* w, uint32_t v32,
+                                              uint32_t* __restrict__ flags, uint64_t pol) {
+  using R = Rec<RB>;
+  constexpr int W = R::kWords, KW = R::kKeyWords;
+  uint32_t* ltab = gtab + ((size_t)4 << glog);
+  const uint32_t lmask = (1u << (glog - 4)) - 1u;
+  uint32_t slot = slot_hash<RB>(w) >> (32 - (glog - 4));
+  bool ldone = !active;
+  if (!ldone && v32 >= 0xfffffff0u) {
+    atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+    ldone = true;
+  }
+#pragma unroll 1
+  for (int probe = 0; probe < kGtabMaxLongProbes; probe++) {
+    if (__all_sync(0xffffffffu, ldone)) break;
+    if (!ldone) {
+      uint32_t* e = ltab + (size_t)slot * W;
+      uint32_t st = ldv_u32(e + KW, pol);
+      if (st == 0) {
+        if (atomicCAS(e + KW, 0u, kCombineLock) == 0u) {
+#pragma unroll
+          for (int i = 0; i < R::kVec; i++)  // the last vector rewrites the lock word with itself
+            stv_v4((uint4*)e + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], 4 * i + 3 == KW ? kCombineLock : w[4 * i + 3]), pol);
+          __threadfence();
+          atomicExch(e + KW, v32 + 1u);
+          ldone = true;
+        }
+        st = kCombineLock;
+      }
+      if (!ldone) {
+        while (st == kCombineLock) st = ldv_u32(e + KW, pol);
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < R::kVec; i++) {
+          const uint4 y = ldv_v4((const uint4*)e + i, pol);
+          eq = eq && y.x == w[4 * i] && y.y == w[4 * i + 1] && y.z == w[4 * i + 2] && (4 * i + 3 == KW || y.w == w[4 * i + 3]);
+        }
+        if (eq) {
+          if (v32) {
+            if (CHECKED) {
+              const uint32_t old = atomicAdd(e + KW, v32);
+              if (old + v32 < old || old + v32 >= 0xfffffff0u) atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+            } else {
+              red_add_u32(e + KW, v32, pol);
+            }
+          }
+          ldone = true;
+        }
+      }
+      slot = (slot + 1) & lmask;
+    }
+  }
+  if (!ldone) atomicOr(flags, (uint32_t)ERRF_SKEW);
 }
 
 // flags[0] |= ERRF_*, flags[2] = max over the values seen (saturated to u32).
@@ -923,131 +883,186 @@ __device__ __forceinline__ void gtab_add(bool active, uint32_t* __restrict__ gta
 template <int RB, bool CHECKED>
 __global__ void __launch_bounds__(kCombineThreads, 1)
     k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t entries, uint32_t vcap, uint32_t* __restrict__ gtab,
-              uint32_t glog, uint32_t* __restrict__ flags) {
+              uint32_t glog, uint32_t* __restrict__ flags, uint32_t tune) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
-  constexpr int KC = KW < 3 ? KW : 3;  // key words a hit verifies at once (keys < 12 bytes end inside them)
+  constexpr int KC = KW < 3 ? KW : 3;  // key words of a shared-table entry: only keys of up to 12 bytes live there
   // Shared table, ARRAY PER FIELD (32 lanes probing 32 random entries hit 32 random banks, not the four a record
   // stride allows): tag[e] = 0 empty / 1 being written / the key's 32-bit hash with bit 1 set; val[e] = u32 partial
-  // sum; key[k][e] = key word k.  A probe reads two neighbouring tags; only a tag hit touches the key words.
+  // sum; key[k][e] = key word k < KC.  A probe reads two neighbouring tags; only a tag hit touches the key words.
+  // Longer keys (rare in a word count) bypass it: 20 bytes per entry instead of 36 buys 1.8 times the entries.
+  // Every kEpochTrips trips the CTA stops at a barrier and evicts the entries that gathered less than two pairs
+  // since they were admitted (into the global table, like a miss): the table is filled first come first served,
+  // and without that the keys that happened to arrive first would keep out warmer keys that arrived later.
   uint32_t* tag = (uint32_t*)smem_raw;
   uint32_t* val = tag + entries;
   uint32_t* key = val + entries;
-  // pairs that found no place in the shared table wait in a per-warp queue (record indices) until 32 of them are
-  // there: the global-table walk, a chain of L2 round trips, then runs with all lanes busy instead of the ~30 %
-  // that miss in one batch
-  __shared__ uint2 queue[kCombineThreads / 32][64];  // (record index, key hash): the walk starts without the record
+  // Pairs that found no place in the shared table queue up per warp as 16-byte compact entries (a ring of 64, with
+  // the number of the probe they are at).  When 32 are there the warp ISSUES their probes -- one 16-byte read per
+  // lane, into registers -- and goes on with the stream; it LOOKS at them when the next 32 are ready: a match is
+  // added to with a fire-and-forget red, an empty entry is claimed, anything else (another key: next probe; an
+  // entry being written: same probe) goes back into the ring.  Nothing ever waits for the table: the L2 round trip,
+  // microseconds with 32 warps per SM and nothing else to run, is spent on the stream (ncu, synchronous walk:
+  // 20-35 % of the stall samples waited for these reads, the walk taking as long as its unluckiest lane).
+  __shared__ uint4 queue[kCombineThreads / 32][64];
+  __shared__ uint8_t queue_probe[kCombineThreads / 32][64];
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   const L2Policy pol = l2_policies();
-  uint2* q = queue[tid >> 5];
-  uint32_t qn = 0, vmax = 0;
-  for (uint32_t i = tid; i < entries * (KW + 2); i += blockDim.x) tag[i] = 0;
+  uint4* q = queue[tid >> 5];
+  uint8_t* qp = queue_probe[tid >> 5];
+  uint32_t q_tail = 0, q_pend = 0;  // ring: [.. in flight ..][.. q_pend pending ..] tail
+  uint32_t fly_base = 0, fly_n = 0; // the batch in flight: fly_n entries from fly_base (0 = none)
+  uint4 fx;                         // ... this lane's probed table entry
+  uint32_t vmax = 0;
+  for (uint32_t i = tid; i < entries * (KC + 2); i += blockDim.x) tag[i] = 0;
   __syncthreads();
-  auto to_gtab = [&](bool active, uint2 qe) {
-    uint32_t w[W];
-#pragma unroll
-    for (int k = 0; k < W; k++) w[k] = 0;
-    if (active) load_rec_hint<RB>(recs + (size_t)qe.x * R::kVec, w, pol.stream);  // (an L2 hit, in flight with the first probe)
-    gtab_add<RB, CHECKED>(active, gtab, glog, w, rec_value<RB>(w), qe.y, flags, pol.keep);
+  const uint32_t gmask = (1u << glog) - 1u;
+  // tune (MRHBM_TUNE, measurement only, results invalid): 4 = misses are dropped
+  auto append = [&](bool p, const uint4& E, uint32_t probe) {  // collective: the entries of the lanes with p go to the tail
+    const uint32_t m = __ballot_sync(0xffffffffu, p);
+    if (p) {
+      const uint32_t at = (q_tail + __popc(m & ((1u << lane) - 1u))) & 63u;
+      q[at] = E;
+      qp[at] = (uint8_t)probe;
+    }
+    q_tail = (q_tail + __popc(m)) & 63u;
+    q_pend += __popc(m);
+    __syncwarp();
   };
-  // every CTA streams ONE contiguous slice of the pairs (a grid-wide stride would walk each CTA through a new
-  // 2 MB page every trip: 148 CTAs x 4.8 MB apart, far beyond the TLB reach)
-  const uint64_t stride = blockDim.x;
+  auto look = [&]() {  // collective: the batch in flight
+    const bool mine = lane < fly_n;
+    uint4 E = make_uint4(0, 0, 0, 0);
+    uint32_t probe = 0;
+    int r = 0;
+    if (mine) {
+      E = q[(fly_base + lane) & 63u];
+      probe = qp[(fly_base + lane) & 63u];
+      const uint32_t slot = (gtab_slot<RB>(E, glog) + probe) & gmask;
+      r = gtab_probe<RB, CHECKED>((uint4*)gtab + slot, fx, E, flags, pol.keep);
+      if (r == 1 && ++probe >= kGtabMaxProbes) {
+        atomicOr(flags, (uint32_t)ERRF_SKEW);  // table full: the host retries with a larger one
+        r = 0;
+      }
+    }
+    fly_n = 0;
+    __syncwarp();
+    append(r != 0, E, probe);  // (never more than the batch just freed: the ring cannot overflow here)
+  };
+  auto issue = [&]() {  // collective: the oldest min(32, q_pend) pending entries
+    fly_n = q_pend < 32u ? q_pend : 32u;
+    fly_base = (q_tail - q_pend) & 63u;
+    if (lane < fly_n) {
+      const uint4 E = q[(fly_base + lane) & 63u];
+      const uint32_t slot = (gtab_slot<RB>(E, glog) + qp[(fly_base + lane) & 63u]) & gmask;
+      fx = ldv_v4((const uint4*)gtab + slot, pol.keep);
+    }
+    q_pend -= fly_n;
+  };
+  auto push = [&](bool p, const uint4& E) {  // collective: new entries; makes room first, starts a batch when 32 wait
+    const uint32_t k = __popc(__ballot_sync(0xffffffffu, p));
+    while (fly_n + q_pend + k > 64) {  // (rare: the ring holds the batch in flight + what came back + what is new)
+      if (fly_n) look();
+      else issue();
+    }
+    append(p, E, 0u);
+    if (q_pend >= 32) {
+      if (fly_n) look();
+      if (q_pend >= 32) issue();
+    }
+  };
+  // (between two barriers) entries with a sum below `below` leave the shared table for the global one
+  auto evict = [&](uint32_t below) {
+    const uint32_t e_round = (entries + 31) / 32 * 32;
+    for (uint32_t e = tid; e < e_round; e += blockDim.x) {
+      const bool out = e < entries && tag[e] > 1u && val[e] < below;
+      uint4 E = make_uint4(0, 0, 0, 0);
+      if (out) {
+        const uint32_t k0 = key[e], k1 = key[entries + e], k2 = KC > 2 ? key[2u * entries + e] : 0u;
+        E = R::kU64 ? make_uint4(k0, k1, val[e], 0u) : make_uint4(k0, k1, k2, val[e]);
+        tag[e] = 0;
+      }
+      if (__any_sync(0xffffffffu, out)) push(out, E);
+    }
+  };
+  // every CTA streams ONE contiguous slice of the pairs
   const uint64_t slice = ((n + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
   const uint64_t slice_lo = slice * blockIdx.x < n ? slice * blockIdx.x : n;
   const uint64_t slice_hi = slice_lo + slice < n ? slice_lo + slice : n;  // (this CTA's pairs: [slice_lo, slice_hi))
-  // TWO pairs per thread and trip, phase by phase (loads, tags, key words, adds): with 32 warps per SM -- the table
-  // takes the shared memory, the register file caps the CTA at 1024 threads -- every dependent wait (DRAM, then
-  // shared memory twice) is otherwise exposed; two independent chains per thread halve that (ncu: 25 % issue
-  // utilisation, 70 % of the stall samples on scoreboards, before).  All of it is straight-line, predicated code: a
-  // probe loop that lanes leave at different trips falls apart into fragments that do not reconverge inside it.
-  constexpr int J = RB <= 32 ? 2 : 1;  // (two 64- or 128-byte records do not fit the 64 registers a 1024-thread CTA leaves)
-  const uint64_t n_round2 = slice_lo + (slice_hi - slice_lo + 31) / 32 * 32;  // (lanes of a warp stay together: ballots inside)
-  for (uint64_t i = slice_lo + tid; i < n_round2; i += J * stride) {
-    uint32_t w[J][W], h[J], t0[J], t1[J], s0[J], s1[J];
-    uint64_t v[J];
-    bool need[J], live[J], hit[J];
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      need[j] = i + j * stride < slice_hi;
-      if (need[j]) load_rec_hint<RB>(recs + (i + j * stride) * R::kVec, w[j], pol.stream);
+  const uint32_t ntrips = (uint32_t)((slice_hi - slice_lo + blockDim.x - 1) / blockDim.x);  // (the same for every thread: barriers inside)
+  // the pair of the NEXT trip is requested before this one is processed
+  uint32_t wn[W];
+  if (slice_lo + tid < slice_hi) load_rec_hint<RB>(recs + (slice_lo + tid) * R::kVec, wn, pol.stream);
+  for (uint32_t trip = 0; trip < ntrips; trip++) {
+    const uint64_t i = slice_lo + (uint64_t)trip * blockDim.x + tid;
+    if (trip % kEpochTrips == kEpochTrips - 1) {
+      __syncthreads();
+      evict(2u);
+      __syncthreads();
     }
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      v[j] = need[j] ? rec_value<RB>(w[j]) : 0ull;
-      vmax = max(vmax, (uint32_t)(v[j] > 0xffffffffull ? 0xffffffffull : v[j]));
-      h[j] = slot_hash<RB>(w[j]);
-      live[j] = need[j] && v[j] != 0 && v[j] <= vcap;  // (a zero would still have to create its key: left to the global table)
-      s0[j] = __umulhi(h[j], entries);
-      s1[j] = s0[j] + 1 == entries ? 0u : s0[j] + 1;
-    }
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      t0[j] = live[j] ? ((volatile uint32_t*)tag)[s0[j]] : 1u;
-      t1[j] = live[j] ? ((volatile uint32_t*)tag)[s1[j]] : 1u;
-    }
-    uint32_t x[J][KC], sl[J];
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const uint32_t tg = h[j] | 2u;
-      hit[j] = live[j] && (t0[j] == tg || t1[j] == tg);
-      sl[j] = t0[j] == tg ? s0[j] : s1[j];
-#pragma unroll
-      for (int k = 0; k < KC; k++) x[j][k] = hit[j] ? ((volatile uint32_t*)key)[(uint32_t)k * entries + sl[j]] : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      if (hit[j]) {
-        bool eq = true;
-#pragma unroll
-        for (int k = 0; k < KC; k++) eq = eq && x[j][k] == w[j][k];
-        if (KW > KC && eq && (w[j][KC - 1] >> 24) != 0) {  // 12 bytes or longer (rare): the remaining words, one by one
-#pragma unroll
-          for (int k = KC; k < KW; k++)  // (unrolled: a run-time index into w[] would move the record to local memory)
-            if (eq) eq = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl[j]] == w[j][k];
-        }
-        if (eq) {
-          atomicAdd(val + sl[j], (uint32_t)v[j]);
-          need[j] = false;
-        }  // (same hash, other key: the pair goes to the global table, which is allowed to hold a key twice)
-      } else if (live[j] && (t0[j] == 0 || t1[j] == 0)) {  // claim the empty slot (the table fills early; then rare)
-        const uint32_t se = t0[j] == 0 ? s0[j] : s1[j];
-        if (atomicCAS(tag + se, 0u, 1u) == 0u) {
-#pragma unroll
-          for (int k = 0; k < KW; k++) key[(uint32_t)k * entries + se] = w[j][k];
-          val[se] = (uint32_t)v[j];
-          __threadfence_block();
-          atomicExch(tag + se, h[j] | 2u);
-          need[j] = false;
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const uint32_t m = __ballot_sync(0xffffffffu, need[j]);
-      if (m) {
-        if (need[j]) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(i + j * stride), h[j]);
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-          qn -= 32;
-          to_gtab(true, q[qn + lane]);
-          __syncwarp();
-        }
-      }
-    }
-  }
-  to_gtab(lane < qn, lane < qn ? q[lane] : make_uint2(0u, 0u));
-  __syncthreads();
-  // flush the shared table into the global one
-  const uint32_t e_round = (entries + 31) / 32 * 32;
-  for (uint32_t e = tid; e < e_round; e += blockDim.x) {
-    const bool has = e < entries && tag[e] > 1u;
     uint32_t w[W];
 #pragma unroll
-    for (int k = 0; k < W; k++) w[k] = (k < KW && has) ? key[(uint32_t)k * entries + e] : 0u;
-    gtab_add<RB, CHECKED>(has, gtab, glog, w, has ? (uint64_t)val[e] : 0ull, slot_hash<RB>(w), flags, pol.keep);
+    for (int k = 0; k < W; k++) w[k] = wn[k];
+    if (i + blockDim.x < slice_hi) load_rec_hint<RB>(recs + (i + blockDim.x) * R::kVec, wn, pol.stream);
+    // ... and the warp's 32 pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine:
+    // one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit it does
+    if (lane == 0 && (i & ~31ull) + (uint64_t)kPrefetchTrips * blockDim.x + 32 <= slice_hi)
+      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)kPrefetchTrips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
+    bool need = i < slice_hi;
+    const uint64_t v = need ? rec_value<RB>(w) : 0ull;
+    vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
+    // Straight-line, predicated code: a probe loop that lanes leave at different trips falls apart into fragments
+    // that do not reconverge inside it, and every fragment then waits for shared memory on its own.
+    bool is_short = true;
+    if (!R::kU64) {
+#pragma unroll
+      for (int k = 3; k < KW; k++) is_short = is_short && w[k] == 0;
+    }
+    if (need && is_short && v != 0 && v <= vcap) {  // (a zero would still have to create its key: left to the global table)
+      const uint32_t h = slot_hash<RB>(w), tg = h | 2u;
+      const uint32_t s0 = __umulhi(h, entries), s1 = s0 + 1 == entries ? 0u : s0 + 1;
+      const uint32_t t0 = ((volatile uint32_t*)tag)[s0], t1 = ((volatile uint32_t*)tag)[s1];
+      if (t0 == tg || t1 == tg) {
+        const uint32_t sl = t0 == tg ? s0 : s1;
+        uint32_t x[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) x[k] = ((volatile uint32_t*)key)[(uint32_t)k * entries + sl];
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < KC; k++) eq = eq && x[k] == w[k];
+        if (eq) {
+          atomicAdd(val + sl, (uint32_t)v);
+          need = false;
+        }  // (same hash, other key: the pair goes to the global table, which is allowed to hold a key twice)
+      } else if (t0 == 0 || t1 == 0) {  // claim the empty slot (the table fills early in the kernel's life; then rare)
+        const uint32_t sl = t0 == 0 ? s0 : s1;
+        if (atomicCAS(tag + sl, 0u, 1u) == 0u) {
+#pragma unroll
+          for (int k = 0; k < KC; k++) key[(uint32_t)k * entries + sl] = w[k];
+          val[sl] = (uint32_t)v;
+          __threadfence_block();
+          atomicExch(tag + sl, tg);
+          need = false;
+        }
+      }
+    }
+    // misses: long string keys walk their table now (rare), everything else queues up as a compact entry
+    if (!R::kU64) {
+      if (__any_sync(0xffffffffu, need && !is_short)) gtab_add_long<RB, CHECKED>(need && !is_short, gtab, glog, w, (uint32_t)v, flags, pol.keep);
+      if (need && v >= 0xfffffff0ull) {
+        atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
+        need = false;
+      }
+    }
+    const bool p = need && is_short && !(tune & 4u);
+    if (__any_sync(0xffffffffu, p)) push(p, R::kU64 ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(w[0], w[1], w[2], (uint32_t)v));
+  }
+  __syncthreads();
+  evict(0xffffffffu);  // the shared table's entries take the same road as the misses
+  // drain: whatever is in flight or pending, batch by batch, until nothing comes back
+  while (fly_n || q_pend) {
+    if (fly_n) look();
+    if (q_pend) issue();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -1363,14 +1378,14 @@ uint64_t gtab_bytes_host(int rb, uint32_t glog) { return gtab_bytes(rb, glog); }
 int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
                    int sm_count, cudaStream_t s) {
   if (!n) return 0;
-  uint32_t entries = (uint32_t)(kCombineSmem / (rb + 4));  // key words + value, + the tag
+  uint32_t entries = (uint32_t)(kCombineSmem / (rb == 16 ? 16 : 20));  // tag + value + 2 (u64) or 3 key words
   // the shared table only takes values whose per-CTA sum cannot wrap 32 bits
   const uint64_t per_cta = (n + sm_count - 1) / sm_count + kCombineThreads;
   const uint32_t vcap = (uint32_t)std::min<uint64_t>(0xffffull, 0xffffffffull / per_cta);
   if (checked) {
-    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags)));
+    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags, g_tune)));
   } else {
-    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags)));
+    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags, g_tune)));
   }
   return 1;
 }
