@@ -403,9 +403,10 @@ def e2e_run(job, a, wl, table, ctx, groups_resident):
     out_keys = ctx.pinned_array(cap_out, np.uint64 if wl["kind"] == mrhbm.KEY_U64 else "S%d" % (rb - 4))
     out_sums = ctx.pinned_array(cap_out, np.uint64)
     if wl["key"] == "zipf32":
+        threads = max(1, min(128, os.cpu_count() or 1) // job.world)
         need = mrhbm.synth_zipf_text(synth.SEED, rank * n, min(n, 1 << 16), table).nbytes * (n / min(n, 1 << 16))
         buf = ctx.pinned_array(int(need * 1.02) + (1 << 20), np.uint8)
-        text = mrhbm.synth_zipf_text(synth.SEED, rank * n, n, table, out=buf)
+        text = mrhbm.synth_zipf_text(synth.SEED, rank * n, n, table, out=buf, threads=threads)
         # chunks end at line ends (a word never straddles two calls)
         chunk, cuts, p = 256 << 20, [0], 0
         while p + chunk < text.nbytes:
@@ -507,7 +508,7 @@ def wordcount_config1(job, a, table):
         nbytes += t.nbytes
     total = files * per_file
     WC = "lua_mapreduce_b200.mapreduce.examples.WordCount"
-    from lua_mapreduce_b200.mapreduce.examples import WordCount
+    from lua_mapreduce_b200.mapreduce.examples.WordCount import init as WordCount
 
     def run_once():
         WordCount.RESULT.clear()

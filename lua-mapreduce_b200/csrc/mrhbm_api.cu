@@ -73,9 +73,10 @@ struct mrhbm_ctx {
   void* l1buf = nullptr;  // coarse regions of the two-level split
   uint64_t l1_cap = 0;
   // device tokeniser scratch (mrhbm_map_wordcount)
-  unsigned char* d_tok_text = nullptr;
+  unsigned char* d_tok_text[2] = {nullptr, nullptr};
   uint32_t *d_tok_cnt = nullptr, *d_tok_off = nullptr;
-  uint64_t tok_text_cap = 0, tok_blocks_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t tok_ev[2] = {nullptr, nullptr};
   // map-side combiner: the global (L2 resident) hash table and the records compacted out of it
   void *comb = nullptr, *gtab = nullptr;
   uint64_t comb_cap = 0, gtab_cap = 0;  // records
@@ -430,8 +431,8 @@ void mrhbm_destroy(mrhbm_ctx* c) {
                    c->sb.big_list, c->sb.counters, c->sb.mid,     c->sb.out_keys, c->sb.out_sums, c->ckeys,
                    c->csums,       c->d_acc,       c->d_table,    c->d_hd,        c->d_hall,    c->d_tot,
                    c->d_outoff,    c->d_segoff,    c->recvbuf,    c->bigbuf,      c->d_small,   c->comb,
-                   c->gtab,        c->l1buf,       c->regions,    c->d_l1all,     c->d_sample,   c->d_tok_text,
-                   c->d_tok_cnt,   c->d_tok_off};
+                   c->gtab,        c->l1buf,       c->regions,    c->d_l1all,     c->d_sample,   c->d_tok_text[0],
+                   c->d_tok_text[1], c->d_tok_cnt, c->d_tok_off};
   for (void* p : frees)
     if (p) cudaFree(p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -439,6 +440,9 @@ void mrhbm_destroy(mrhbm_ctx* c) {
   if (c->h_small) cudaFreeHost(c->h_small);
   for (int i = 0; i < EV_N; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (c->tok_ev[i]) cudaEventDestroy(c->tok_ev[i]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (prev >= 0) cudaSetDevice(prev);
   cudaGetLastError();
@@ -608,64 +612,97 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
   if (words) *words = 0;
   if (c->cfg.key_kind != MRHBM_KEY_STR) return fail(c, MRHBM_E_INVAL, "wordcount needs a string-key ctx");
   if (!len) return MRHBM_OK;
-  if (len >= (1ull << 38)) return fail(c, MRHBM_E_INVAL, "text too large for one call");
   int rc = stage_flush(m);
   if (rc) return rc;
-  const uint64_t nb = tok_blocks(len);
-  // scratch of the tokeniser (text + per-block word counts and offsets) lives with the ctx and only grows: a
-  // cudaMalloc / cudaFree pair per call would synchronise the device every time
-  if (len > c->tok_text_cap || nb + 1 > c->tok_blocks_cap) {
-    CU(c, cudaStreamSynchronize(c->stream));
-    for (void** p : {(void**)&c->d_tok_text, (void**)&c->d_tok_cnt, (void**)&c->d_tok_off}) {
-      if (*p) cudaFree(*p);
-      *p = nullptr;
-    }
-    c->tok_text_cap = c->tok_blocks_cap = 0;
-    const uint64_t tcap = len + len / 8 + 4096, bcap = tok_blocks(tcap) + 1;
-    cudaError_t ea = cudaMalloc((void**)&c->d_tok_text, tcap);
+  // The text is tokenised in pieces of <= kTokPiece bytes that end at white space, through two device buffers: the
+  // upload of piece k+1 (copy stream) runs while piece k is counted, scanned and emitted (ctx stream).  The scratch
+  // (text x 2, per-256-byte-block word counts and offsets) lives with the ctx.
+  constexpr size_t kTokPiece = 64u << 20;
+  const unsigned char* t = (const unsigned char*)text;
+  auto is_space = [](unsigned char ch) { return ch == ' ' || (ch >= 9 && ch <= 13); };
+  if (!c->d_tok_text[0]) {
+    const uint64_t tcap = kTokPiece + 4096, bcap = tok_blocks(tcap) + 1;
+    cudaError_t ea = cudaMalloc((void**)&c->d_tok_text[0], tcap);
+    if (ea == cudaSuccess) ea = cudaMalloc((void**)&c->d_tok_text[1], tcap);
     if (ea == cudaSuccess) ea = cudaMalloc((void**)&c->d_tok_cnt, bcap * 4);
     if (ea == cudaSuccess) ea = cudaMalloc((void**)&c->d_tok_off, (bcap + 1) * 4);
+    if (ea == cudaSuccess) ea = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && ea == cudaSuccess; i++) ea = cudaEventCreateWithFlags(&c->tok_ev[i], cudaEventDisableTiming);
     if (ea != cudaSuccess) {
       cudaGetLastError();
       return fail(c, MRHBM_E_NOMEM, "wordcount: %s", cudaGetErrorString(ea));
     }
-    c->tok_text_cap = tcap;
-    c->tok_blocks_cap = bcap;
   }
-  unsigned char* d_text = c->d_tok_text;
-  uint32_t *d_cnt = c->d_tok_cnt, *d_off = c->d_tok_off;
+  // undo information: a word that does not fit emits NOTHING of this call
+  const size_t nr0 = c->ranges.size();
+  const uint64_t last_cnt0 = nr0 ? c->ranges.back().cnt : 0, used0 = c->pool_used;
+  auto undo = [&]() {
+    c->ranges.resize(nr0);
+    if (nr0) c->ranges.back().cnt = last_cnt0;
+    c->pool_used = used0;
+  };
+  auto piece_end = [&](size_t p) -> size_t {  // end of the piece that starts at p: <= kTokPiece bytes, cut after white space
+    size_t e = std::min(len, p + kTokPiece);
+    if (e < len) {
+      size_t q = e;
+      while (q > p && !is_space(t[q - 1])) q--;
+      if (q > p) e = q;  // (no white space in 64 MB: one giant "word", the length check below refuses it)
+    }
+    return e;
+  };
   cudaError_t e = cudaSuccess;
-  uint64_t total = 0, off = 0;
-  do {
-    if ((e = cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) break;
-    if ((e = cudaMemsetAsync(c->sb.counters ? c->sb.counters : c->d_small, 0, 4, c->stream)) != cudaSuccess) break;
-    launch_tok_count(d_text, len, d_cnt, c->stream);
-    // exclusive scan of the block counts (chunks of at most 2^30 blocks is far beyond any text here)
-    launch_exscan(d_cnt, (uint32_t)nb, d_off, nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small, 0, c->stream,
+  uint64_t total_words = 0;
+  uint32_t* flagw = c->d_small + 1;
+  size_t p = 0, pe = piece_end(0);
+  int k = 0;
+  e = cudaMemcpyAsync(c->d_tok_text[0], t, pe, cudaMemcpyHostToDevice, c->copy_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(c->tok_ev[0], c->copy_stream);
+  while (e == cudaSuccess && rc == 0 && p < len) {
+    const size_t n = pe - p, pn = pe, pne = pe < len ? piece_end(pe) : pe;
+    unsigned char* d_text = c->d_tok_text[k & 1];
+    if (pn < len) {  // next piece's upload: its buffer was last read by piece k-1, whose kernels are behind a sync
+      e = cudaMemcpyAsync(c->d_tok_text[(k + 1) & 1], t + pn, pne - pn, cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(c->tok_ev[(k + 1) & 1], c->copy_stream);
+      if (e != cudaSuccess) break;
+    }
+    const uint64_t nb = tok_blocks(n);
+    if ((e = cudaStreamWaitEvent(c->stream, c->tok_ev[k & 1], 0)) != cudaSuccess) break;
+    launch_tok_count(d_text, n, c->d_tok_cnt, c->stream);
+    launch_exscan(c->d_tok_cnt, (uint32_t)nb, c->d_tok_off, nullptr, nullptr, 0xffffffffu, nullptr, nullptr, c->d_small, 0, c->stream,
                   c->d_small + 64);
     if ((e = cudaMemcpyAsync(c->h_small, c->d_small, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
-    total = c->h_small[0];
-    if (!total) break;
-    rc = pool_reserve(c, total, &off);
-    if (rc) break;
-    if ((e = cudaMemsetAsync(c->d_small + 1, 0, 4, c->stream)) != cudaSuccess) break;
-    launch_tok_emit(c->rb, d_text, len, d_off, (char*)c->pool + off * c->rb, c->d_small + 1, c->stream);
-    if ((e = cudaMemcpyAsync(c->h_small + 1, c->d_small + 1, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
-    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
-    if (c->h_small[1] & ERRF_KEYLEN) {
-      c->pool_used = off;  // nothing emitted
-      rc = fail(c, MRHBM_E_KEY, "a word is longer than the %d-byte key slot of this record class", c->kb - 1);
-      break;
+    const uint64_t total = c->h_small[0];
+    if (total) {
+      uint64_t off = 0;
+      rc = pool_reserve(c, total, &off);
+      if (rc) break;
+      if ((e = cudaMemsetAsync(flagw, 0, 4, c->stream)) != cudaSuccess) break;
+      launch_tok_emit(c->rb, d_text, n, c->d_tok_off, (char*)c->pool + off * c->rb, flagw, c->stream);
+      if ((e = cudaMemcpyAsync(c->h_small + 1, flagw, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
+      if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
+      if (c->h_small[1] & ERRF_KEYLEN) {
+        rc = fail(c, MRHBM_E_KEY, "a word is longer than the %d-byte key slot of this record class", c->kb - 1);
+        break;
+      }
+      add_range(m, off, total);
+      total_words += total;
     }
-    add_range(m, off, total);
-  } while (0);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return fail(c, MRHBM_E_CUDA, "wordcount: %s", cudaGetErrorString(e));
+    p = pn;
+    pe = pne;
+    k++;
   }
-  if (rc) return rc;
-  if (words) *words = total;
+  if (e != cudaSuccess || rc) {
+    cudaStreamSynchronize(c->copy_stream);  // an upload may still be reading the caller's text
+    cudaStreamSynchronize(c->stream);
+    undo();
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, MRHBM_E_CUDA, "wordcount: %s", cudaGetErrorString(e));
+    }
+    return rc;
+  }
+  if (words) *words = total_words;
   return MRHBM_OK;
 }
 

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(1024) k_exscan_rows(const uint32_t* __restrict
 // the combiner; a u32 sum about to wrap raises ERRF_OVERFLOW (string records carry u32 values).
 constexpr uint32_t kCombineLock = 0xffffffffu;
 constexpr int kCombineThreads = 1024;
-constexpr int kCombineSmem = 190 * 1024;  // (+ 32 KB of per-warp miss queues = 222 of the 227 KB)
+constexpr int kCombineSmem = 188 * 1024;  // (+ 38 KB of per-warp miss queues = 226 of the 227 KB)
 
 // cheap 32-bit hash of the key words (one IMAD per word); the shared table takes its top bits, the global
 // table a remix of it
@@ -703,7 +703,8 @@ __device__ __forceinline__ uint4 ldg_stream_hint(const uint4* p, uint64_t pol) {
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes, uint64_t pol) {
   asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
-constexpr int kPrefetchTrips = 6;
+constexpr int kPrefetchTrips = 4;  // (3..6 measure the same) x 32 KB per CTA x 148 CTAs = 19 MB of the stream in L2 ahead of its use; 12 trips
+                                    // (57 MB) pushed the 32 MB global table out of L2 again: 10.8 -> 12.9 ms
 constexpr uint32_t kEpochTrips = 256;  // shared-table clean-up period: 256 trips = 262,144 pairs per CTA
 __device__ __forceinline__ uint32_t ldv_u32(const uint32_t* p, uint64_t pol) {
   uint32_t v;
@@ -907,10 +908,13 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   // 20-35 % of the stall samples waited for these reads, the walk taking as long as its unluckiest lane).
   __shared__ uint4 queue[kCombineThreads / 32][64];
   __shared__ uint8_t queue_probe[kCombineThreads / 32][64];
+  __shared__ uint32_t long_queue[kCombineThreads / 32][32];  // indices of pairs with long keys, walked 32 at a time
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   const L2Policy pol = l2_policies();
   uint4* q = queue[tid >> 5];
   uint8_t* qp = queue_probe[tid >> 5];
+  uint32_t* lq = long_queue[tid >> 5];
+  uint32_t lq_n = 0;
   uint32_t q_tail = 0, q_pend = 0;  // ring: [.. in flight ..][.. q_pend pending ..] tail
   uint32_t fly_base = 0, fly_n = 0; // the batch in flight: fly_n entries from fly_base (0 = none)
   uint4 fx;                         // ... this lane's probed table entry
@@ -971,6 +975,16 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
       if (q_pend >= 32) issue();
     }
   };
+  auto long_walk = [&]() {  // collective
+    uint32_t w[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) w[k] = 0;
+    const bool mine = lane < lq_n;
+    if (mine) load_rec_hint<RB>(recs + (size_t)lq[lane] * R::kVec, w, pol.stream);
+    gtab_add_long<RB, CHECKED>(mine, gtab, glog, w, (uint32_t)rec_value<RB>(w), flags, pol.keep);
+    lq_n = 0;
+    __syncwarp();
+  };
   // (between two barriers) entries with a sum below `below` leave the shared table for the global one
   auto evict = [&](uint32_t below) {
     const uint32_t e_round = (entries + 31) / 32 * 32;
@@ -991,6 +1005,7 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   const uint64_t slice_hi = slice_lo + slice < n ? slice_lo + slice : n;  // (this CTA's pairs: [slice_lo, slice_hi))
   const uint32_t ntrips = (uint32_t)((slice_hi - slice_lo + blockDim.x - 1) / blockDim.x);  // (the same for every thread: barriers inside)
   // the pair of the NEXT trip is requested before this one is processed
+  const uint32_t pf_trips = (tune >> 8) & 0xffu ? (tune >> 8) & 0xffu : (uint32_t)kPrefetchTrips;  // (MRHBM_TUNE bits 8-15: override)
   uint32_t wn[W];
   if (slice_lo + tid < slice_hi) load_rec_hint<RB>(recs + (slice_lo + tid) * R::kVec, wn, pol.stream);
   for (uint32_t trip = 0; trip < ntrips; trip++) {
@@ -1006,8 +1021,8 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
     if (i + blockDim.x < slice_hi) load_rec_hint<RB>(recs + (i + blockDim.x) * R::kVec, wn, pol.stream);
     // ... and the warp's 32 pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine:
     // one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit it does
-    if (lane == 0 && (i & ~31ull) + (uint64_t)kPrefetchTrips * blockDim.x + 32 <= slice_hi)
-      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)kPrefetchTrips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
+    if (lane == 0 && (i & ~31ull) + (uint64_t)pf_trips * blockDim.x + 32 <= slice_hi)
+      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)pf_trips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
     bool need = i < slice_hi;
     const uint64_t v = need ? rec_value<RB>(w) : 0ull;
     vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
@@ -1019,7 +1034,13 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
       for (int k = 3; k < KW; k++) is_short = is_short && w[k] == 0;
     }
     if (need && is_short && v != 0 && v <= vcap) {  // (a zero would still have to create its key: left to the global table)
-      const uint32_t h = slot_hash<RB>(w), tg = h | 2u;
+      uint32_t h = 0x9E3779B9u;  // slot_hash over the KC words a short key has
+#pragma unroll
+      for (int k = 0; k < KC; k++) h = (h ^ w[k]) * 0x85EBCA6Bu + (h >> 15);
+      h ^= h >> 16;
+      h *= 0xC2B2AE35u;
+      h ^= h >> 13;
+      const uint32_t tg = h | 2u;
       const uint32_t s0 = __umulhi(h, entries), s1 = s0 + 1 == entries ? 0u : s0 + 1;
       const uint32_t t0 = ((volatile uint32_t*)tag)[s0], t1 = ((volatile uint32_t*)tag)[s1];
       if (t0 == tg || t1 == tg) {
@@ -1046,12 +1067,19 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
         }
       }
     }
-    // misses: long string keys walk their table now (rare), everything else queues up as a compact entry
+    // misses: long string keys (rare) are remembered by index and walk their table 32 at a time, all lanes busy;
+    // everything else queues up as a compact entry
     if (!R::kU64) {
-      if (__any_sync(0xffffffffu, need && !is_short)) gtab_add_long<RB, CHECKED>(need && !is_short, gtab, glog, w, (uint32_t)v, flags, pol.keep);
-      if (need && v >= 0xfffffff0ull) {
+      if (need && v >= 0xfffffff0ull) {  // (its state word, value + 1, would read "being written")
         atomicOr(flags, (uint32_t)ERRF_OVERFLOW);
         need = false;
+      }
+      const uint32_t ml = __ballot_sync(0xffffffffu, need && !is_short);
+      if (ml) {
+        if (lq_n + __popc(ml) > 32) long_walk();
+        if (need && !is_short) lq[lq_n + __popc(ml & ((1u << lane) - 1u))] = (uint32_t)i;
+        lq_n += __popc(ml);
+        __syncwarp();
       }
     }
     const bool p = need && is_short && !(tune & 4u);
@@ -1059,6 +1087,7 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   }
   __syncthreads();
   evict(0xffffffffu);  // the shared table's entries take the same road as the misses
+  if (!R::kU64 && lq_n) long_walk();
   // drain: whatever is in flight or pending, batch by batch, until nothing comes back
   while (fly_n || q_pend) {
     if (fly_n) look();
@@ -1381,7 +1410,7 @@ int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_
   uint32_t entries = (uint32_t)(kCombineSmem / (rb == 16 ? 16 : 20));  // tag + value + 2 (u64) or 3 key words
   // the shared table only takes values whose per-CTA sum cannot wrap 32 bits
   const uint64_t per_cta = (n + sm_count - 1) / sm_count + kCombineThreads;
-  const uint32_t vcap = (uint32_t)std::min<uint64_t>(0xffffull, 0xffffffffull / per_cta);
+  const uint32_t vcap = (uint32_t)std::min<uint64_t>(0xffffull, 0xffffffefull / per_cta);
   if (checked) {
     DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags, g_tune)));
   } else {

@@ -14,6 +14,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available() and torch.cuda.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """a plain `pytest` on a machine without a GPU skips the gpu-marked tests instead of failing them (the product
+    itself still fails loudly there: mrhbm_init returns MRHBM_E_NODEVICE, tests/test_bench_contract.py)"""
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_vectors():
     import json
