@@ -190,6 +190,8 @@ typedef struct mrhbm_stats {
   uint32_t launches;  /* kernels launched by the last shuffle */
   uint32_t bins, big_bins, sub_bins, attempts;
   uint64_t pairs, groups, bytes_exchanged;
+  float ms_setup;     /* key sampling, job-wide agreement, buffer set-up, counter clears (between combine and hist/level 1) */
+  float ms_finish;    /* offsets of the groups, totals, error flags back to the host (after the sort) */
 } mrhbm_stats;
 int mrhbm_stats_get(mrhbm_ctx *, mrhbm_stats *);
 /* drops committed pairs and results, keeps buffers (next iteration of a "loop" task,

@@ -1117,6 +1117,8 @@ void finish_stats(mrhbm_ctx* c, mrhbm_stats& st) {
   st.ms_scatter = ev_ms(c, EV_PLAN, EV_SCATTER);
   st.ms_sort_reduce = ev_ms(c, EV_EXCH, EV_SORT);
   st.ms_bigbins = ev_ms(c, EV_SORT, EV_BIG);
+  st.ms_setup = ev_ms(c, EV_CSTART, EV_COMBINE);
+  st.ms_finish = ev_ms(c, EV_BIG, EV_END);
   c->stats = st;
 }
 

@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("ms_sort_reduce", C.c_float), ("ms_bigbins", C.c_float), ("launches", C.c_uint32),
                 ("bins", C.c_uint32), ("big_bins", C.c_uint32), ("sub_bins", C.c_uint32),
                 ("attempts", C.c_uint32), ("pairs", C.c_uint64), ("groups", C.c_uint64),
-                ("bytes_exchanged", C.c_uint64)]
+                ("bytes_exchanged", C.c_uint64), ("ms_setup", C.c_float), ("ms_finish", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
