@@ -57,9 +57,9 @@ enum {
   /* general (non-built-in) Lua reducefn, job.lua:264-284: the device only partitions, sorts and
    * groups; mrhbm_groups_next hands out every value of a key (order unspecified, like the
    * reference's heap-pop order among equal keys) and the host calls reducefn per group.
-   * Needs combiner = 0.  mrhbm_result_copy then returns one row per pair (keys repeat).  On several
-   * GPUs a key may carry at most one shared-memory bin of values (2048 for u64 keys, 1024 / 512 /
-   * 256 for 32 / 64 / 128-byte records), else MRHBM_E_SKEW; on one GPU there is no limit. */
+   * Needs combiner = 0.  mrhbm_result_copy then returns one row per pair (keys repeat).  A key may
+   * carry any number of values, on one GPU or several: a bin larger than one shared-memory sort is
+   * sorted run by run on its owner and the iterator merges the runs. */
   MRHBM_RED_NONE = 1
 };
 

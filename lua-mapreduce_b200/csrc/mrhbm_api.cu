@@ -1218,13 +1218,17 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     // ---- buffers
     rc = ensure_small_arrays(c, std::max<uint64_t>(Bl, pl.C1));
     if (rc) return rc;
-    rc = ensure_records(c, &c->sb.mid, &c->mid_cap, Bl * bin_stride);
+    // k_split_tma addresses destination slots with 32 bits, and lets the records of a run that does not fit (the
+    // attempt is abandoned then) land at the start of the run's region: one tile of slack behind the last region
+    const uint64_t tile_slack = kSplitTileBytes / c->rb;
+    if (Bl * bin_stride + tile_slack >= (1ull << 32) || (uint64_t)pl.C1 * pl.sub_stride + tile_slack >= (1ull << 32)) return 0;
+    rc = ensure_records(c, &c->sb.mid, &c->mid_cap, Bl * bin_stride + tile_slack);
     if (rc) return rc;
     rc = ensure_out(c, Bl * (uint64_t)c->cap);
     if (rc) return rc;
     if (!single_level) {
       bool shared_ok = true;
-      rc = ensure_regions(c, (uint64_t)pl.C1 * pl.sub_stride, &shared_ok);
+      rc = ensure_regions(c, (uint64_t)pl.C1 * pl.sub_stride + tile_slack, &shared_ok);
       if (rc) return rc;
       if (!shared_ok) {  // peer mapping unavailable (decided by all ranks together): NCCL exchange instead
         c->no_optimistic = true;
@@ -1611,6 +1615,11 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     st.launches += launch_big_bins(c->rb, v, nbig, c->cap, s);
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
+    c->h_big.clear();
+    if (c->sb.no_reduce && nbig) {  // group-only mode: the iterator merges the runs of an oversized bin
+      c->h_big.resize(nbig);
+      CU(c, cudaMemcpyAsync(c->h_big.data(), c->sb.big_list, nbig * 4, cudaMemcpyDeviceToHost, s));
+    }
     st.launches += launch_exscan(c->sb.ucount, (uint32_t)Bl, c->sb.uoff, nullptr, nullptr, 0xffffffffu, nullptr, nullptr,
                                  c->sb.counters + CNT_TOTAL, 0, s, c->d_small + 64);
     c->h_bin_off.resize(Bl + 1);

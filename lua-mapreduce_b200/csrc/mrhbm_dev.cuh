@@ -181,7 +181,8 @@ __host__ __device__ __forceinline__ uint32_t mulhi_u64_u32(uint64_t x, uint32_t 
 }
 
 // partition id, owning rank and bin (= slot(pid)*S + sub) of a record held in registers / smem words
-template <int RB>
+// WORLD: 0 = bp.world read at run time, 1 = one GPU, 2 = several (folded by the caller's template)
+template <int RB, int WORLD = 0>
 __device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& bp, uint32_t* pid_out,
                                            uint32_t* dest_out = nullptr) {
   uint32_t pid;
@@ -212,7 +213,7 @@ __device__ __forceinline__ uint32_t bin_of(const uint32_t* r, const BinParams& b
   if (pid_out) *pid_out = pid;
   // partition p is owned by rank p % world and sits in slot pbase[rank] + p / world
   uint32_t slot = pid, dest = 0;
-  if (bp.world > 1) {
+  if (WORLD == 2 || (WORLD == 0 && bp.world > 1)) {
     uint32_t q;
     if (bp.wshift != 0xffffffffu) {  // power-of-two world: no integer division
       dest = pid & (bp.world - 1u);

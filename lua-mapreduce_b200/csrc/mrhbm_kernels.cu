@@ -11,6 +11,7 @@
 #include "mrhbm_kernels.h"
 
 #include <algorithm>
+#include <type_traits>
 
 #include "mrhbm_dev.cuh"
 #include "mrhbm_sort.cuh"
@@ -287,7 +288,7 @@ struct SplitArgs {
 };
 
 constexpr int kTmaSplitThreads = 512;
-constexpr int kTmaTileBytes = 40 * 1024;
+constexpr int kTmaTileBytes = kSplitTileBytes;
 __host__ __device__ constexpr size_t tma_split_smem(int rb, int tile_bytes = kTmaTileBytes) {
   return 2 * (size_t)tile_bytes + (size_t)(tile_bytes / rb) * sizeof(uint32_t);
 }
@@ -320,10 +321,14 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 }
 
 // One thread issues ONE cp.async.bulk per tile (global -> shared, completion on an mbarrier),
-// double-buffered, so tile t+1 lands while tile t is split; the tile is not re-staged: a u16
+// double-buffered, so tile t+1 lands while tile t is split; the tile is not re-staged: a
 // permutation says which raw record goes to which output position, and the copy-out reads the raw
 // tile through it.
-template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads>
+// The kernel is issue bound (profiles/README.md: 57 % issue utilisation, time follows the instruction count), so
+// what is known at launch time is folded at compile time.  SPEC = 0: level, number of GPUs and layout are read from
+// the arguments (exact layouts, the rare paths).  Otherwise the optimistic layout with bits 0-1 = level and
+// bit 2 = several GPUs.
+template <int RB, int TILE_BYTES = kTmaTileBytes, int MINB = 2, int THREADS_ = kTmaSplitThreads, int SPEC = 0>
 __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinParams bp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using R = Rec<RB>;
@@ -331,18 +336,21 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   constexpr int T = TILE_BYTES / RB;              // records per tile
   constexpr int U = (T + THREADS - 1) / THREADS;     // records per thread
   constexpr int IPT = kSplitMaxBins / THREADS;       // bins per thread in the scan
-  uint4* raw0 = (uint4*)smem_raw;
-  uint4* raw1 = (uint4*)(smem_raw + TILE_BYTES);
+  constexpr int WORLD = SPEC ? ((SPEC & 4) ? 2 : 1) : 0;
+  static_assert(T < 65536 && kSplitMaxBins <= 65536, "perm packs (raw index, bin) into 16 + 16 bits");
   uint32_t* perm = (uint32_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index | bin << 16
   __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins];
-  __shared__ unsigned long long sbase[kSplitMaxBins];  // this tile: byte address output position 0 would have in the
-                                                       // bin's run (0: the run does not fit, nothing is stored)
+  // this tile: the slot (record index in a.dst, 32-bit wrap-around arithmetic) output position 0 would have in the bin's run
+  __shared__ uint32_t sbase[kSplitMaxBins];
   __shared__ uint32_t wsum[THREADS / 32];
   __shared__ uint32_t s_rbase[9], s_fbase[9];  // (kernel-parameter arrays indexed by a register would be copied to local memory)
   __shared__ unsigned long long s_src[8];      // byte address and length (records) of the tile streams of this CTA
   __shared__ uint32_t s_n[8];
   __shared__ __align__(8) uint64_t mbar[2];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t level = SPEC ? (uint32_t)(SPEC & 3) : a.level;
+  const bool exact = SPEC ? false : a.base_off != nullptr;
+  const bool multi = SPEC ? (SPEC & 4) != 0 : a.ndest > 1;
 #pragma unroll
   for (int i = 0; i < 9; i++)
     if (tid == (uint32_t)i) {
@@ -352,9 +360,9 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   const uint4* src = a.src;
   uint64_t n = a.n;
   uint32_t coarse = 0;
-  if (a.level == 2) {
+  if (level == 2) {
     coarse = blockIdx.y;
-    if (a.base_off) {  // exact: the coarse region is the union of its fine bins
+    if (exact) {  // the coarse region is the union of its fine bins
       uint32_t f0 = coarse * a.F, f1 = f0 + a.F < a.B ? f0 + a.F : a.B;
       uint32_t o0 = a.base_off[(size_t)f0 << a.rep_shift], o1 = a.base_off[(size_t)f1 << a.rep_shift];
       src += (size_t)o0 * R::kVec;
@@ -366,11 +374,12 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   // EVERY stream, round-robin over the streams, so that its remote bulk copies fly while it splits local tiles
   // (with one CTA per source the ranks first did all their local tiles, then sat on the link: level 2 took
   // local time + link time).
-  const uint32_t nsrc = (a.level == 2 && !a.base_off) ? a.ndest : 1u;
+  const bool region_streams = level == 2 && !exact;
+  const uint32_t nsrc = (region_streams && multi) ? a.ndest : 1u;
 #pragma unroll
   for (int z = 0; z < 8; z++) {
     if (tid == (uint32_t)z && (uint32_t)z < nsrc) {
-      if (nsrc == 1 && !(a.level == 2 && !a.base_off)) {
+      if (!region_streams) {
         s_src[0] = (unsigned long long)(uintptr_t)src;
         s_n[0] = (uint32_t)n;
       } else {
@@ -381,9 +390,11 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     }
   }
   uint32_t fine_base = a.fbase[0];  // first fine bin of this rank
+  if (multi) {
 #pragma unroll
-  for (int z = 1; z < 8; z++)
-    if (a.me == (uint32_t)z) fine_base = a.fbase[z];
+    for (int z = 1; z < 8; z++)
+      if (a.me == (uint32_t)z) fine_base = a.fbase[z];
+  }
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -395,43 +406,54 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   for (uint32_t z = 0; z < nsrc; z++) ntmax = max(ntmax, (s_n[z] + T - 1) / T);
   // (tiles x, x + gridDim.x, ...: a contiguous range of tiles per CTA measured 4 % slower)
   const uint32_t rounds = ntmax > blockIdx.x ? (ntmax - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-  const uint32_t ksteps = rounds * nsrc;
-  // step k of this CTA: round k / nsrc, stream (k % nsrc + blockIdx.x + me) % nsrc, tile blockIdx.x + round * gridDim.x
-  auto step = [&](uint32_t k, const uint4*& p) -> uint32_t {
-    const uint32_t r = k / nsrc, z = (k - r * nsrc + blockIdx.x + a.me) % nsrc;
-    const uint64_t t0 = (uint64_t)(blockIdx.x + r * gridDim.x) * T;
-    const uint32_t nz = s_n[z];
-    p = (const uint4*)(uintptr_t)s_src[z] + t0 * R::kVec;
-    return t0 < nz ? (uint32_t)((nz - t0) < (uint64_t)T ? (nz - t0) : (uint64_t)T) : 0u;
-  };
-  auto next_valid = [&](uint32_t k, const uint4*& p, uint32_t& len) -> uint32_t {
-    for (; k < ksteps; k++)
-      if ((len = step(k, p)) != 0) return k;
-    len = 0;
-    return ksteps;
-  };
+  // the CTA's steps in order: round r = 0, 1, ... (tile blockIdx.x + r * gridDim.x), inside a round the streams
+  // zrot, zrot + 1, ... (mod nsrc); kept as counters, advanced without a division
+  const uint32_t zrot = nsrc > 1 ? (blockIdx.x + a.me) % nsrc : 0u;
+  uint32_t st_r = 0, st_zi = 0, st_z = zrot;
   const uint4* cur_p = nullptr;
   uint32_t cur_len = 0;
-  uint32_t k = next_valid(0, cur_p, cur_len);
-  if (tid == 0 && k < ksteps) bulk_load(raw0, cur_p, cur_len * RB, &mbar[0]);
-  uint32_t it = 0;
-  for (; k < ksteps; it++) {
-    const uint32_t tn = cur_len;
-    const uint4* raw = (it & 1) ? raw1 : raw0;
-    // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
-    const uint32_t knext = next_valid(k + 1, cur_p, cur_len);
-    if (tid == 0 && knext < ksteps) bulk_load((it & 1) ? raw0 : raw1, cur_p, cur_len * RB, &mbar[(it & 1) ^ 1]);
-    k = knext;
-    mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+  // describes the step the counters stand on (cur_p, cur_len), skipping empty ones; false when the CTA is done
+  auto settle = [&]() -> bool {
+    while (st_r < rounds) {
+      const uint64_t t0 = (uint64_t)(blockIdx.x + st_r * gridDim.x) * T;
+      const uint32_t nz = s_n[st_z];
+      if (t0 < nz) {
+        cur_p = (const uint4*)(uintptr_t)s_src[st_z] + t0 * R::kVec;
+        cur_len = (nz - t0) < (uint64_t)T ? (uint32_t)(nz - t0) : (uint32_t)T;
+        return true;
+      }
+      if (++st_zi == nsrc) {
+        st_zi = 0;
+        st_r++;
+      }
+      if (++st_z == nsrc) st_z = 0;
+    }
+    cur_len = 0;
+    return false;
+  };
+  auto advance = [&]() -> bool {
+    if (++st_zi == nsrc) {
+      st_zi = 0;
+      st_r++;
+    }
+    if (++st_z == nsrc) st_z = 0;
+    return settle();
+  };
+  bool more = settle();
+  if (tid == 0 && more) bulk_load(smem_raw, cur_p, cur_len * RB, &mbar[0]);
+
+  // one tile of tn records in `raw`; FULL: tn == T, no per-record bounds checks
+  auto split_tile = [&](auto full_c, const uint4* raw, const uint32_t tn) {
+    constexpr bool FULL = decltype(full_c)::value;
     uint32_t sub[U], rk[U];
 #pragma unroll
     for (int k = 0; k < U; k++) {
       const uint32_t i = tid + k * THREADS;
-      if (i < tn) {
+      if (((k + 1) * THREADS <= T || i < (uint32_t)T) && (FULL || i < tn)) {
         uint32_t dest;
-        const uint32_t fine = bin_of<RB>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr, &dest);
-        if (a.level == 1) {
-          if (a.ndest > 1)
+        const uint32_t fine = bin_of<RB, WORLD>((const uint32_t*)(raw + (size_t)i * R::kVec), bp, nullptr, &dest);
+        if (level == 1) {
+          if (multi)
             sub[k] = s_rbase[dest] + ((fine - s_fbase[dest]) >> a.logF);
           else
             sub[k] = fine >> a.logF;
@@ -446,7 +468,8 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     uint32_t v[IPT], ex[IPT], g[IPT], s = 0;
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
-      v[i] = IPT * tid + i < a.nbins ? scnt[IPT * tid + i] : 0u;
+      v[i] = scnt[IPT * tid + i];  // (bins >= a.nbins stay zero)
+      scnt[IPT * tid + i] = 0;     // ready for the next tile: every count of this one has been taken
       s += v[i];
     }
 #pragma unroll
@@ -454,7 +477,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       g[i] = 0;
       const uint32_t b = IPT * tid + i;
       if (v[i]) {
-        const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
+        const uint32_t dbin = level == 1 ? b : coarse * a.F + b;
         g[i] = atomicAdd(a.cursor + ((size_t)dbin << a.ctr_shift), v[i]);  // result needed only after the placement
       }
     }
@@ -469,7 +492,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     {
       uint32_t ws = lane < THREADS / 32 ? wsum[lane] : 0u, wi = ws;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
+      for (int d = 1; d < THREADS / 32; d <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
         if (lane >= (uint32_t)d) wi += t;
       }
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
 #pragma unroll
       for (int i = 0; i < IPT; i++) {
         ex[i] = e;
-        if (IPT * tid + i < a.nbins) soff[IPT * tid + i] = e;
+        soff[IPT * tid + i] = e;
         e += v[i];
       }
     }
@@ -486,45 +509,58 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
 #pragma unroll
     for (int k = 0; k < U; k++) {
       const uint32_t i = tid + k * THREADS;
-      if (i < tn) {
-        perm[soff[sub[k]] + rk[k]] = i | (sub[k] << 16);
-      }
+      if (((k + 1) * THREADS <= T || i < (uint32_t)T) && (FULL || i < tn)) perm[soff[sub[k]] + rk[k]] = i | (sub[k] << 16);
     }
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
       const uint32_t b = IPT * tid + i;
-      if (b < a.nbins) {
-        uint32_t gg = g[i];
-        bool fits = true;
-        if (v[i]) {
-          if (a.base_off) {  // exact layout: absolute start of the destination region, always large enough
-            const uint32_t dbin = a.level == 1 ? b : coarse * a.F + b;
-            const uint32_t f = a.level == 1 ? b * a.F : dbin;
-            gg += a.base_off[(size_t)f << a.rep_shift];
-          } else if (gg + v[i] > a.capacity) {
+      if (v[i]) {
+        const uint32_t dbin = level == 1 ? b : coarse * a.F + b;
+        uint32_t gg = g[i], first;
+        if (exact) {  // absolute start of the destination region, always large enough
+          const uint32_t f = level == 1 ? b * a.F : dbin;
+          first = a.base_off[(size_t)f << a.rep_shift];
+        } else {
+          first = dbin * (uint32_t)a.dst_stride;
+          if (gg + v[i] > a.capacity) {
+            // The run does not fit: the whole attempt is abandoned (ERRF_CAPACITY, the host redoes the shuffle with
+            // the exact layout from the untouched input), so these records only have to land INSIDE the buffer:
+            // at the start of the bin's region (the buffers carry one tile of slack behind the last region).
             atomicOr(a.err_flags, (uint32_t)ERRF_CAPACITY);
-            fits = false;
+            gg = 0;
           }
         }
-        // output position p of this tile goes to slot gg - ex[i] + p of the bin (64-bit wrap-around arithmetic)
-        unsigned long long dstb = (unsigned long long)(uintptr_t)a.dst;
-        if (!a.base_off) dstb += (unsigned long long)(a.level == 1 ? b : coarse * a.F + b) * a.dst_stride * RB;
-        sbase[b] = fits ? dstb + ((unsigned long long)gg - (unsigned long long)ex[i]) * RB : 0ull;
+        sbase[b] = first + gg - ex[i];  // output position p of this tile goes to slot sbase[b] + p
       }
     }
     __syncthreads();
-    // copy out: consecutive output positions of one bin are consecutive in global (or peer) memory
-    for (uint32_t p = tid; p < tn; p += THREADS) {
-      const uint32_t pb = perm[p];
-      const unsigned long long base = sbase[pb >> 16];
-      const uint4* r = raw + (size_t)(pb & 0xffffu) * R::kVec;
-      if (!base) continue;  // flagged above
-      uint4* d = (uint4*)(uintptr_t)(base + (unsigned long long)p * RB);
+    // copy out: consecutive output positions of one bin are consecutive in global memory
 #pragma unroll
-      for (int vv = 0; vv < R::kVec; vv++) stg_stream(d + vv, r[vv]);
+    for (int k = 0; k < U; k++) {
+      const uint32_t p = tid + k * THREADS;
+      if (((k + 1) * THREADS <= T || p < (uint32_t)T) && (FULL || p < tn)) {
+        const uint32_t pb = perm[p];
+        const uint32_t slot = sbase[pb >> 16] + p;
+        const uint4* r = raw + (size_t)(pb & 0xffffu) * R::kVec;
+        uint4* d = a.dst + (size_t)slot * R::kVec;
+#pragma unroll
+        for (int vv = 0; vv < R::kVec; vv++) stg_stream(d + vv, r[vv]);
+      }
     }
-    for (uint32_t b = tid; b < a.nbins; b += THREADS) scnt[b] = 0;
-    __syncthreads();
+    __syncthreads();  // the raw tile may be overwritten, perm / soff / sbase reused
+  };
+
+  for (uint32_t it = 0; more; it++) {
+    const uint32_t tn = cur_len;
+    const uint4* raw = (const uint4*)(smem_raw + (it & 1) * TILE_BYTES);
+    // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
+    more = advance();
+    if (tid == 0 && more) bulk_load(smem_raw + ((it & 1) ^ 1) * TILE_BYTES, cur_p, cur_len * RB, &mbar[(it & 1) ^ 1]);
+    mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+    if (tn == (uint32_t)T)
+      split_tile(std::true_type{}, raw, tn);
+    else
+      split_tile(std::false_type{}, raw, tn);
   }
 }
 
@@ -1341,11 +1377,14 @@ cudaError_t kernels_configure() {
   CFGC(16) CFGC(32) CFGC(64) CFGC(128)
 #undef CFGC1
 #undef CFGC
-#define CFGT(RB)                                                                                         \
-  e = cudaFuncSetAttribute(k_split_tma<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(RB)); \
+#define CFGT1(RB, SPEC)                                                                                  \
+  e = cudaFuncSetAttribute(k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, SPEC>,                    \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_split_smem(RB));        \
   if (e != cudaSuccess) return e;
+#define CFGT(RB) CFGT1(RB, 0) CFGT1(RB, 1) CFGT1(RB, 2) CFGT1(RB, 5) CFGT1(RB, 6)
   CFGT(16) CFGT(32) CFGT(64) CFGT(128)
 #undef CFGT
+#undef CFGT1
   return cudaSuccess;
 }
 
@@ -1472,6 +1511,22 @@ static SplitArgs split_args(const BinParams& bp, const SplitPlan& pl) {
   }
   return a;
 }
+// the instantiation that has the launch-time facts folded in (k_split_tma's SPEC)
+template <int RB>
+static void launch_split_rb(dim3 grid, const SplitArgs& a, const BinParams& bp, cudaStream_t s) {
+  const int spec = a.base_off ? 0 : (int)a.level | (a.ndest > 1 ? 4 : 0);
+  const size_t smem = tma_split_smem(RB);
+  switch (spec) {
+    case 1: k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, 1><<<grid, kTmaSplitThreads, smem, s>>>(a, bp); break;
+    case 2: k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, 2><<<grid, kTmaSplitThreads, smem, s>>>(a, bp); break;
+    case 5: k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, 5><<<grid, kTmaSplitThreads, smem, s>>>(a, bp); break;
+    case 6: k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, 6><<<grid, kTmaSplitThreads, smem, s>>>(a, bp); break;
+    default: k_split_tma<RB, kTmaTileBytes, 2, kTmaSplitThreads, 0><<<grid, kTmaSplitThreads, smem, s>>>(a, bp); break;
+  }
+}
+static void launch_split(int rb, dim3 grid, const SplitArgs& a, const BinParams& bp, cudaStream_t s) {
+  DISPATCH_RB(rb, (launch_split_rb<RB>(grid, a, bp, s)));
+}
 int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, const SplitPlan& pl, cudaStream_t s) {
   if (!n) return 0;
   SplitArgs a = split_args(bp, pl);
@@ -1484,7 +1539,7 @@ int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, c
   a.capacity = (uint32_t)std::min<uint64_t>(pl.sub_stride, 0xffffffffull);
   a.nbins = pl.C1;
   a.level = 1;
-  DISPATCH_RB(rb, (k_split_tma<RB><<<ctas, kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
+  launch_split(rb, dim3(ctas), a, bp, s);
   return 1;
 }
 int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s) {
@@ -1518,7 +1573,7 @@ int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream
       x = cand;
     }
   }
-  DISPATCH_RB(rb, (k_split_tma<RB><<<dim3(x, regions), kTmaSplitThreads, tma_split_smem(RB), s>>>(a, bp)));
+  launch_split(rb, dim3(x, regions), a, bp, s);
   return 1;
 }
 int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap, int sm_count,

@@ -32,6 +32,7 @@ MRHBM_HD inline uint32_t partition_slot(const BinParams& bp, uint32_t pid) {
   return bp.world > 1 ? bp.pbase[pid % bp.world] + pid / bp.world : pid;
 }
 
+constexpr int kSplitTileBytes = 40 * 1024;  // bytes of records k_split_tma partitions in shared memory at a time
 constexpr int kCapBytes = 32 * 1024;  // record bytes one CTA sorts in shared memory (2 CTAs per SM)
 inline uint32_t cap_records(int rb) { return (uint32_t)(kCapBytes / rb); }
 

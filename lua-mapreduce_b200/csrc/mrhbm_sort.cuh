@@ -637,16 +637,20 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
       const uint64_t range = pmax - pmin;
       const int bits = range ? 64 - __clzll((long long)range) : 0;
       const int sh = bits > kLogNB ? bits - kLogNB : 0;
-      uint32_t br[ITEMS];
+      // 32-bit sort key of a record inside this bin: the top 32 significant bits of key - pmin (all of them when the
+      // sub-bin's range has at most 32 bits).  Its top bits are the bucket; two records of one bucket tie on it with
+      // probability 2^-20 (or are real duplicates), and only then are the 64-bit keys compared.
+      const int sh0 = bits > 32 ? bits - 32 : 0, sh1 = sh - sh0;
+      uint32_t rpack = 0;  // 4 bits per item: arrival order inside the bucket
       int over = 0;
 #pragma unroll
       for (int k = 0; k < ITEMS; k++) {
-        br[k] = 0;
         if (tid + k * T < cnt) {
-          uint64_t key = (uint64_t)rg[k].x | ((uint64_t)rg[k].y << 32);
-          uint32_t bk = (uint32_t)((key - pmin) >> sh) & (NB - 1);
-          uint32_t r = atomicAdd(bcnt + bk, 1u);
-          br[k] = (bk << 4) | (r & 15u);
+          const uint64_t key = (uint64_t)rg[k].x | ((uint64_t)rg[k].y << 32);
+          const uint32_t kk = (uint32_t)((key - pmin) >> sh0);
+          const uint32_t bk = (kk >> sh1) & (NB - 1);
+          const uint32_t r = atomicAdd(bcnt + bk, 1u);
+          rpack |= (r & 15u) << (4 * k);
           if (r >= kFixMax) over = 1;
         }
       }
@@ -664,9 +668,18 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         ((uint4*)bcnt)[2 * tid + 1] = zero4;
       } else {
         block_exscan_u32x8(bcnt);  // bcnt[bk] = first position of bucket bk
+        uint32_t* kk2 = (uint32_t*)sm.rec;                             // bucket-ordered 32-bit sort keys (+ 4 sentinels)
+        uint64_t* dsum = (uint64_t*)((unsigned char*)sm.rec + kCapBytes / 2);  // sums of the groups that had duplicates
 #pragma unroll
         for (int k = 0; k < ITEMS; k++)
-          if (tid + k * T < cnt) sm.rec2[bcnt[br[k] >> 4] + (br[k] & 15u)] = rg[k];
+          if (tid + k * T < cnt) {
+            const uint64_t key = (uint64_t)rg[k].x | ((uint64_t)rg[k].y << 32);
+            const uint32_t kk = (uint32_t)((key - pmin) >> sh0);
+            const uint32_t pos = bcnt[(kk >> sh1) & (NB - 1)] + ((rpack >> (4 * k)) & 15u);
+            sm.rec2[pos] = rg[k];
+            kk2[pos] = kk;
+          }
+        if (tid < 4) kk2[cnt + tid] = 0xffffffffu;  // what the four-slot window reads behind the last bucket
         if (MULTI && warp == 0) desc_store(d_so, d_sn);  // the current bin's loads were issued an iteration ago
         __syncthreads();
         // the registers are free: start loading the next bin
@@ -675,24 +688,30 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
           for (int k = 0; k < ITEMS; k++)
             if (tid + k * T < ncnt) rg[k] = ldg_stream(rec_addr(tid + k * T, noff));
         }
-        // every position of the bucket-ordered buffer ranks itself among its bucket mates
-        uint32_t fpos[ITEMS];
-        uint64_t hsum[ITEMS];
+        // every position of the bucket-ordered buffer ranks itself among its bucket mates: a four-slot window of
+        // 32-bit keys from the bucket's start (later buckets and the sentinels compare greater)
+        uint32_t fpos[ITEMS];  // sorted slot of a group's head (bit 31: its sum is in dsum), 0xffffffff: not a head
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
           const uint32_t j = tid + k * T;
           fpos[k] = 0xffffffffu;
-          hsum[k] = 0;
           if (j < cnt) {
-            const uint4 me = sm.rec2[j];
-            const uint64_t key = (uint64_t)me.x | ((uint64_t)me.y << 32);
-            const uint32_t bk = (uint32_t)((key - pmin) >> sh) & (NB - 1);
+            const uint32_t mk = kk2[j];
+            const uint32_t bk = (mk >> sh1) & (NB - 1);
             const uint32_t s0 = bcnt[bk], e0 = (bk + 1 < NB) ? bcnt[bk + 1] : cnt;
-            uint32_t rank = 0, head = 1;
-            uint64_t sum = (uint64_t)me.z | ((uint64_t)me.w << 32);
-            const uint32_t c = e0 - s0;
-            if (c > 1) {  // 65 % of the records sit alone in their bucket
-              auto mate = [&](uint32_t m, uint64_t q) {
+            const uint32_t k0 = kk2[s0], k1 = kk2[s0 + 1], k2 = kk2[s0 + 2], k3 = kk2[s0 + 3];
+            uint32_t rank = (uint32_t)(k0 < mk) + (uint32_t)(k1 < mk) + (uint32_t)(k2 < mk) + (uint32_t)(k3 < mk);
+            const uint32_t same = (uint32_t)(k0 == mk) + (uint32_t)(k1 == mk) + (uint32_t)(k2 == mk) + (uint32_t)(k3 == mk);
+            uint32_t head = 1, dup = 0;
+            if (same > 1 || e0 - s0 > 4) {  // a tie on the 32-bit key (real duplicates, mostly) or a long bucket: the exact walk
+              const uint4 me = sm.rec2[j];
+              const uint64_t key = (uint64_t)me.x | ((uint64_t)me.y << 32);
+              uint64_t sum = (uint64_t)me.z | ((uint64_t)me.w << 32);
+              rank = 0;
+              for (uint32_t m = s0; m < e0; m++) {
+                if (m == j) continue;
+                const uint2 qk = *(const uint2*)(sm.rec2 + m);
+                const uint64_t q = (uint64_t)qk.x | ((uint64_t)qk.y << 32);
                 if (q < key) {
                   rank++;
                 } else if (q == key) {
@@ -704,29 +723,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
                     sum += (uint64_t)qv.x | ((uint64_t)qv.y << 32);
                   }
                 }
-              };
-              // the first four bucket slots: all loads first, then the compares (no load -> branch chain)
-              uint64_t q[4];
-#pragma unroll
-              for (int t = 0; t < 4; t++) {
-                q[t] = 0;
-                if ((uint32_t)t < c) {
-                  const uint2 qk = *(const uint2*)(sm.rec2 + s0 + t);
-                  q[t] = (uint64_t)qk.x | ((uint64_t)qk.y << 32);
-                }
               }
-#pragma unroll
-              for (int t = 0; t < 4; t++)
-                if ((uint32_t)t < c && s0 + t != j) mate(s0 + t, q[t]);
-              for (uint32_t m = s0 + 4; m < e0; m++) {
-                if (m == j) continue;
-                const uint2 qk = *(const uint2*)(sm.rec2 + m);
-                mate(m, (uint64_t)qk.x | ((uint64_t)qk.y << 32));
-              }
+              dsum[j] = sum;
+              dup = 0x80000000u;
             }
             heads[s0 + rank] = (uint16_t)head;
-            fpos[k] = head ? s0 + rank : 0xffffffffu;
-            hsum[k] = sum;
+            fpos[k] = head ? ((s0 + rank) | dup) : 0xffffffffu;
           }
         }
         __syncthreads();
@@ -734,10 +736,10 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
           if (fpos[k] != 0xffffffffu) {
-            const uint64_t o = out.base + heads[fpos[k]];
-            const uint2 kk = *(const uint2*)(sm.rec2 + tid + k * T);
-            ((uint64_t*)out.keys)[o] = (uint64_t)kk.x | ((uint64_t)kk.y << 32);
-            out.sums[o] = hsum[k];
+            const uint64_t o = out.base + heads[fpos[k] & 0x7fffffffu];
+            const uint4 me = sm.rec2[tid + k * T];
+            ((uint64_t*)out.keys)[o] = (uint64_t)me.x | ((uint64_t)me.y << 32);
+            out.sums[o] = (fpos[k] >> 31) ? dsum[tid + k * T] : ((uint64_t)me.z | ((uint64_t)me.w << 32));
           }
         }
         ((uint4*)bcnt)[2 * tid] = zero4;
@@ -774,26 +776,6 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, 
   SortSmem sm = carve(smem_raw, RB);
   uint32_t bin = b.big_list[blockIdx.x];
   uint32_t off = (uint32_t)bin_start(b, bin), n = bin_count(b, bin);
-  if (b.no_reduce) {
-    // group-only mode cannot shrink a bin (a key with more values than one CTA sorts): sort it
-    // chunk by chunk; the bin becomes ceil(n / cap) ascending runs of cap rows, which the host
-    // iterator merges (it knows the oversized bins from big_list).  Contiguous bins only.
-    if (b.src != b.mid || b.nseg != 1) {
-      if (threadIdx.x == 0) {
-        atomicOr(b.counters + CNT_ERR, (uint32_t)ERRF_SKEW);
-        b.ucount[bin] = 0;
-      }
-      return;
-    }
-    const uint4* src = (const uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
-    for (uint32_t c = 0; c < n; c += cap) {
-      uint32_t m = n - c < cap ? n - c : cap;
-      ChunkOut out{b.out_keys, b.out_sums, (uint64_t)off + c, b.counters + CNT_ERR, 1u};
-      process_chunk<RB, MODE_FINAL, false>(sm, src + (uint64_t)c * Rec<RB>::kVec, m, out);
-    }
-    if (threadIdx.x == 0) b.ucount[bin] = n;
-    return;
-  }
   uint4* base = (uint4*)b.mid + (uint64_t)off * Rec<RB>::kVec;
   if (b.src != b.mid) {  // after an exchange: make the bin contiguous inside the (free) send buffer
     uint64_t filled = 0;
@@ -805,6 +787,18 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_big_bins(ShuffleBuffers b, 
       filled += sc;
     }
     __syncthreads();
+  }
+  if (b.no_reduce) {
+    // group-only mode cannot shrink a bin (a key with more values than one CTA sorts): sort it
+    // chunk by chunk; the bin becomes ceil(n / cap) ascending runs of cap rows, which the host
+    // iterator merges (it knows the oversized bins from big_list).
+    for (uint32_t c = 0; c < n; c += cap) {
+      uint32_t m = n - c < cap ? n - c : cap;
+      ChunkOut out{b.out_keys, b.out_sums, (uint64_t)off + c, b.counters + CNT_ERR, 1u};
+      process_chunk<RB, MODE_FINAL, false>(sm, base + (uint64_t)c * Rec<RB>::kVec, m, out);
+    }
+    if (threadIdx.x == 0) b.ucount[bin] = n;
+    return;
   }
   while (n > cap) {
     uint32_t w = 0;

@@ -107,6 +107,44 @@ def run_zipf(rank, world, n_per, P, combiner=False):
               % (world, n_per, P, combiner, osum.size, st["big_bins"], st["attempts"]), flush=True)
 
 
+def run_group_only(rank, world, P):
+    """MRHBM_RED_NONE on several GPUs (job.lua:275-284 hands reducefn EVERY value of a key): one key carries more
+    values than a shared-memory bin holds and they come from all ranks -- the owner makes the bin contiguous,
+    sorts it run by run, and the iterator merges the runs."""
+    hot, nhot, nother = 7, 5000, 3000
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, device=int(os.environ["LOCAL_RANK"]), reducer=mrhbm.RED_NONE) as ctx:
+        parallel.init_comm(ctx, dist)
+        keys = np.concatenate([np.full(nhot, hot, dtype=np.uint64),
+                               np.arange(1000 + rank * nother, 1000 + (rank + 1) * nother, dtype=np.uint64) // 3])
+        vals = (np.arange(keys.size, dtype=np.uint64) + rank * keys.size)
+        rec = np.zeros(keys.size, dtype=mrhbm.record_dtype(mrhbm.KEY_U64))
+        rec["key"], rec["val"] = keys, vals
+        m = ctx.map_begin("r%d" % rank)
+        m.emit_batch(rec)
+        m.commit()
+        ctx.shuffle()
+        pairs = parallel.gather_final_pairs(ctx, dist)
+        st = ctx.stats()
+        allk = [None] * world if rank == 0 else None
+        dist.gather_object((keys.tolist(), vals.tolist()), allk, dst=0)
+        if rank != 0:
+            return
+        want = {}
+        for ks, vs in allk:
+            for k, v in zip(ks, vs):
+                want.setdefault(k, []).append(v)
+        got = {int.from_bytes(k, "big"): sorted(v) for _, k, v in pairs}
+        check("group-only: every value of every key, once", got == {k: sorted(v) for k, v in want.items()})
+        check("group-only: the hot key has all its values", len(got[hot]) == nhot * world)
+        per_part = {}
+        for p_, k, _ in pairs:
+            per_part.setdefault(p_, []).append(k)
+        check("group-only: keys ascending and distinct inside a partition",
+              all(v == sorted(v) and len(set(v)) == len(v) for v in per_part.values()))
+        print("group-only world=%d P=%d ok: keys=%d hot key values=%d big_bins(rank0)=%d"
+              % (world, P, len(got), len(got[hot]), st["big_bins"]), flush=True)
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -120,6 +158,7 @@ def main():
     run_u64(rank, world, 150_000, 3, flags=mrhbm.F_FORCE_RUNS)
     run_zipf(rank, world, 200_000, 15)
     run_zipf(rank, world, 1_500_000, 15, combiner=True)  # local combine (global table) on every rank, then the exchange
+    run_group_only(rank, world, 5)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world=%d" % world, flush=True)
