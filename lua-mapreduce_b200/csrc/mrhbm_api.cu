@@ -1259,6 +1259,15 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaMemsetAsync(c->sb.hist, 0, (((uint64_t)pl.C1) << c->ctr_shift) * sizeof(uint32_t), s));
     if (!single_level) CU(c, cudaMemsetAsync(c->sb.cursor, 0, (std::max<uint64_t>(Bl, 1) << c->ctr_shift) * sizeof(uint32_t), s));
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
+    if (c->tune & 128u)  // measurement hook: leave the L2 clean (a read sweep of 128 MB) before level 1
+      for (auto& r : live) launch_checksum_in(c->rb, r.p, std::min<uint64_t>(r.n, (128ull << 20) / c->rb), c->d_acc, s);
+    if (c->tune & 64u) {  // measurement hook: when do the CTAs of the two split levels really run (%globaltimer)?
+      pl.span = (unsigned long long*)(c->d_acc + 4);
+      CU(c, cudaMemsetAsync(c->d_acc + 4, 0xff, 8, s));
+      CU(c, cudaMemsetAsync(c->d_acc + 5, 0, 8, s));
+      CU(c, cudaMemsetAsync(c->d_acc + 6, 0xff, 8, s));
+      CU(c, cudaMemsetAsync(c->d_acc + 7, 0, 8, s));
+    }
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
     for (auto& r : live) st.launches += launch_split_l1(c->rb, r.p, r.n, bp, pl, s);
@@ -1295,11 +1304,15 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     st.launches += launch_region_totals(pl.l1_counts, pl.l1_zstride, (uint32_t)G, (uint32_t)me, pl.rbase[me], pl.C1_local,
                                         c->ctr_shift, (uint32_t)std::min<uint64_t>(single_level ? bin_stride : pl.sub_stride, 0xffffffffull),
                                         c->d_acc, s);
-    CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_acc, c->d_acc, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaMemcpyAsync(c->h_counters, c->sb.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaEventRecord(c->ev[EV_END], s));
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
+    if (c->tune & 64u)
+      fprintf(stderr, "[mrhbm] split spans: level 1 %.3f ms, gap %.3f ms, level 2 %.3f ms (events: %.3f / %.3f)\n",
+              (c->h_acc[5] - c->h_acc[4]) * 1e-6, ((double)c->h_acc[6] - (double)c->h_acc[5]) * 1e-6, (c->h_acc[7] - c->h_acc[6]) * 1e-6,
+              ev_ms(c, EV_HIST, EV_PLAN), ev_ms(c, EV_GATH, EV_SCATTER));
     uint32_t ef = c->h_counters[CNT_ERR];
     if (G > 1) {  // every rank must take the same branch; also: nobody leaves while a peer still reads its regions
       uint32_t efs[8];

@@ -285,6 +285,8 @@ struct SplitArgs {
   // [fbase[d], fbase[d+1]) in blocks of F (one GPU: rbase = {0, C1}, fbase = {0, B})
   uint32_t rbase[9], fbase[9];
   uint32_t ndest, me;
+  unsigned long long* span;  // measurement hook or nullptr (SplitPlan::span)
+  uint32_t stagger_ns;       // the second wave of CTAs (the co-residents of the first) starts this much later
 };
 
 constexpr int kTmaSplitThreads = 512;
@@ -351,6 +353,12 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   const uint32_t level = SPEC ? (uint32_t)(SPEC & 3) : a.level;
   const bool exact = SPEC ? false : a.base_off != nullptr;
   const bool multi = SPEC ? (SPEC & 4) != 0 : a.ndest > 1;
+  if (a.span && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(a.span + 2 * (level - 1), t);
+  }
+  if (a.stagger_ns && blockIdx.x >= (gridDim.x >> 1)) __nanosleep(a.stagger_ns);
 #pragma unroll
   for (int i = 0; i < 9; i++)
     if (tid == (uint32_t)i) {
@@ -561,6 +569,11 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
       split_tile(std::true_type{}, raw, tn);
     else
       split_tile(std::false_type{}, raw, tn);
+  }
+  if (a.span && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(a.span + 2 * (level - 1) + 1, t);
   }
 }
 
@@ -1055,10 +1068,13 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
 #pragma unroll
     for (int k = 0; k < W; k++) w[k] = wn[k];
     if (i + blockDim.x < slice_hi) load_rec_hint<RB>(recs + (i + blockDim.x) * R::kVec, wn, pol.stream);
-    // ... and the warp's 32 pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine:
-    // one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit it does
-    if (lane == 0 && (i & ~31ull) + (uint64_t)pf_trips * blockDim.x + 32 <= slice_hi)
-      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)pf_trips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
+    // ... and the CTA's pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine (one
+    // request of blockDim.x records by one thread: the kernel is issue bound, 32 warps each asking for their own KB cost
+    // 10 % of its instructions): one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit does
+    if (tid == 0) {
+      const uint64_t pf = i + (uint64_t)pf_trips * blockDim.x;
+      if (pf + blockDim.x <= slice_hi) bulk_prefetch_l2(recs + pf * R::kVec, blockDim.x * RB, pol.stream);
+    }
     bool need = i < slice_hi;
     const uint64_t v = need ? rec_value<RB>(w) : 0ull;
     vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
@@ -1502,6 +1518,8 @@ static SplitArgs split_args(const BinParams& bp, const SplitPlan& pl) {
   while ((1u << a.logF) < pl.F) a.logF++;
   a.ctr_shift = bp.ctr_shift;
   a.err_flags = pl.err_flags;
+  a.span = pl.span;
+  a.stagger_ns = ((g_tune >> 16) & 0xffu) * 250u;
   a.ndest = pl.base_off ? 1u : pl.ndest;
   a.me = pl.base_off ? 0u : pl.me;
   for (int d = 0; d < 8; d++) a.peer[d] = pl.base_off ? 0ull : pl.peer[d];

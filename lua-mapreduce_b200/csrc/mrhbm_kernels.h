@@ -150,6 +150,7 @@ struct SplitPlan {
   uint32_t rbase[9], fbase[9];  // first region / first fine bin of every rank
   const uint32_t* l1_counts;  // level 2: fill of region r on rank z at l1_counts[z * l1_zstride + (r << ctr_shift)]
   uint64_t l1_zstride;
+  unsigned long long* span;   // measurement hook (MRHBM_TUNE bit 6) or nullptr: [2 (level - 1)] = first CTA start, [+1] = last CTA end, %globaltimer ns
 };
 int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);
 int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);

@@ -602,6 +602,14 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     off = bin_start(b, bin);
     cnt = bin_count(b, bin);
   }
+  // sub = mulhi(key, S): the keys of sub-bin `sub` lie in [sub * q, sub * q + q + S), q = floor(2^64 / S), so one
+  // bucket shift serves every bin.  32-bit sort key of a record inside its bin: the top 32 significant bits of
+  // key - sub * q (all of them when q + S has at most 32 bits).  Its top kLogNB bits are the bucket; two records of
+  // one bucket tie on it with probability 2^-20 (or are real duplicates), and only then are the 64-bit keys compared.
+  const int bits = 64 - __clzll((long long)(b.hint_q + b.hint_S));
+  const int sh0 = bits > 32 ? bits - 32 : 0, sh1 = (bits > kLogNB ? bits - kLogNB : 0) - sh0;
+  const uint32_t sub_step = gridDim.x % b.hint_S;  // the CTA's bins advance by gridDim.x: sub follows without a division
+  uint32_t sub = bin % b.hint_S;
   uint4 rg[ITEMS];
   if (MULTI) {
     uint32_t so, sn;
@@ -630,17 +638,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
       if (cnt == 0 && tid == 0) b.ucount[bin] = 0;
     } else {
       ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
-      // sub = mulhi(key, S): keys of sub-bin `sub` lie in [sub*q, (sub+1)*(q+1)]
-      const uint32_t sub = bin % b.hint_S;
       const uint64_t pmin = (uint64_t)sub * b.hint_q;
-      const uint64_t pmax = sub + 1 == b.hint_S ? ~0ull : (uint64_t)(sub + 1) * (b.hint_q + 1);
-      const uint64_t range = pmax - pmin;
-      const int bits = range ? 64 - __clzll((long long)range) : 0;
-      const int sh = bits > kLogNB ? bits - kLogNB : 0;
-      // 32-bit sort key of a record inside this bin: the top 32 significant bits of key - pmin (all of them when the
-      // sub-bin's range has at most 32 bits).  Its top bits are the bucket; two records of one bucket tie on it with
-      // probability 2^-20 (or are real duplicates), and only then are the 64-bit keys compared.
-      const int sh0 = bits > 32 ? bits - 32 : 0, sh1 = sh - sh0;
       uint32_t rpack = 0;  // 4 bits per item: arrival order inside the bucket
       int over = 0;
 #pragma unroll
@@ -668,8 +666,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         ((uint4*)bcnt)[2 * tid + 1] = zero4;
       } else {
         block_exscan_u32x8(bcnt);  // bcnt[bk] = first position of bucket bk
-        uint32_t* kk2 = (uint32_t*)sm.rec;                             // bucket-ordered 32-bit sort keys (+ 4 sentinels)
-        uint64_t* dsum = (uint64_t*)((unsigned char*)sm.rec + kCapBytes / 2);  // sums of the groups that had duplicates
+        uint32_t* kk2 = (uint32_t*)sm.rec;  // bucket-ordered 32-bit sort keys (+ 4 sentinels)
 #pragma unroll
         for (int k = 0; k < ITEMS; k++)
           if (tid + k * T < cnt) {
@@ -690,7 +687,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         }
         // every position of the bucket-ordered buffer ranks itself among its bucket mates: a four-slot window of
         // 32-bit keys from the bucket's start (later buckets and the sentinels compare greater)
-        uint32_t fpos[ITEMS];  // sorted slot of a group's head (bit 31: its sum is in dsum), 0xffffffff: not a head
+        uint32_t fpos[ITEMS];  // sorted slot of a group's head, 0xffffffff: not a head
+        int merged = 0;        // some record of the bin is not a head: the groups have to be counted
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
           const uint32_t j = tid + k * T;
@@ -702,7 +700,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
             const uint32_t k0 = kk2[s0], k1 = kk2[s0 + 1], k2 = kk2[s0 + 2], k3 = kk2[s0 + 3];
             uint32_t rank = (uint32_t)(k0 < mk) + (uint32_t)(k1 < mk) + (uint32_t)(k2 < mk) + (uint32_t)(k3 < mk);
             const uint32_t same = (uint32_t)(k0 == mk) + (uint32_t)(k1 == mk) + (uint32_t)(k2 == mk) + (uint32_t)(k3 == mk);
-            uint32_t head = 1, dup = 0;
+            uint32_t head = 1;
             if (same > 1 || e0 - s0 > 4) {  // a tie on the 32-bit key (real duplicates, mostly) or a long bucket: the exact walk
               const uint4 me = sm.rec2[j];
               const uint64_t key = (uint64_t)me.x | ((uint64_t)me.y << 32);
@@ -724,22 +722,29 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
                   }
                 }
               }
-              dsum[j] = sum;
-              dup = 0x80000000u;
+              // the head of a group keeps the group's sum in its own value slot: nobody reads that slot (a walk only
+              // reads the values of equal keys BEHIND its own position, and the head is the first of its keys)
+              if (head && !out.no_reduce) *((uint2*)(sm.rec2 + j) + 1) = make_uint2((uint32_t)sum, (uint32_t)(sum >> 32));
+              merged |= (int)(head == 0);
             }
             heads[s0 + rank] = (uint16_t)head;
-            fpos[k] = head ? ((s0 + rank) | dup) : 0xffffffffu;
+            fpos[k] = head ? s0 + rank : 0xffffffffu;
           }
         }
-        __syncthreads();
-        const uint32_t groups = block_exscan_u16x4(heads, cnt);  // heads[f] = groups before sorted slot f
+        uint32_t groups = cnt;
+        if (__syncthreads_or(merged)) {  // (unique keys: sorted slot = output slot, no scan)
+          groups = block_exscan_u16x4(heads, cnt);  // heads[f] = groups before sorted slot f
+#pragma unroll
+          for (int k = 0; k < ITEMS; k++)
+            if (fpos[k] != 0xffffffffu) fpos[k] = heads[fpos[k]];
+        }
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
           if (fpos[k] != 0xffffffffu) {
-            const uint64_t o = out.base + heads[fpos[k] & 0x7fffffffu];
+            const uint64_t o = out.base + fpos[k];
             const uint4 me = sm.rec2[tid + k * T];
             ((uint64_t*)out.keys)[o] = (uint64_t)me.x | ((uint64_t)me.y << 32);
-            out.sums[o] = (fpos[k] >> 31) ? dsum[tid + k * T] : ((uint64_t)me.z | ((uint64_t)me.w << 32));
+            out.sums[o] = (uint64_t)me.z | ((uint64_t)me.w << 32);
           }
         }
         ((uint4*)bcnt)[2 * tid] = zero4;
@@ -748,6 +753,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         bin = nbin;
         off = noff;
         cnt = ncnt;
+        sub += sub_step;
+        if (sub >= b.hint_S) sub -= b.hint_S;
         __syncthreads();
         continue;
       }
@@ -756,6 +763,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     bin = nbin;
     off = noff;
     cnt = ncnt;
+    sub += sub_step;
+    if (sub >= b.hint_S) sub -= b.hint_S;
     if (MULTI) {
       if (warp == 0) desc_store(d_so, d_sn);
       __syncthreads();
