@@ -1068,13 +1068,12 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
 #pragma unroll
     for (int k = 0; k < W; k++) w[k] = wn[k];
     if (i + blockDim.x < slice_hi) load_rec_hint<RB>(recs + (i + blockDim.x) * R::kVec, wn, pol.stream);
-    // ... and the CTA's pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine (one
-    // request of blockDim.x records by one thread: the kernel is issue bound, 32 warps each asking for their own KB cost
-    // 10 % of its instructions): one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit does
-    if (tid == 0) {
-      const uint64_t pf = i + (uint64_t)pf_trips * blockDim.x;
-      if (pf + blockDim.x <= slice_hi) bulk_prefetch_l2(recs + pf * R::kVec, blockDim.x * RB, pol.stream);
-    }
+    // ... and the warp's 32 pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine:
+    // one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit it does.  (One 32 KB
+    // request per CTA by a single thread instead of 1 KB per warp saves 10 % of the instructions and LOSES 25 %:
+    // 10.8 -> 13.6 ms, the warps of a CTA are not in step.)
+    if (lane == 0 && (i & ~31ull) + (uint64_t)pf_trips * blockDim.x + 32 <= slice_hi)
+      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)pf_trips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
     bool need = i < slice_hi;
     const uint64_t v = need ? rec_value<RB>(w) : 0ull;
     vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
