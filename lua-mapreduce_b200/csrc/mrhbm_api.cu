@@ -1074,12 +1074,21 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
     if (rc) return rc;
     CU(c, cudaMemsetAsync(c->gtab, 0, tab_bytes, s));
     CU(c, cudaMemsetAsync(c->d_small, 0, 3 * sizeof(uint32_t), s));  // [0] flags, [1] records out, [2] largest value
+    if (c->tune & 64u) {  // measurement hook: k_combine's first CTA start, last CTA end, first CTA end at words 8..13
+      CU(c, cudaMemsetAsync(c->d_small + 8, 0xff, 8, s));
+      CU(c, cudaMemsetAsync(c->d_small + 10, 0, 8, s));
+      CU(c, cudaMemsetAsync(c->d_small + 12, 0xff, 8, s));
+    }
     for (auto& sr : srcs)
       st.launches += launch_combine(c->rb, sr.p, sr.n, (uint32_t*)c->gtab, glog, c->d_small, checked, c->sm_count, s);
     st.launches += launch_gtab_compact(c->rb, (const uint32_t*)c->gtab, glog, c->comb, c->d_small + 1, s);
     CU(c, cudaGetLastError());
-    CU(c, cudaMemcpyAsync(c->h_small, c->d_small, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->h_small, c->d_small, 14 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(c, cudaStreamSynchronize(s));
+    if (c->tune & 64u) {
+      const uint64_t* t = (const uint64_t*)(c->h_small + 8);
+      fprintf(stderr, "[mrhbm] k_combine: first CTA ends after %.3f ms, last after %.3f ms\n", (t[2] - t[0]) * 1e-6, (t[1] - t[0]) * 1e-6);
+    }
     const uint32_t ef = c->h_small[0];
     if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
     if (ef & ERRF_SKEW) {  // the table filled up: more distinct keys than it takes
@@ -1102,9 +1111,12 @@ int collect_sources(mrhbm_ctx* c, std::vector<Src>& srcs, uint64_t* N, mrhbm_sta
   }
 }
 
-uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total) {
-  // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill
-  uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap));
+uint32_t pick_sub_bins(const mrhbm_ctx* c, uint64_t n_total, uint32_t copies = 1) {
+  // mean bin = capacity of one CTA's shared-memory sort minus 6 sigma of a Poisson fill.  `copies`: records arrive in
+  // clumps of up to that many with one key (every rank's combiner emits each key once: a bin then holds Poisson-many
+  // KEYS times `copies` records, its sigma is sqrt(copies) times wider -- measured on 8 GPUs: 1 % of the bins of the
+  // combined Zipf stream overflowed a 6-sigma-of-records capacity and sent every shuffle to the exact layout)
+  uint64_t target = (uint64_t)std::max(1.0, (double)c->cap - 6.0 * std::sqrt((double)c->cap * (double)copies));
   uint64_t P = c->cfg.num_partitions;
   return (uint32_t)std::max<uint64_t>(1, (n_total + P * target - 1) / (P * target));
 }
@@ -1169,7 +1181,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     nonuniform |= all[2 * r + 1];
   }
   if (Nglobal == 0) return 0;  // nothing to do here: the exact path handles the empty shuffle
-  const uint32_t S = pick_sub_bins(c, Nglobal);
+  const uint32_t S = pick_sub_bins(c, Nglobal, c->cfg.combiner && G > 1 ? (uint32_t)G : 1u);
   {
     const uint64_t B = (uint64_t)P * S;
     if (B >= (1ull << 31)) return 0;
@@ -1250,6 +1262,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     pl.l1 = single_level ? c->sb.mid : c->regions;
     pl.mid = c->sb.mid;
     pl.err_flags = c->sb.counters + CNT_ERR;
+    pl.ticket = c->sb.counters + 5;  // (words 5 and 6 of the 8 counters cleared below)
     pl.base_off = nullptr;
     for (int r = 0; r < 8; r++) pl.peer[r] = (unsigned long long)(uintptr_t)(G == 1 ? (r == 0 ? c->regions : nullptr) : c->peer_regions[r]);
     pl.l1_counts = G == 1 ? c->sb.hist : c->d_l1all;
@@ -1261,12 +1274,11 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
     if (c->tune & 128u)  // measurement hook: leave the L2 clean (a read sweep of 128 MB) before level 1
       for (auto& r : live) launch_checksum_in(c->rb, r.p, std::min<uint64_t>(r.n, (128ull << 20) / c->rb), c->d_acc, s);
-    if (c->tune & 64u) {  // measurement hook: when do the CTAs of the two split levels really run (%globaltimer)?
-      pl.span = (unsigned long long*)(c->d_acc + 4);
+    if (c->tune & 64u) {  // measurement hook: when do the CTAs of level 1 (bit 8 set: of the u64 sort) start and end (%globaltimer)?
+      if (!(c->tune & 256u)) pl.span = (unsigned long long*)(c->d_acc + 4);
       CU(c, cudaMemsetAsync(c->d_acc + 4, 0xff, 8, s));
-      CU(c, cudaMemsetAsync(c->d_acc + 5, 0, 8, s));
-      CU(c, cudaMemsetAsync(c->d_acc + 6, 0xff, 8, s));
-      CU(c, cudaMemsetAsync(c->d_acc + 7, 0, 8, s));
+      CU(c, cudaMemsetAsync(c->d_acc + 5, 0, 16, s));
+      CU(c, cudaMemsetAsync(c->d_acc + 7, 0xff, 8, s));
     }
     CU(c, cudaEventRecord(c->ev[EV_COMBINE], s));
     CU(c, cudaEventRecord(c->ev[EV_HIST], s));
@@ -1291,7 +1303,9 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     ShuffleBuffers v = c->sb;
     v.cursor = fine_cursor;
     set_range_hint(v, S, ordered);
+    if ((c->tune & 64u) && (c->tune & 256u)) v.span = (unsigned long long*)(c->d_acc + 4);
     if (Bl) st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
+    v.span = nullptr;
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
     CU(c, cudaEventRecord(c->ev[EV_BIG], s));
     c->h_uoff.assign(Bl + 1, 0);
@@ -1310,9 +1324,9 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
     if (c->tune & 64u)
-      fprintf(stderr, "[mrhbm] split spans: level 1 %.3f ms, gap %.3f ms, level 2 %.3f ms (events: %.3f / %.3f)\n",
-              (c->h_acc[5] - c->h_acc[4]) * 1e-6, ((double)c->h_acc[6] - (double)c->h_acc[5]) * 1e-6, (c->h_acc[7] - c->h_acc[6]) * 1e-6,
-              ev_ms(c, EV_HIST, EV_PLAN), ev_ms(c, EV_GATH, EV_SCATTER));
+      fprintf(stderr, (c->tune & 256u) ? "[mrhbm] u64 sort: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (level 1 events: %.3f ms)\n" : "[mrhbm] level 1: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (events: %.3f ms)\n",
+              (c->h_acc[6] - c->h_acc[4]) * 1e-6, (c->h_acc[7] - c->h_acc[4]) * 1e-6, (c->h_acc[5] - c->h_acc[4]) * 1e-6,
+              ev_ms(c, EV_HIST, EV_PLAN));
     uint32_t ef = c->h_counters[CNT_ERR];
     if (G > 1) {  // every rank must take the same branch; also: nobody leaves while a peer still reads its regions
       uint32_t efs[8];

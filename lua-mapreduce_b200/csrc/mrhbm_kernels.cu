@@ -287,6 +287,7 @@ struct SplitArgs {
   uint32_t ndest, me;
   unsigned long long* span;  // measurement hook or nullptr (SplitPlan::span)
   uint32_t stagger_ns;       // the second wave of CTAs (the co-residents of the first) starts this much later
+  uint32_t* ticket;          // level 1, optimistic layout: {next tile - gridDim.x, CTAs that have left}, both 0 at launch
 };
 
 constexpr int kTmaSplitThreads = 512;
@@ -339,6 +340,7 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   constexpr int U = (T + THREADS - 1) / THREADS;     // records per thread
   constexpr int IPT = kSplitMaxBins / THREADS;       // bins per thread in the scan
   constexpr int WORLD = SPEC ? ((SPEC & 4) ? 2 : 1) : 0;
+  constexpr bool DYN = SPEC != 0 && (SPEC & 3) == 1;  // tiles from a ticket counter (level 1, optimistic layout)
   static_assert(T < 65536 && kSplitMaxBins <= 65536, "perm packs (raw index, bin) into 16 + 16 bits");
   uint32_t* perm = (uint32_t*)(smem_raw + 2 * TILE_BYTES);  // output position -> raw index | bin << 16
   __shared__ uint32_t scnt[kSplitMaxBins], soff[kSplitMaxBins];
@@ -349,14 +351,16 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
   __shared__ unsigned long long s_src[8];      // byte address and length (records) of the tile streams of this CTA
   __shared__ uint32_t s_n[8];
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t s_next_len[2];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t level = SPEC ? (uint32_t)(SPEC & 3) : a.level;
   const bool exact = SPEC ? false : a.base_off != nullptr;
   const bool multi = SPEC ? (SPEC & 4) != 0 : a.ndest > 1;
-  if (a.span && tid == 0) {
+  if (a.span && tid == 0 && level == 1) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    atomicMin(a.span + 2 * (level - 1), t);
+    atomicMin(a.span + 0, t);  // first CTA start
+    atomicMax(a.span + 2, t);  // last CTA start
   }
   if (a.stagger_ns && blockIdx.x >= (gridDim.x >> 1)) __nanosleep(a.stagger_ns);
 #pragma unroll
@@ -447,8 +451,8 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     if (++st_z == nsrc) st_z = 0;
     return settle();
   };
-  bool more = settle();
-  if (tid == 0 && more) bulk_load(smem_raw, cur_p, cur_len * RB, &mbar[0]);
+  bool more = DYN ? false : settle();
+  if (!DYN && tid == 0 && more) bulk_load(smem_raw, cur_p, cur_len * RB, &mbar[0]);
 
   // one tile of tn records in `raw`; FULL: tn == T, no per-record bounds checks
   auto split_tile = [&](auto full_c, const uint4* raw, const uint32_t tn) {
@@ -558,22 +562,64 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     __syncthreads();  // the raw tile may be overwritten, perm / soff / sbase reused
   };
 
-  for (uint32_t it = 0; more; it++) {
-    const uint32_t tn = cur_len;
-    const uint4* raw = (const uint4*)(smem_raw + (it & 1) * TILE_BYTES);
-    // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
-    more = advance();
-    if (tid == 0 && more) bulk_load(smem_raw + ((it & 1) ^ 1) * TILE_BYTES, cur_p, cur_len * RB, &mbar[(it & 1) ^ 1]);
-    mbar_wait(&mbar[it & 1], (it >> 1) & 1);
-    if (tn == (uint32_t)T)
-      split_tile(std::true_type{}, raw, tn);
-    else
-      split_tile(std::false_type{}, raw, tn);
+  if (!DYN) {
+    for (uint32_t it = 0; more; it++) {
+      const uint32_t tn = cur_len;
+      const uint4* raw = (const uint4*)(smem_raw + (it & 1) * TILE_BYTES);
+      // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
+      more = advance();
+      if (tid == 0 && more) bulk_load(smem_raw + ((it & 1) ^ 1) * TILE_BYTES, cur_p, cur_len * RB, &mbar[(it & 1) ^ 1]);
+      mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+      if (tn == (uint32_t)T)
+        split_tile(std::true_type{}, raw, tn);
+      else
+        split_tile(std::false_type{}, raw, tn);
+    }
+  } else {
+    // Level 1 of the optimistic layout: ONE stream, and the CTAs do not run at one speed (measured inside a shuffle:
+    // with 132 tiles each the first CTA ended after 0.62 ms, the last after 0.80 ms).  After its first tile
+    // (blockIdx.x) a CTA takes the next tile nobody has from a ticket counter; thread 0 fetches the ticket one
+    // iteration before it needs it, so the L2 round trip is not waited for.
+    const uint64_t nrec = s_n[0];
+    const uint4* base = (const uint4*)(uintptr_t)s_src[0];
+    auto tile_len = [&](uint32_t t) -> uint32_t {
+      const uint64_t t0 = (uint64_t)t * T;
+      return t0 < nrec ? ((nrec - t0) < (uint64_t)T ? (uint32_t)(nrec - t0) : (uint32_t)T) : 0u;
+    };
+    uint32_t tn = tile_len(blockIdx.x);
+    uint32_t tk = 0;  // (thread 0) the tile to prefetch next
+    if (tid == 0) {
+      if (tn) bulk_load(smem_raw, base + (uint64_t)blockIdx.x * T * R::kVec, tn * RB, &mbar[0]);
+      tk = gridDim.x + atomicAdd(a.ticket, 1u);
+    }
+    for (uint32_t it = 0; tn; it++) {
+      const uint4* raw = (const uint4*)(smem_raw + (it & 1) * TILE_BYTES);
+      if (tid == 0) {  // the other buffer was last read by the copy-out of the previous iteration (barrier at its end)
+        const uint32_t len = tile_len(tk);
+        s_next_len[(it & 1) ^ 1] = len;
+        if (len) {
+          bulk_load(smem_raw + ((it & 1) ^ 1) * TILE_BYTES, base + (uint64_t)tk * T * R::kVec, len * RB, &mbar[(it & 1) ^ 1]);
+          tk = gridDim.x + atomicAdd(a.ticket, 1u);
+        }
+      }
+      mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+      if (tn == (uint32_t)T)
+        split_tile(std::true_type{}, raw, tn);
+      else
+        split_tile(std::false_type{}, raw, tn);
+      tn = s_next_len[(it & 1) ^ 1];  // (written before the barriers of split_tile)
+    }
+    // the last CTA to leave resets the counters for the next launch on the stream
+    if (tid == 0 && atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1) {
+      a.ticket[0] = 0;
+      a.ticket[1] = 0;
+    }
   }
-  if (a.span && tid == 0) {
+  if (a.span && tid == 0 && level == 1) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    atomicMax(a.span + 2 * (level - 1) + 1, t);
+    atomicMax(a.span + 1, t);  // last CTA end
+    atomicMin(a.span + 3, t);  // first CTA end
   }
 }
 
@@ -937,6 +983,11 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = Rec<RB>;
   constexpr int W = R::kWords, KW = R::kKeyWords;
+  if ((tune & 64u) && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin((unsigned long long*)(flags + 8), t);
+  }
   constexpr int KC = KW < 3 ? KW : 3;  // key words of a shared-table entry: only keys of up to 12 bytes live there
   // Shared table, ARRAY PER FIELD (32 lanes probing 32 random entries hit 32 random banks, not the four a record
   // stride allows): tag[e] = 0 empty / 1 being written / the key's 32-bit hash with bit 1 set; val[e] = u32 partial
@@ -1147,6 +1198,12 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
   if (lane == 0 && vmax) atomicMax(flags + 2, vmax);
+  if ((tune & 64u) && threadIdx.x == 0) {  // measurement hook: when does the first CTA end, when the last?
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax((unsigned long long*)(flags + 8) + 1, t);
+    atomicMin((unsigned long long*)(flags + 8) + 2, t);
+  }
 }
 
 // one record per non-empty entry of the global table (short entries first, then the long ones), appended to out
@@ -1518,6 +1575,7 @@ static SplitArgs split_args(const BinParams& bp, const SplitPlan& pl) {
   a.ctr_shift = bp.ctr_shift;
   a.err_flags = pl.err_flags;
   a.span = pl.span;
+  a.ticket = pl.ticket;
   a.stagger_ns = ((g_tune >> 16) & 0xffu) * 250u;
   a.ndest = pl.base_off ? 1u : pl.ndest;
   a.me = pl.base_off ? 0u : pl.me;

@@ -68,6 +68,7 @@ struct ShuffleBuffers {
   uint64_t hint_q;     // floor(2^64 / S)
   uint32_t rep_shift;  // bin_off / seg_off are indexed by virtual bin = bin << rep_shift
   uint32_t no_reduce;  // MRHBM_RED_NONE: every pair is its own output row (sorted, grouped on the host)
+  unsigned long long* span;  // measurement hook or nullptr: k_sort_reduce_u64's first CTA start, last CTA end, -, first CTA end
 };
 MRHBM_HD inline uint64_t bin_start(const ShuffleBuffers& b, uint32_t bin) {
   return b.stride ? (uint64_t)bin * b.stride : (uint64_t)b.bin_off[(size_t)bin << b.rep_shift];
@@ -150,7 +151,8 @@ struct SplitPlan {
   uint32_t rbase[9], fbase[9];  // first region / first fine bin of every rank
   const uint32_t* l1_counts;  // level 2: fill of region r on rank z at l1_counts[z * l1_zstride + (r << ctr_shift)]
   uint64_t l1_zstride;
-  unsigned long long* span;   // measurement hook (MRHBM_TUNE bit 6) or nullptr: [2 (level - 1)] = first CTA start, [+1] = last CTA end, %globaltimer ns
+  uint32_t* ticket;           // two zeroed words: level 1 hands out its tiles from a counter (the kernel zeroes them again)
+  unsigned long long* span;   // measurement hook (MRHBM_TUNE bit 6) or nullptr: level 1's first CTA start, last CTA end, last CTA start, first CTA end (%globaltimer ns)
 };
 int launch_split_l1(int rb, const void* recs, uint64_t n, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);
 int launch_split_l2(int rb, const BinParams& bp, const SplitPlan& pl, cudaStream_t s);

@@ -595,6 +595,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     return src + s_addr[sg] + i;
   };
 
+  if (b.span && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(b.span, t);
+  }
   uint32_t bin = blockIdx.x;
   uint64_t off = 0;
   uint32_t cnt = 0;
@@ -775,6 +780,12 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
         if (tid + k * T < cnt) rg[k] = ldg_stream(rec_addr(tid + k * T, off));
     }
     __syncthreads();
+  }
+  if (b.span && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(b.span + 1, t);
+    atomicMin(b.span + 3, t);
   }
 }
 

@@ -114,6 +114,42 @@ def test_u64_sparse_duplicates_inside_key_ordered_bins():
             check_vs_oracle_u64(ctx, keys, vals, P)
 
 
+def test_u64_neighbouring_keys_and_small_repeats_in_key_ordered_bins():
+    """The u64 sort kernel ranks bucket mates on the top 32 significant bits of key - bin start and compares whole
+    keys only on a tie.  Keys that differ in their LOWEST bits only (k, k+1, k+2, k+5: same bin, same bucket, same
+    32-bit sort key) and keys repeated 2..4 times (real duplicates: the head sums its equals in place) must come
+    out in full 64-bit order with exact sums; the bins stay balanced, so everything stays on the one-pass path."""
+    rng = np.random.default_rng(29)
+    n0, P = 400_000, 4
+    base, vals = O.gen_u64(SEED, 777, n0)
+    base = base & np.uint64(0xFFFFFFFFFFFFFFF0)  # room for the small offsets
+    near = np.concatenate([base[:60_000] + np.uint64(d) for d in (1, 2, 5)])
+    reps = np.repeat(base[60_000:90_000], rng.integers(1, 4, 30_000))  # 2..4 copies with the original
+    keys = np.concatenate([base, near, reps])
+    vals = np.concatenate([vals, rng.integers(0, 1 << 31, near.size + reps.size).astype(np.uint32)])
+    perm = rng.permutation(keys.size)
+    keys, vals = keys[perm], vals[perm]
+    for flags in (0, mrhbm.F_NO_OPTIMISTIC):
+        with mrhbm.Ctx(mrhbm.KEY_U64, P, flags=flags) as ctx:
+            m = ctx.map_begin("near")
+            m.emit_batch(u64_records(keys, vals))
+            m.commit()
+            ctx.shuffle()
+            st = ctx.stats()
+            assert st["attempts"] == 1 and st["sub_bins"] > 1 and ctx.result_info().sorted == 1
+            check_vs_oracle_u64(ctx, keys, vals, P)
+    with mrhbm.Ctx(mrhbm.KEY_U64, P, reducer=mrhbm.RED_NONE) as ctx:  # group-only: equal keys keep all their rows
+        m = ctx.map_begin("near")
+        m.emit_batch(u64_records(keys, vals))
+        m.commit()
+        ctx.shuffle()
+        want = {}
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            want.setdefault(k, []).append(v)
+        got = {int.from_bytes(k, "big"): sorted(v) for p in ctx.partitions() for k, v in ctx.groups(p)}
+        assert got == {k: sorted(v) for k, v in want.items()}
+
+
 @pytest.mark.parametrize("combiner", [False, True])
 def test_u64_values_wider_than_32_bits(combiner):
     """u64-key records carry 64-bit values (ABI 2): any integer-valued Lua number < 2^53 (job.lua:83-97 emits
