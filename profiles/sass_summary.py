@@ -26,7 +26,13 @@ for part in re.split(r"\n\s*Function : ", txt)[1:]:
     c = collections.Counter()
     for o in ops:
         for p in pats:
-            if o.startswith(p.strip()) and (p.strip() != "LDG.E" or o in ("LDG.E", "LDG.E.CONSTANT", "LDG.E.NA", "LDG.E.STRONG.GPU")):
+            q = p.strip()
+            if q.startswith(("LDG", "STG")):  # width classes: .128 / .64 / 32-bit, whatever cache modifiers sit in between
+                width = "128" if ".128" in o else "64" if ".64" in o else ""
+                want = "128" if q.endswith("128") else "64" if q.endswith("64") else ""
+                if o.startswith(q[:3]) and width == want:
+                    c[p] += 1
+            elif o.startswith(q):
                 c[p] += 1
     d = demangle(name)
     d = re.sub(r"\(.*", "", d).replace("void mrhbm::", "").replace("(int)", "").replace("(bool)", "")
