@@ -978,7 +978,7 @@ __device__ __forceinline__ void gtab_add_long(bool active, uint32_t* __restrict_
 // wrap 32 bits (pairs per CTA x vcap < 2^32), which keeps saturation tests out of the per-pair path.
 template <int RB, bool CHECKED>
 __global__ void __launch_bounds__(kCombineThreads, 1)
-    k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t entries, uint32_t vcap, uint32_t* __restrict__ gtab,
+    k_combine(const uint4* __restrict__ recs, uint64_t n, uint32_t pf_trips, uint32_t vcap, uint32_t* __restrict__ gtab,
               uint32_t glog, uint32_t* __restrict__ flags, uint32_t tune) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = Rec<RB>;
@@ -996,6 +996,8 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   // Every kEpochTrips trips the CTA stops at a barrier and evicts the entries that gathered less than two pairs
   // since they were admitted (into the global table, like a miss): the table is filled first come first served,
   // and without that the keys that happened to arrive first would keep out warmer keys that arrived later.
+  // (compile-time sizes: table addresses become immediates -- the kernel is issue bound and short of registers)
+  constexpr uint32_t entries = (uint32_t)(kCombineSmem / (R::kU64 ? 16 : 20));  // tag + value + 2 (u64) or 3 key words
   uint32_t* tag = (uint32_t*)smem_raw;
   uint32_t* val = tag + entries;
   uint32_t* key = val + entries;
@@ -1104,12 +1106,22 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   const uint64_t slice_lo = slice * blockIdx.x < n ? slice * blockIdx.x : n;
   const uint64_t slice_hi = slice_lo + slice < n ? slice_lo + slice : n;  // (this CTA's pairs: [slice_lo, slice_hi))
   const uint32_t ntrips = (uint32_t)((slice_hi - slice_lo + blockDim.x - 1) / blockDim.x);  // (the same for every thread: barriers inside)
-  // the pair of the NEXT trip is requested before this one is processed
-  const uint32_t pf_trips = (tune >> 8) & 0xffu ? (tune >> 8) & 0xffu : (uint32_t)kPrefetchTrips;  // (MRHBM_TUNE bits 8-15: override)
+  // the pair of the NEXT trip is requested before this one is processed.  Index arithmetic of the loop: running
+  // 64-bit pointers and 32-bit trip bounds (the kernel is issue bound; the per-trip 64-bit index, bounds checks and
+  // prefetch address were 15 % of its instructions)
+  const uint32_t span = (uint32_t)(slice_hi - slice_lo);                                    // pairs of this CTA (< 2^32)
+  const uint32_t my_trips = tid < span ? (span - tid + blockDim.x - 1) / blockDim.x : 0u;   // trips in which this thread has a pair
+  // the warp's 32 pairs of trip t + pf_trips lie inside the slice for t < pf_ok
+  const uint32_t wbase = (tid & ~31u) + 32u;
+  const uint32_t pf_full = span >= wbase ? (span - wbase) / blockDim.x + 1u : 0u;          // trips whose 32 pairs are all there
+  const uint32_t pf_ok = pf_full > pf_trips ? pf_full - pf_trips : 0u;
+  const uint4* p_next = recs + (slice_lo + tid) * R::kVec;                                  // this thread's pair of the next trip
+  const uint4* p_pf = recs + (slice_lo + (tid & ~31u) + (uint64_t)pf_trips * blockDim.x) * R::kVec;  // the warp's prefetch target
+  const size_t p_step = (size_t)blockDim.x * R::kVec;
+  uint32_t i32 = (uint32_t)slice_lo + tid;  // index of the pair in hand (all pairs of one shuffle: < 2^32)
   uint32_t wn[W];
-  if (slice_lo + tid < slice_hi) load_rec_hint<RB>(recs + (slice_lo + tid) * R::kVec, wn, pol.stream);
-  for (uint32_t trip = 0; trip < ntrips; trip++) {
-    const uint64_t i = slice_lo + (uint64_t)trip * blockDim.x + tid;
+  if (my_trips) load_rec_hint<RB>(p_next, wn, pol.stream);
+  for (uint32_t trip = 0; trip < ntrips; trip++, i32 += blockDim.x) {
     if (trip % kEpochTrips == kEpochTrips - 1) {
       __syncthreads();
       evict(2u);
@@ -1118,14 +1130,15 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
     uint32_t w[W];
 #pragma unroll
     for (int k = 0; k < W; k++) w[k] = wn[k];
-    if (i + blockDim.x < slice_hi) load_rec_hint<RB>(recs + (i + blockDim.x) * R::kVec, wn, pol.stream);
+    p_next += p_step;
+    if (trip + 1 < my_trips) load_rec_hint<RB>(p_next, wn, pol.stream);
     // ... and the warp's 32 pairs of kPrefetchTrips trips ahead are pulled from DRAM into L2 by the bulk-copy engine:
     // one trip of work (~0.4 us) does not cover a DRAM access under load (1.5-2 us), an L2 hit it does.  (One 32 KB
     // request per CTA by a single thread instead of 1 KB per warp saves 10 % of the instructions and LOSES 25 %:
     // 10.8 -> 13.6 ms, the warps of a CTA are not in step.)
-    if (lane == 0 && (i & ~31ull) + (uint64_t)pf_trips * blockDim.x + 32 <= slice_hi)
-      bulk_prefetch_l2(recs + ((i & ~31ull) + (uint64_t)pf_trips * blockDim.x) * R::kVec, 32u * RB, pol.stream);
-    bool need = i < slice_hi;
+    if (lane == 0 && trip < pf_ok) bulk_prefetch_l2(p_pf, 32u * RB, pol.stream);
+    p_pf += p_step;
+    bool need = trip < my_trips;
     const uint64_t v = need ? rec_value<RB>(w) : 0ull;
     vmax = max(vmax, (uint32_t)(v > 0xffffffffull ? 0xffffffffull : v));
     // Straight-line, predicated code: a probe loop that lanes leave at different trips falls apart into fragments
@@ -1179,7 +1192,7 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
       const uint32_t ml = __ballot_sync(0xffffffffu, need && !is_short);
       if (ml) {
         if (lq_n + __popc(ml) > 32) long_walk();
-        if (need && !is_short) lq[lq_n + __popc(ml & ((1u << lane) - 1u))] = (uint32_t)i;
+        if (need && !is_short) lq[lq_n + __popc(ml & ((1u << lane) - 1u))] = i32;
         lq_n += __popc(ml);
         __syncwarp();
       }
@@ -1518,14 +1531,14 @@ uint64_t gtab_bytes_host(int rb, uint32_t glog) { return gtab_bytes(rb, glog); }
 int launch_combine(int rb, const void* recs, uint64_t n, uint32_t* gtab, uint32_t glog, uint32_t* flags, bool checked,
                    int sm_count, cudaStream_t s) {
   if (!n) return 0;
-  uint32_t entries = (uint32_t)(kCombineSmem / (rb == 16 ? 16 : 20));  // tag + value + 2 (u64) or 3 key words
+  const uint32_t pf_trips = (g_tune >> 8) & 0xffu ? (g_tune >> 8) & 0xffu : (uint32_t)kPrefetchTrips;  // (MRHBM_TUNE bits 8-15: override)
   // the shared table only takes values whose per-CTA sum cannot wrap 32 bits
   const uint64_t per_cta = (n + sm_count - 1) / sm_count + kCombineThreads;
   const uint32_t vcap = (uint32_t)std::min<uint64_t>(0xffffull, 0xffffffefull / per_cta);
   if (checked) {
-    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags, g_tune)));
+    DISPATCH_RB(rb, (k_combine<RB, true><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, pf_trips, vcap, gtab, glog, flags, g_tune)));
   } else {
-    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, entries, vcap, gtab, glog, flags, g_tune)));
+    DISPATCH_RB(rb, (k_combine<RB, false><<<sm_count, kCombineThreads, kCombineSmem, s>>>((const uint4*)recs, n, pf_trips, vcap, gtab, glog, flags, g_tune)));
   }
   return 1;
 }

@@ -1,0 +1,5 @@
+# round 2, call c2 (1 GPU): combiner loop on running pointers and 32-bit trip bounds
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -k "combiner or zipf or wordcount or nul" > gpurun_out/r02_c2_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 2 gpurun_out/r02_c2_pytest.log | cut -c1-200
+timeout 600 python bench.py --workload zipf32 --steps 8 --warmup 3 --e2e-steps 0 --no-cpu-baseline > gpurun_out/r02_c2_zipf.json 2> gpurun_out/r02_c2_zipf.err; echo "zipf rc=$?"
+python profiles/show.py gpurun_out/r02_c2_zipf.json | cut -c1-300
