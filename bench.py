@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "zipf32", "u64", "u64big", "wordcount"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "zipf32", "u64", "u64big", "u64seq", "wordcount"])
     ap.add_argument("--only-headline", action="store_true", help="skip the ride-along configs")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: the config's size)")
     ap.add_argument("--partitions", type=int, default=0)
@@ -126,6 +126,12 @@ def workload(name, a, world):
         return dict(key="u64", rb=16, pairs=n, P=a.partitions or 1024, kind=mrhbm.KEY_U64, part=mrhbm.PART_MULHASH,
                     combiner=False, scaling="weak", dtype="u64",
                     name="config2: 1e8 uniform u64 keys / u32 values, 16 B records" + ("" if world == 1 else " per GPU"))
+    if name == "u64seq":  # NOT a BASELINE config: the distribution the key-ordered fast path cannot take
+        n = a.pairs or 100_000_000
+        return dict(key="u64seq", rb=16, pairs=n, P=a.partitions or 1024, kind=mrhbm.KEY_U64, part=mrhbm.PART_MULHASH,
+                    combiner=False, scaling="weak", dtype="u64",
+                    name="1e8 SEQUENTIAL u64 keys (rank * n + i) / u32 values, 16 B records: sampled as non-uniform, hash sub-bins "
+                         "in the first attempt, the partitions are merged from S runs by the iterator")
     if name == "u64big":
         total = (a.pairs * world) if a.pairs else 1_000_000_000
         return dict(key="u64big", rb=16, pairs=total // world, P=a.partitions or 1024, kind=mrhbm.KEY_U64,
@@ -144,6 +150,14 @@ def host_u64_records(seed, start, n, out):
         i = np.arange(start + a, start + b, dtype=np.uint64)
         out["key"][a:b] = splitmix64_np(np.uint64(seed) + i)
         out["val"][a:b] = splitmix64_np(np.uint64(seed) + np.uint64(1 << 40) + i) >> np.uint64(32)
+
+
+def seq_records(start, n):
+    from lua_mapreduce_b200 import mrhbm
+    rec = np.zeros(n, dtype=mrhbm.record_dtype(mrhbm.KEY_U64))
+    rec["key"] = np.arange(start, start + n, dtype=np.uint64)
+    rec["val"] = (rec["key"] * np.uint64(2654435761)) & np.uint64(0xFFFF)
+    return rec
 
 
 def oracle_mod():
@@ -300,6 +314,12 @@ def parity_vs_oracle(job, ctx, wl, table):
         okeys, osums, opo = O.wordcount_from_counts(counts, O.PART_FNV_LUA, P, world, rank)
         okeys = okeys.view("S28").reshape(-1)
         pairs_checked = int(counts.sum())
+    elif wl["key"] == "u64seq":  # every key once: the oracle is the keys themselves, sorted per partition (one rank only)
+        if world > 1:
+            return None
+        r = seq_records(0, n)
+        okeys, osums, opo = O.groupby_u64(r["key"], r["val"].astype(np.uint32), O.PART_MULHASH, P)
+        pairs_checked = n
     else:
         total = n * world
         okeys, osums, opo = O.groupby_u64_stream(synth.SEED, 0, total, O.PART_MULHASH, P, world, rank, nthreads=threads,
@@ -322,6 +342,10 @@ def resident_run(job, a, wl, table, sample_clocks):
     m = ctx.map_begin("resident")
     if wl["key"] == "zipf32":
         m.gen_zipf(synth.SEED, rank * n, n, table)
+    elif wl["key"] == "u64seq":
+        step = 1 << 24
+        for s0 in range(0, n, step):
+            m.emit_batch(seq_records(rank * n + s0, min(step, n - s0)))
     else:
         m.gen_u64(synth.SEED, rank * n, n)
     m.commit()
@@ -423,7 +447,10 @@ def e2e_run(job, a, wl, table, ctx, groups_resident):
         how = "text (%.2f GB) -> mrhbm_map_wordcount in %d chunks -> commit -> shuffle -> result_copy" % (h2d / 1e9, len(cuts) - 1)
     else:
         host = ctx.pinned_array(n, mrhbm.record_dtype(wl["kind"], 27))
-        host_u64_records(synth.SEED, rank * n, n, host)
+        if wl["key"] == "u64seq":
+            host[:] = seq_records(rank * n, n)
+        else:
+            host_u64_records(synth.SEED, rank * n, n, host)
         chunk = 1 << 22
         h2d = n * rb
 

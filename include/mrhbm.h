@@ -33,7 +33,7 @@ enum { /* error codes */
   MRHBM_E_INVAL = -1,     /* bad argument / bad state */
   MRHBM_E_CUDA = -2,      /* CUDA runtime error (message has the CUDA string) */
   MRHBM_E_NOMEM = -3,     /* host or device allocation failed */
-  MRHBM_E_KEY = -4,       /* key does not fit the ctx record layout (too long) */
+  MRHBM_E_KEY = -4,       /* key does not fit: a fixed-width record or result slot, a word of the device tokeniser, > 1 MB */
   MRHBM_E_SKEW = -5,      /* a bin holds more distinct keys than one SM can sort */
   MRHBM_E_OVERFLOW = -6,  /* u32 partial sum overflow while combining string-keyed records */
   MRHBM_E_NCCL = -7,      /* NCCL missing or failed */
@@ -105,7 +105,12 @@ int mrhbm_map_begin(mrhbm_ctx *, const char *map_job_id, mrhbm_map **out);
 /* key bytes are copied before return (Lua strings may be collected).  Any byte string is a key: bytes 0x00 and
  * 0x01 are stored escaped (01 01 / 01 02, order preserving; each costs one more byte of the key slot), hashed by
  * the built-in partitioners as the original bytes and handed back unescaped by mrhbm_groups_next.  Key slots in
- * emit_batch records and in mrhbm_result_copy are in the stored (escaped) form. */
+ * emit_batch records and in mrhbm_result_copy are in the stored (escaped) form.
+ * A key LONGER than the ctx record class (max_key_bytes) is accepted too (the reference takes any key,
+ * utils.lua:104-110): such pairs are assumed rare, stay on the host, are partitioned (same partitioner), exchanged
+ * and grouped at the barrier, and mrhbm_groups_next hands them out at their place in the key order.  They follow
+ * commit / abort / replace-by-job-id like every other pair; the combiner does not see them; the fixed-width bulk
+ * calls (emit_batch, map_wordcount, result_copy, checksums) do not carry them. */
 int mrhbm_emit_str(mrhbm_map *, const void *key, size_t klen, uint32_t value);
 int mrhbm_emit_u64(mrhbm_map *, uint64_t key, uint64_t value); /* value < 2^53 keeps Lua-number sums exact */
 /* n records in the ctx layout.  Pageable memory is consumed before return; memory from
@@ -122,8 +127,9 @@ int mrhbm_map_gen_zipf(mrhbm_map *, uint64_t seed, uint64_t start, uint64_t n,
                        const uint64_t *table, uint64_t V);
 /* device-side WordCount mapfn (examples/WordCount/mapfn.lua:3-9, misc/naive.lua:2-5): emits
  * (word, 1) for every maximal run of non-space bytes of `text`; the space class is C-locale
- * isspace (' ' \t \n \v \f \r), i.e. Lua's "[^%s]+".  A word that does not fit the ctx record
- * class fails with MRHBM_E_KEY and emits nothing.  *words (optional) receives the token count. */
+ * isspace (' ' \t \n \v \f \r), i.e. Lua's "[^%s]+".  A 64 MB piece of the text that holds a word longer than
+ * the ctx record class (a URL in a corpus) is tokenised on the host instead, the long words going the way of
+ * mrhbm_emit_str's long keys.  On failure nothing of the call is emitted.  *words (optional) receives the token count. */
 int mrhbm_map_wordcount(mrhbm_map *, const void *text, size_t len, uint64_t *words);
 /* host-side generator of the synthetic word-count text of SURVEY App. B (bench + tests; needs no ctx):
  * words first .. first+n-1 of the Zipf(table) word stream, one space between words, '\n' after every
@@ -172,7 +178,8 @@ typedef struct mrhbm_result_info {
 int mrhbm_result_info_get(mrhbm_ctx *, mrhbm_result_info *);
 /* copies all groups of this rank, partition-major, to host: keys (groups*key_bytes; u64
  * keys native little endian) and sums (groups*8); part_off[P+1] receives group offsets.
- * Inside a partition the order is ascending iff info.sorted, else run-major. */
+ * Inside a partition the order is ascending iff info.sorted, else run-major.
+ * MRHBM_E_KEY when the result holds keys longer than a slot (see mrhbm_emit_str): iterate instead. */
 int mrhbm_result_copy(mrhbm_ctx *, void *keys, uint64_t *sums, uint64_t *part_off);
 /* size-independent parity properties computed on the device:
  *  in[0..3]  = { sum f1(key)*v, sum f2(key)*v, sum v, pairs }       over committed pairs

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -15,11 +16,23 @@
 #include "../../include/mrhbm.h"
 #include "mrhbm_comm.h"
 #include "mrhbm_kernels.h"
+#include "mrhbm_dev.cuh"  // fnv_lua_step, mulhi_u64_u32: the host side partitions the keys that do not fit a slot
 
 using namespace mrhbm;
 
 namespace {
 enum { R_OPEN = 0, R_COMMITTED = 1, R_DEAD = 2 };
+constexpr uint32_t kErrfLongKeys = 0x80000000u;  // rides on the error-flag all-gather of a multi-GPU shuffle: this rank holds long keys
+constexpr size_t kMaxLongKey = 1u << 20;  // bytes; longer keys are refused (MRHBM_E_KEY)
+struct LongPair {
+  std::string esc;  // the key as a record slot would hold it: 0x00 / 0x01 escaped (order preserving, see mrhbm_emit_str)
+  uint64_t value;
+};
+struct LongGroup {
+  std::string esc;
+  std::vector<uint64_t> values;  // built-in sum: one element
+};
+
 struct Range {
   uint64_t off, cnt;
   std::string job;
@@ -41,6 +54,13 @@ struct mrhbm_ctx {
   uint64_t pool_cap = 0, pool_used = 0;
   std::vector<Range> ranges;
   uint64_t map_serial = 0;
+  // Keys that do not fit a record slot (rare: the reference takes any key length, utils.lua:104-110) never reach the
+  // device: their pairs wait on the host, per committed map job, are partitioned and grouped at the barrier (on several
+  // GPUs after an all-gather) and merged into the reduce-side iteration at their place in the key order.
+  std::map<std::string, std::vector<LongPair>> long_jobs;  // committed pairs by job id (commit = replace-by-id)
+  std::vector<std::vector<LongGroup>> long_groups;         // after a shuffle: per owned partition, ascending escaped key
+  uint64_t long_group_count = 0;
+  bool any_long = false;  // several GPUs: some rank holds such pairs (learnt with the error flags every shuffle gathers anyway)
   // shuffle state
   ShuffleBuffers sb{};
   uint64_t B_cap = 0, mid_cap = 0, out_cap = 0;
@@ -106,6 +126,7 @@ struct mrhbm_ctx {
 struct mrhbm_map {
   mrhbm_ctx* ctx;
   std::string job;
+  std::vector<LongPair> long_pairs;  // keys longer than a record slot (host side, see mrhbm_ctx::long_jobs)
   uint64_t serial;
   unsigned char* stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -126,6 +147,8 @@ struct mrhbm_iter {
   std::vector<uint64_t> sums;
   std::vector<RunCursor> runs;
   uint64_t base = 0;
+  const std::vector<LongGroup>* longs = nullptr;  // the partition's long-key groups and the next one to hand out
+  size_t long_pos = 0;
   unsigned char keybuf[8];
   bool sorted = true;
   size_t cur_run = 0;
@@ -247,6 +270,8 @@ void map_release(mrhbm_map* m) {
 void invalidate(mrhbm_ctx* c) {
   c->shuffled = false;
   c->compacted = false;
+  c->long_groups.clear();
+  c->long_group_count = 0;
 }
 
 // per-bin arrays (offsets, group counts, spread-out atomic counters) for B bins
@@ -492,8 +517,22 @@ int mrhbm_emit_str(mrhbm_map* m, const void* key, size_t klen, uint32_t value) {
   const unsigned char* k = (const unsigned char*)key;
   size_t extra = 0;
   for (size_t i = 0; i < klen; i++) extra += k[i] <= 1;
-  if (klen + extra >= (size_t)c->kb)
-    return fail(c, MRHBM_E_KEY, "key of %zu bytes does not fit the %d-byte record class", klen + extra, c->rb);
+  if (klen + extra >= (size_t)c->kb) {  // longer than a record slot: kept on the host (escaped like a slot would hold it)
+    if (klen > kMaxLongKey) return fail(c, MRHBM_E_KEY, "key of %zu bytes (limit %zu)", klen, (size_t)kMaxLongKey);
+    LongPair lp;
+    lp.esc.reserve(klen + extra);
+    for (size_t i = 0; i < klen; i++) {
+      if (k[i] <= 1) {
+        lp.esc.push_back((char)1);
+        lp.esc.push_back((char)(k[i] + 1));
+      } else {
+        lp.esc.push_back((char)k[i]);
+      }
+    }
+    lp.value = value;
+    m->long_pairs.push_back(std::move(lp));
+    return MRHBM_OK;
+  }
   unsigned char* slot;
   int rc = stage_slot(m, &slot);
   if (rc) return rc;
@@ -636,10 +675,13 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
   // undo information: a word that does not fit emits NOTHING of this call
   const size_t nr0 = c->ranges.size();
   const uint64_t last_cnt0 = nr0 ? c->ranges.back().cnt : 0, used0 = c->pool_used;
+  const size_t long0 = m->long_pairs.size();
   auto undo = [&]() {
     c->ranges.resize(nr0);
     if (nr0) c->ranges.back().cnt = last_cnt0;
     c->pool_used = used0;
+    m->long_pairs.resize(long0);  // (words of a piece that was tokenised on the host)
+    m->fill = 0;                  // the staging buffer was empty when the call began (stage_flush above)
   };
   auto piece_end = [&](size_t p) -> size_t {  // end of the piece that starts at p: <= kTokPiece bytes, cut after white space
     size_t e = std::min(len, p + kTokPiece);
@@ -682,11 +724,27 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
       if ((e = cudaMemcpyAsync(c->h_small + 1, flagw, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) break;
       if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) break;
       if (c->h_small[1] & ERRF_KEYLEN) {
-        rc = fail(c, MRHBM_E_KEY, "a word is longer than the %d-byte key slot of this record class", c->kb - 1);
-        break;
+        // a word of this piece does not fit the key slot (a URL in a corpus): the piece's records are dropped again and
+        // the piece is tokenised on the host -- words that fit are staged like emit_str pairs, the long ones go to the
+        // host-side store of long keys.  Rare by assumption: 64 MB take a fraction of a second here.
+        c->pool_used = off;
+        uint64_t words_here = 0;
+        for (size_t a = p; a < pn && rc == 0;) {
+          while (a < pn && is_space(t[a])) a++;
+          size_t b = a;
+          while (b < pn && !is_space(t[b])) b++;
+          if (b > a) {
+            rc = mrhbm_emit_str(m, t + a, b - a, 1u);
+            words_here++;
+          }
+          a = b;
+        }
+        if (rc) break;
+        total_words += words_here;
+      } else {
+        add_range(m, off, total);
+        total_words += total;
       }
-      add_range(m, off, total);
-      total_words += total;
     }
     p = pn;
     pe = pne;
@@ -708,13 +766,7 @@ int mrhbm_map_wordcount(mrhbm_map* m, const void* text, size_t len, uint64_t* wo
 
 // ---- synthetic word-count text, host side: the input of the end-to-end word-count measurements
 namespace {
-inline uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  uint64_t z = x;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
+// (splitmix64: mrhbm_dev.cuh)
 inline int synth_rank_to_key(uint64_t rank, char* out) {  // bijective base 26 prefix + hashed upper-case suffix
   char tmp[16];
   int n = 0, o = 0;
@@ -821,6 +873,8 @@ int mrhbm_map_commit(mrhbm_map* m) {
   }
   for (Range& r : c->ranges)
     if (r.owner == m->serial && r.state == R_OPEN) r.state = R_COMMITTED;
+  c->long_jobs.erase(m->job);  // replace-by-job-id on the host side too
+  if (!m->long_pairs.empty()) c->long_jobs[m->job] = std::move(m->long_pairs);
   invalidate(c);
   map_release(m);
   return MRHBM_OK;
@@ -846,6 +900,7 @@ int mrhbm_reset(mrhbm_ctx* c) {
   Entry g(c);
   c->ranges.clear();
   c->pool_used = 0;
+  c->long_jobs.clear();
   invalidate(c);
   return MRHBM_OK;
 }
@@ -1330,9 +1385,11 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     uint32_t ef = c->h_counters[CNT_ERR];
     if (G > 1) {  // every rank must take the same branch; also: nobody leaves while a peer still reads its regions
       uint32_t efs[8];
-      rc = gather_u32(c, ef, efs);
+      rc = gather_u32(c, ef | (c->long_jobs.empty() ? 0u : kErrfLongKeys), efs);
       if (rc) return rc;
       for (int r = 0; r < G; r++) ef |= efs[r];
+      c->any_long = (ef & kErrfLongKeys) != 0;
+      ef &= ~kErrfLongKeys;
     }
     if (ef & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
     if (ef & ERRF_CAPACITY) {  // skewed keys: the exact layout from now on
@@ -1658,10 +1715,12 @@ int shuffle_multi_exact(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
     uint32_t ef = c->h_counters[CNT_ERR];
-    rc = gather_u32(c, ef, all);  // every rank must take the same branch
+    rc = gather_u32(c, ef | (c->long_jobs.empty() ? 0u : kErrfLongKeys), all);  // every rank must take the same branch
     if (rc) return rc;
     uint32_t ef_any = 0;
     for (int r = 0; r < G; r++) ef_any |= all[r];
+    c->any_long = (ef_any & kErrfLongKeys) != 0;
+    ef_any &= ~kErrfLongKeys;
     if (ef_any & ERRF_OVERFLOW) return fail(c, MRHBM_E_OVERFLOW, "u32 partial sum overflow while combining a hot key");
     if (ef_any & ERRF_SKEW) {
       if (widen < 4 && (uint64_t)P * S * 2 < (1ull << 31)) {
@@ -1699,6 +1758,124 @@ inline int64_t slot_of(const mrhbm_ctx* c, uint32_t p) {
 
 }  // namespace
 
+namespace {
+// ---- keys longer than a record slot: partitioned, exchanged and grouped on the host --------------------------
+std::string unescape_key(const std::string& esc) {
+  std::string raw;
+  raw.reserve(esc.size());
+  for (size_t i = 0; i < esc.size(); i++) {
+    if (esc[i] == 1 && i + 1 < esc.size())
+      raw.push_back((char)(esc[++i] - 1));
+    else
+      raw.push_back(esc[i]);
+  }
+  return raw;
+}
+// the partition bin_of (mrhbm_dev.cuh) would give the key if it fitted a slot: FNV-in-doubles over the ORIGINAL bytes
+// (examples/WordCount/partitionfn.lua:8-16), or the word hash over the little-endian words of the STORED bytes
+uint32_t host_partition(const mrhbm_ctx* c, const std::string& esc) {
+  const uint32_t P = c->cfg.num_partitions;
+  if (c->cfg.partitioner == MRHBM_PART_FNV_LUA) {
+    uint32_t h = 2166136261u;
+    for (unsigned char b : unescape_key(esc)) h = fnv_lua_step(h, b);
+    return h % P;
+  }
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  for (size_t i = 0; i < esc.size(); i += 4) {
+    uint32_t w = 0;
+    memcpy(&w, esc.data() + i, std::min<size_t>(4, esc.size() - i));
+    h = (h ^ w) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
+  }
+  h ^= h >> 32;
+  h *= 0x94D049BB133111EBull;
+  return mulhi_u64_u32(h, P);
+}
+
+int build_long_groups(mrhbm_ctx* c) {
+  c->long_groups.clear();
+  c->long_group_count = 0;
+  const int G = c->world;
+  // this rank's committed long pairs as one blob: {u32 key bytes, u64 value, key bytes padded to 4}*
+  std::vector<uint32_t> blob;
+  for (auto& job : c->long_jobs)
+    for (const LongPair& lp : job.second) {
+      const size_t w0 = blob.size(), kw = (lp.esc.size() + 3) / 4;
+      blob.resize(w0 + 3 + kw, 0u);
+      blob[w0] = (uint32_t)lp.esc.size();
+      memcpy(&blob[w0 + 1], &lp.value, 8);
+      memcpy(&blob[w0 + 3], lp.esc.data(), lp.esc.size());
+    }
+  std::vector<uint32_t> all_blobs;
+  std::vector<uint32_t> sizes(G, 0u);
+  if (G == 1) {
+    if (blob.empty()) return MRHBM_OK;
+    sizes[0] = (uint32_t)blob.size();
+    all_blobs.swap(blob);
+  } else {  // COLLECTIVE, entered by all ranks or none (any_long travelled with the shuffle's error flags): sizes first,
+            // then the blobs padded to the largest
+    if (!c->any_long) return MRHBM_OK;
+    if (blob.size() >= (1u << 28)) return fail(c, MRHBM_E_NOMEM, "more than 1 GB of long keys on one rank");
+    int rc = gather_u32(c, (uint32_t)blob.size(), sizes.data());
+    if (rc) return rc;
+    uint32_t mx = 0;
+    for (int r = 0; r < G; r++) mx = std::max(mx, sizes[r]);
+    if (!mx) return MRHBM_OK;
+    uint32_t *d_send = nullptr, *d_recv = nullptr;
+    CU(c, cudaMalloc((void**)&d_send, (size_t)mx * 4));
+    cudaError_t e = cudaMalloc((void**)&d_recv, (size_t)mx * 4 * G);
+    if (e != cudaSuccess) {
+      cudaFree(d_send);
+      cudaGetLastError();
+      return fail(c, MRHBM_E_NOMEM, "long keys: %s", cudaGetErrorString(e));
+    }
+    blob.resize(mx, 0u);
+    all_blobs.resize((size_t)mx * G);
+    e = cudaMemcpyAsync(d_send, blob.data(), (size_t)mx * 4, cudaMemcpyHostToDevice, c->stream);
+    int rc2 = e == cudaSuccess ? comm_allgather_u32(c->comm, d_send, d_recv, mx, c->stream, &c->err) : 0;
+    if (e == cudaSuccess && !rc2) e = cudaMemcpyAsync(all_blobs.data(), d_recv, (size_t)mx * 4 * G, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && !rc2) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (rc2) return rc2;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, MRHBM_E_CUDA, "long keys: %s", cudaGetErrorString(e));
+    }
+    // compact: rank r's blob starts at r * mx and holds sizes[r] words
+    std::vector<uint32_t> packed;
+    for (int r = 0; r < G; r++) packed.insert(packed.end(), all_blobs.begin() + (size_t)r * mx, all_blobs.begin() + (size_t)r * mx + sizes[r]);
+    all_blobs.swap(packed);
+  }
+  // group the pairs of the partitions this rank owns (partition p lives on rank p % G, slot p / G)
+  std::vector<std::map<std::string, std::vector<uint64_t>>> acc(c->Pl);
+  const bool sum = c->cfg.reducer != MRHBM_RED_NONE;
+  for (size_t w = 0; w + 3 <= all_blobs.size();) {
+    const uint32_t klen = all_blobs[w];
+    uint64_t v;
+    memcpy(&v, &all_blobs[w + 1], 8);
+    std::string esc((const char*)&all_blobs[w + 3], klen);
+    w += 3 + (klen + 3) / 4;
+    const uint32_t pid = host_partition(c, esc);
+    if ((int)(pid % (uint32_t)G) != c->rank) continue;
+    const uint32_t slot = pid / (uint32_t)G;
+    if (slot >= c->Pl) continue;
+    std::vector<uint64_t>& vals = acc[slot][esc];
+    if (sum && !vals.empty())
+      vals[0] += v;
+    else
+      vals.push_back(v);
+  }
+  c->long_groups.resize(c->Pl);
+  for (uint32_t sl = 0; sl < c->Pl; sl++)
+    for (auto& kv : acc[sl]) {  // std::map iterates in ascending bytewise key order (unsigned char_traits compare)
+      c->long_groups[sl].push_back(LongGroup{kv.first, std::move(kv.second)});
+      c->long_group_count++;
+    }
+  return MRHBM_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int mrhbm_shuffle(mrhbm_ctx* c) {
@@ -1721,9 +1898,10 @@ int mrhbm_shuffle(mrhbm_ctx* c) {
     bool done = false;
     rc = shuffle_fast(c, live, N, N_in, st, &done);
     if (rc) return rc;
-    if (done) return MRHBM_OK;
+    if (done) return build_long_groups(c);
   }
-  return c->world > 1 ? shuffle_multi_exact(c, live, N, N_in, st) : shuffle_single_exact(c, live, N, N_in, st);
+  rc = c->world > 1 ? shuffle_multi_exact(c, live, N, N_in, st) : shuffle_single_exact(c, live, N, N_in, st);
+  return rc ? rc : build_long_groups(c);
 }
 
 int mrhbm_stats_get(mrhbm_ctx* c, mrhbm_stats* out) {
@@ -1739,7 +1917,8 @@ int mrhbm_partitions(mrhbm_ctx* c, uint32_t* ids, size_t cap, size_t* n) {
   if (!c->shuffled) return fail(c, MRHBM_E_INVAL, "no shuffle result (call mrhbm_shuffle first)");
   size_t k = 0;
   for (uint32_t i = 0; i < c->Pl; i++) {
-    if (c->h_uoff[(uint64_t)(i + 1) * c->S] > c->h_uoff[(uint64_t)i * c->S]) {
+    const bool longs = i < c->long_groups.size() && !c->long_groups[i].empty();
+    if (c->h_uoff[(uint64_t)(i + 1) * c->S] > c->h_uoff[(uint64_t)i * c->S] || longs) {
       if (ids && k < cap) ids[k] = (uint32_t)c->rank + i * (uint32_t)c->world;
       k++;
     }
@@ -1769,6 +1948,9 @@ int mrhbm_result_copy(mrhbm_ctx* c, void* keys, uint64_t* sums, uint64_t* part_o
   Entry g(c);
   int rc = ensure_compact(c);
   if (rc) return rc;
+  if (c->long_group_count)
+    return fail(c, MRHBM_E_KEY, "%llu groups have keys longer than the %d-byte slots of mrhbm_result_copy: iterate with mrhbm_groups_*",
+                (unsigned long long)c->long_group_count, c->kb);
   if (keys && c->groups) CU(c, cudaMemcpyAsync(keys, c->ckeys, c->groups * c->kb, cudaMemcpyDeviceToHost, c->stream));
   if (sums && c->groups) CU(c, cudaMemcpyAsync(sums, c->csums, c->groups * 8, cudaMemcpyDeviceToHost, c->stream));
   if (part_off)
@@ -1844,6 +2026,7 @@ int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
       return fail(c, MRHBM_E_CUDA, "groups_open: %s", cudaGetErrorString(e));
     }
   }
+  if ((uint64_t)slot < c->long_groups.size() && !c->long_groups[(size_t)slot].empty()) it->longs = &c->long_groups[(size_t)slot];
   it->sorted = (c->ordered || c->S == 1) && c->h_big.empty();
   if (it->sorted) {
     it->runs.push_back(RunCursor{0, hi - lo});
@@ -1871,6 +2054,28 @@ int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint
   for (size_t r = 0; r < it->runs.size(); r++) {
     if (it->runs[r].pos >= it->runs[r].end) continue;
     if (best < 0 || slot_cmp(c, &it->keys[it->runs[r].pos * c->kb], &it->keys[it->runs[best].pos * c->kb]) < 0) best = (int)r;
+  }
+  if (it->longs && it->long_pos < it->longs->size()) {
+    // a key longer than a slot comes next when it sorts before the smallest device key: both are compared as the
+    // escaped byte strings a slot holds (the device key ends at its zero padding; a proper prefix sorts first)
+    const LongGroup& lg = (*it->longs)[it->long_pos];
+    bool take = best < 0;
+    if (!take) {
+      const unsigned char* dk = &it->keys[it->runs[best].pos * c->kb];
+      const size_t dl = strnlen((const char*)dk, c->kb);
+      const int cmp = memcmp(lg.esc.data(), dk, std::min(dl, lg.esc.size()));
+      take = cmp < 0 || (cmp == 0 && lg.esc.size() < dl);
+    }
+    if (take) {
+      it->long_pos++;
+      const std::string raw = unescape_key(lg.esc);
+      it->unesc.assign(raw.begin(), raw.end());
+      *key = it->unesc.data();
+      *klen = it->unesc.size();
+      *values = lg.values.data();
+      *nvalues = lg.values.size();
+      return 1;
+    }
   }
   if (best < 0) return 0;
   uint64_t i = it->runs[best].pos++;

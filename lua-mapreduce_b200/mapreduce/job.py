@@ -93,9 +93,17 @@ class Job:
             return None
         cache = getattr(b, "_bulk", None)
         if cache is None or cache[0] is not ctx or cache[1] != b.iteration:
-            keys, sums, po = ctx.result_copy()
+            try:
+                keys, sums, po = ctx.result_copy()
+            except Exception as e:  # keys longer than a result slot live on the host side: the iterator merges them in
+                if getattr(e, "code", None) != -4:  # MRHBM_E_KEY
+                    raise
+                b._bulk = (ctx, b.iteration, None, None, None, False)
+                return None
             cache = b._bulk = (ctx, b.iteration, keys, sums, po, bool(ctx.result_info().sorted))
         _, _, keys, sums, po, is_sorted = cache
+        if keys is None:
+            return None
         a, e = int(po[part]), int(po[part + 1])
         k, v = keys[a:e], sums[a:e]
         if not is_sorted:  # several ascending runs (hash sub-bins): merge = stable sort by key

@@ -145,6 +145,38 @@ def run_group_only(rank, world, P):
               % (world, P, len(got), len(got[hot]), st["big_bins"]), flush=True)
 
 
+def run_long_keys(rank, world, P):
+    """Keys that do not fit a record slot (host side store): every rank emits them, the barrier all-gathers them and
+    the owner of a key's partition groups them; the job's result is the oracle engine's."""
+    import oracle as O
+    rng = np.random.default_rng(100 + rank)
+    stem = b"abcdefghijklmnopqrstuvwxyz0"
+    longs = [stem + b"X", stem + b"Y" * 300, b"q" * 4000, stem + b"\x00\x01z", b"w" * 28]
+    pairs = [(O.rank_to_key(int(r)), int(v)) for r, v in zip(rng.integers(1, 500, 3000), rng.integers(1, 100, 3000))]
+    pairs += [(k, rank + 1 + i) for i, k in enumerate(longs)] * 2
+    pairs += [(b"only-rank-%d-" % rank + b"L" * 100, 5)]
+    with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, max_key_bytes=27, device=int(os.environ["LOCAL_RANK"])) as ctx:
+        parallel.init_comm(ctx, dist)
+        m = ctx.map_begin("r%d" % rank)
+        for k, v in pairs:
+            m.emit(k, v)
+        m.commit()
+        ctx.shuffle()
+        got = parallel.gather_final_pairs(ctx, dist)
+        allp = [None] * world if rank == 0 else None
+        dist.gather_object(pairs, allp, dst=0)
+        if rank != 0:
+            return
+        e = O.Engine(O.PART_FNV_LUA, P, combiner=-1, reducer=O.RED_SUM, aci=True)
+        for j, pp in enumerate(allp):
+            e.map_job(j, pairs=pp)
+        e.reduce_all()
+        want = [(p_, k, [int(x) for x in v]) for p_, k, v in e.final_pairs()]
+        check("long keys over all ranks", got == want)
+        print("long keys world=%d P=%d ok: groups=%d of them longer than a slot=%d"
+              % (world, P, len(want), sum(len(k) > 27 for _, k, _ in want)), flush=True)
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -159,6 +191,7 @@ def main():
     run_zipf(rank, world, 200_000, 15)
     run_zipf(rank, world, 1_500_000, 15, combiner=True)  # local combine (global table) on every rank, then the exchange
     run_group_only(rank, world, 5)
+    run_long_keys(rank, world, 15)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world=%d" % world, flush=True)

@@ -182,6 +182,7 @@ def test_keys_with_nul_and_control_bytes():
     keys = [b"", b"a", b"a\0", b"a\0\0", b"a\1", b"a\1\1", b"a\2", b"ab", b"\0", b"\1", b"\0a", b"\1\0\1"]
     keys += [b"".join(alphabet[j] for j in rng.integers(0, len(alphabet), rng.integers(1, 12))) for _ in range(3000)]
     pairs = [(keys[j], int(v)) for j, v in zip(rng.integers(0, len(keys), 40_000), rng.integers(0, 1000, 40_000))]
+    pairs += [(b"\0" * 14, 3), (b"\0" * 13, 4), (b"\0" * 14, 5)]  # 14 NULs need 28 slot bytes: one too many for the record
     eng = O.Engine(O.PART_FNV_LUA, 15, combiner=-1, reducer=O.RED_SUM, aci=True)
     for job in range(4):
         eng.map_job(job + 1, pairs=pairs[job::4])
@@ -193,11 +194,90 @@ def test_keys_with_nul_and_control_bytes():
             for k, v in pairs[job::4]:
                 m.emit(k, v)
             m.commit()
-        with pytest.raises(mrhbm.MrhbmError):  # 14 NULs need 28 slot bytes
-            ctx.map_begin(9).emit(b"\0" * 14, 1)
         ctx.shuffle()
         got = [(p, k, v) for p in ctx.partitions() for k, v in ctx.groups(p)]
     assert got == want
+
+
+def test_keys_longer_than_a_record_slot():
+    """The reference takes keys of any length (utils.lua:104-110).  Pairs whose key does not fit the ctx record class
+    stay on the host, are partitioned with the same FNV-in-doubles partitioner, grouped at the barrier and merged
+    into the reduce-side iteration at their place in the bytewise key order -- also next to device keys that are
+    their proper prefixes, with NUL bytes inside, across map jobs, after a re-commit and an abort."""
+    rng = np.random.default_rng(31)
+    P = 15
+    short = [O.rank_to_key(int(r)) for r in rng.integers(1, 3000, 20_000)]
+    stem = b"abcdefghijklmnopqrstuvwxyz0"  # 27 bytes: the longest key a 32-byte record holds
+    longs = [stem + b"X", stem + b"X" * 40, stem + b"\x00tail", stem + b"Y" * 200, b"q" * 5000, b"\x01" * 20, b"z" * 28,
+             bytes(range(1, 200)), stem[:20] + b"\x00" * 8]
+    jobs = []
+    for j in range(3):
+        pairs = [(w, int(v)) for w, v in zip(short[j::3], rng.integers(1, 1000, len(short[j::3])))]
+        pairs += [(stem, 7 + j), (stem[:26], 1)]  # device keys that are proper prefixes of long ones
+        pairs += [(k, int(v)) for k, v in zip(longs, rng.integers(1, 1 << 31, len(longs)))] * (j + 1)
+        rng.shuffle(pairs)
+        jobs.append(pairs)
+    e = O.Engine(O.PART_FNV_LUA, P, combiner=-1, reducer=O.RED_SUM, aci=True)
+    for j, pairs in enumerate(jobs):
+        e.map_job(j, pairs=pairs)
+    e.reduce_all()
+    want = [(p, k, [int(x) for x in v]) for p, k, v in e.final_pairs()]
+    for combiner in (False, True):
+        with mrhbm.Ctx(mrhbm.KEY_STR, P, mrhbm.PART_FNV_LUA, max_key_bytes=27, combiner=combiner) as ctx:
+            m = ctx.map_begin(1)  # a first version of job 1 that the re-commit below replaces, long keys included
+            m.emit(b"gone" * 20, 5)
+            m.emit(b"gone", 5)
+            m.commit()
+            for j, pairs in enumerate(jobs):
+                m = ctx.map_begin(j)
+                for k, v in pairs:
+                    m.emit(k, v)
+                m.commit()
+            m = ctx.map_begin("broken")
+            m.emit(b"never" * 30, 1)
+            m.abort()
+            ctx.shuffle()
+            got = [(p, k, v) for p in ctx.partitions() for k, v in ctx.groups(p)]
+            assert got == want
+            with pytest.raises(mrhbm.MrhbmError) as ei:  # fixed-width rows cannot hold them
+                ctx.result_copy()
+            assert ei.value.code == -4
+            ctx.reset()  # the next task iteration starts empty on the host side too
+            m = ctx.map_begin(0)
+            m.emit(b"only", 1)
+            m.commit()
+            ctx.shuffle()
+            assert [(k, v) for p in ctx.partitions() for k, v in ctx.groups(p)] == [(b"only", [1])]
+            # the device tokeniser meets a word that does not fit: that piece of the text is tokenised on the host
+            ctx.reset()
+            url = b"http://" + b"x" * 300
+            text = b"aa bb " + url + b"\ncc aa\t" + url + b" " + b"y" * 28
+            m = ctx.map_begin("text")
+            assert m.wordcount(text) == 7
+            m.commit()
+            ctx.shuffle()
+            assert sorted((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p)) == \
+                sorted({b"aa": 2, b"bb": 1, b"cc": 1, url: 2, b"y" * 28: 1}.items())
+    # general reducer: every value of a long key; the other partitioner: each key in exactly one partition, ascending
+    with mrhbm.Ctx(mrhbm.KEY_STR, 4, mrhbm.PART_WORDHASH, max_key_bytes=27, reducer=mrhbm.RED_NONE) as ctx:
+        for j, pairs in enumerate(jobs):
+            m = ctx.map_begin(j)
+            for k, v in pairs:
+                m.emit(k, v)
+            m.commit()
+        ctx.shuffle()
+        allv = {}
+        for pairs in jobs:
+            for k, v in pairs:
+                allv.setdefault(k, []).append(v)
+        seen = {}
+        for p in ctx.partitions():
+            ks = [k for k, _ in ctx.groups(p)]
+            assert ks == sorted(ks)
+            for k, v in ctx.groups(p):
+                assert k not in seen
+                seen[k] = sorted(v)
+        assert seen == {k: sorted(v) for k, v in allv.items()}
 
 
 def test_u64_clustered_keys_fall_back_to_runs():
@@ -369,10 +449,13 @@ def test_commit_replaces_abort_discards_and_empty_shuffle():
         ctx.shuffle()
         assert ctx.partitions() == [10]  # "a" -> partition 10
         assert list(ctx.groups(10)) == [(b"a", [5])]
+        m = ctx.map_begin(4)
+        m.emit(b"x" * 28, 1)  # does not fit the 32-byte record class: kept on the host (test_keys_longer_than_a_record_slot)
         with pytest.raises(mrhbm.MrhbmError):
-            m = ctx.map_begin(4)
-            m.emit(b"x" * 28, 1)  # does not fit the 32-byte record class
+            m.emit(b"x" * ((1 << 20) + 1), 1)  # beyond the 1 MB limit
         m.abort()
+        ctx.shuffle()
+        assert list(ctx.groups(10)) == [(b"a", [5])]  # the aborted job left nothing, on the device or beside it
         ctx.reset()
         ctx.shuffle()
         assert ctx.partitions() == []
@@ -537,9 +620,8 @@ def test_device_tokeniser_wordcount_golden(golden_vectors, golden_wordcount):
         assert sorted((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p)) == wc
         m = ctx.map_begin("long")
         m.emit(b"ok", 1)
-        with pytest.raises(mrhbm.MrhbmError) as err:
-            m.wordcount(b"fits " + b"x" * 28 + b" tail")
-        assert err.value.code == -4
+        assert m.wordcount(b"fits " + b"x" * 28 + b" tail") == 3  # a word longer than the slot: this piece goes through the host
         m.commit()
         ctx.shuffle()
-        assert dict((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p))[b"ok"] == 1
+        got = dict((k, v[0]) for p in ctx.partitions() for k, v in ctx.groups(p))
+        assert got[b"ok"] == 1 and got[b"x" * 28] == 1 and got[b"fits"] == 1 and got[b"tail"] == 1
