@@ -175,6 +175,8 @@ typedef struct mrhbm_result_info {
   uint32_t runs_per_partition;
   uint32_t partitions_nonempty;
 } mrhbm_result_info;
+/* `groups` counts the rows mrhbm_result_copy returns; groups whose key is longer than a slot (mrhbm_emit_str) are not
+ * among them -- mrhbm_partitions and mrhbm_groups_* see both kinds. */
 int mrhbm_result_info_get(mrhbm_ctx *, mrhbm_result_info *);
 /* copies all groups of this rank, partition-major, to host: keys (groups*key_bytes; u64
  * keys native little endian) and sums (groups*8); part_off[P+1] receives group offsets.

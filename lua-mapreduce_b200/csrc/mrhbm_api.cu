@@ -85,7 +85,9 @@ struct mrhbm_ctx {
   uint64_t l1all_cap = 0;
   uint32_t *d_ipc = nullptr, *h_ipc = nullptr;  // 16 words per rank: the IPC handles
   uint32_t *d_sample = nullptr, *h_sample = nullptr;  // 256 buckets of the key sample
-  uint32_t tune = 0;                          // MRHBM_TUNE bits read once at init (measurement hooks): 1 = no fast path
+  uint32_t tune = 0;                          // MRHBM_TUNE, read once at init, measurement hooks only: bit 0 = no fast path,
+                                              // bit 6 = print when the CTAs of level 1 and of the combiner start / end (with bit 24:
+                                              // of the u64 sort), bits 8-15 = the combiner's L2 prefetch distance in trips
   std::recursive_mutex mu;                    // entry points serialise per ctx
   uint32_t *d_small = nullptr, *h_small = nullptr;  // 64 words each
   bool no_optimistic = false;  // sticky: a fixed-capacity bin overflowed once (skewed keys)
@@ -1327,10 +1329,8 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaMemsetAsync(c->sb.hist, 0, (((uint64_t)pl.C1) << c->ctr_shift) * sizeof(uint32_t), s));
     if (!single_level) CU(c, cudaMemsetAsync(c->sb.cursor, 0, (std::max<uint64_t>(Bl, 1) << c->ctr_shift) * sizeof(uint32_t), s));
     CU(c, cudaMemsetAsync(c->sb.counters, 0, 8 * sizeof(uint32_t), s));
-    if (c->tune & 128u)  // measurement hook: leave the L2 clean (a read sweep of 128 MB) before level 1
-      for (auto& r : live) launch_checksum_in(c->rb, r.p, std::min<uint64_t>(r.n, (128ull << 20) / c->rb), c->d_acc, s);
-    if (c->tune & 64u) {  // measurement hook: when do the CTAs of level 1 (bit 8 set: of the u64 sort) start and end (%globaltimer)?
-      if (!(c->tune & 256u)) pl.span = (unsigned long long*)(c->d_acc + 4);
+    if (c->tune & 64u) {  // measurement hook: when do the CTAs of level 1 (bit 24 set: of the u64 sort) start and end (%globaltimer)?
+      if (!(c->tune & (1u << 24))) pl.span = (unsigned long long*)(c->d_acc + 4);
       CU(c, cudaMemsetAsync(c->d_acc + 4, 0xff, 8, s));
       CU(c, cudaMemsetAsync(c->d_acc + 5, 0, 16, s));
       CU(c, cudaMemsetAsync(c->d_acc + 7, 0xff, 8, s));
@@ -1358,7 +1358,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     ShuffleBuffers v = c->sb;
     v.cursor = fine_cursor;
     set_range_hint(v, S, ordered);
-    if ((c->tune & 64u) && (c->tune & 256u)) v.span = (unsigned long long*)(c->d_acc + 4);
+    if ((c->tune & 64u) && (c->tune & (1u << 24))) v.span = (unsigned long long*)(c->d_acc + 4);
     if (Bl) st.launches += launch_sort_reduce(c->rb, v, (uint32_t)Bl, c->cap, c->sm_count, s);
     v.span = nullptr;
     CU(c, cudaEventRecord(c->ev[EV_SORT], s));
@@ -1379,7 +1379,7 @@ int shuffle_fast(mrhbm_ctx* c, std::vector<Src>& live, uint64_t N, uint64_t N_in
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
     if (c->tune & 64u)
-      fprintf(stderr, (c->tune & 256u) ? "[mrhbm] u64 sort: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (level 1 events: %.3f ms)\n" : "[mrhbm] level 1: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (events: %.3f ms)\n",
+      fprintf(stderr, (c->tune & (1u << 24)) ? "[mrhbm] u64 sort: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (level 1 events: %.3f ms)\n" : "[mrhbm] level 1: CTAs start over %.3f ms, first ends after %.3f ms, last after %.3f ms (events: %.3f ms)\n",
               (c->h_acc[6] - c->h_acc[4]) * 1e-6, (c->h_acc[7] - c->h_acc[4]) * 1e-6, (c->h_acc[5] - c->h_acc[4]) * 1e-6,
               ev_ms(c, EV_HIST, EV_PLAN));
     uint32_t ef = c->h_counters[CNT_ERR];

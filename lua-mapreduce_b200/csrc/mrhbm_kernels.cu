@@ -286,7 +286,6 @@ struct SplitArgs {
   uint32_t rbase[9], fbase[9];
   uint32_t ndest, me;
   unsigned long long* span;  // measurement hook or nullptr (SplitPlan::span)
-  uint32_t stagger_ns;       // the second wave of CTAs (the co-residents of the first) starts this much later
   uint32_t* ticket;          // level 1, optimistic layout: {next tile - gridDim.x, CTAs that have left}, both 0 at launch
 };
 
@@ -362,7 +361,6 @@ __global__ void __launch_bounds__(THREADS_, MINB) k_split_tma(SplitArgs a, BinPa
     atomicMin(a.span + 0, t);  // first CTA start
     atomicMax(a.span + 2, t);  // last CTA start
   }
-  if (a.stagger_ns && blockIdx.x >= (gridDim.x >> 1)) __nanosleep(a.stagger_ns);
 #pragma unroll
   for (int i = 0; i < 9; i++)
     if (tid == (uint32_t)i) {
@@ -1024,7 +1022,6 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
   for (uint32_t i = tid; i < entries * (KC + 2); i += blockDim.x) tag[i] = 0;
   __syncthreads();
   const uint32_t gmask = (1u << glog) - 1u;
-  // tune (MRHBM_TUNE, measurement only, results invalid): 4 = misses are dropped
   auto append = [&](bool p, const uint4& E, uint32_t probe) {  // collective: the entries of the lanes with p go to the tail
     const uint32_t m = __ballot_sync(0xffffffffu, p);
     if (p) {
@@ -1197,7 +1194,7 @@ __global__ void __launch_bounds__(kCombineThreads, 1)
         __syncwarp();
       }
     }
-    const bool p = need && is_short && !(tune & 4u);
+    const bool p = need && is_short;
     if (__any_sync(0xffffffffu, p)) push(p, R::kU64 ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(w[0], w[1], w[2], (uint32_t)v));
   }
   __syncthreads();
@@ -1589,7 +1586,6 @@ static SplitArgs split_args(const BinParams& bp, const SplitPlan& pl) {
   a.err_flags = pl.err_flags;
   a.span = pl.span;
   a.ticket = pl.ticket;
-  a.stagger_ns = ((g_tune >> 16) & 0xffu) * 250u;
   a.ndest = pl.base_off ? 1u : pl.ndest;
   a.me = pl.base_off ? 0u : pl.me;
   for (int d = 0; d < 8; d++) a.peer[d] = pl.base_off ? 0ull : pl.peer[d];
