@@ -1448,10 +1448,11 @@ cudaError_t kernels_configure() {
 
   CFG(16) CFG(32) CFG(64) CFG(128)
 #undef CFG
-  e = cudaFuncSetAttribute(k_sort_reduce_u64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
+#define CFGS(M, X)                                                                                                       \
+  e = cudaFuncSetAttribute(k_sort_reduce_u64<M, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16)); \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_sort_reduce_u64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem_bytes(16));
-  if (e != cudaSuccess) return e;
+  CFGS(false, false) CFGS(false, true) CFGS(true, false) CFGS(true, true)
+#undef CFGS
 #define CFGC1(RB, CH)                                                                                      \
   e = cudaFuncSetAttribute(k_combine<RB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmem);  \
   if (e != cudaSuccess) return e;
@@ -1664,12 +1665,14 @@ int launch_sort_reduce(int rb, const ShuffleBuffers& b, uint32_t B, uint32_t cap
                        cudaStream_t s) {
   int grid = (int)(B < (uint32_t)(2 * sm_count) ? B : (uint32_t)(2 * sm_count));
   if (grid < 1) grid = 1;
-  // u64 keys in key-ordered sub-bins read from one segment: the register-pipelined variant
-  if (rb == 16 && b.hint_S > 1) {
-    if (b.stride || b.nseg == 1)
-      k_sort_reduce_u64<false><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
-    else
-      k_sort_reduce_u64<true><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+  // u64 keys: the register-pipelined variant -- the key range of a bin from its index (key-ordered sub-bins) or from a
+  // min / max over its records (hash sub-bins of clustered or sequential keys: 2.18 -> see profiles/README.md)
+  if (rb == 16) {
+    const bool multi = !(b.stride || b.nseg == 1), minmax = !(b.hint_S > 1);
+    if (!multi && !minmax) k_sort_reduce_u64<false, false><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+    if (!multi && minmax) k_sort_reduce_u64<false, true><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+    if (multi && !minmax) k_sort_reduce_u64<true, false><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
+    if (multi && minmax) k_sort_reduce_u64<true, true><<<grid, kSortThreads, sort_smem_bytes(16), s>>>(b, B, cap);
     return 1;
   }
   DISPATCH_RB(rb, (k_sort_reduce<RB><<<grid, kSortThreads, sort_smem_bytes(RB), s>>>(b, B, cap)));

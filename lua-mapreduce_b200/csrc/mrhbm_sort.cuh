@@ -549,7 +549,9 @@ __device__ __forceinline__ uint32_t block_exscan_u16x4(uint16_t* a, uint32_t n) 
 
 // MULTI: a bin is gathered from one segment per source rank (after the all-to-all); a small
 // descriptor (cumulative counts + rebased segment addresses) is built by warp 0 one bin ahead.
-template <bool MULTI>
+// MINMAX: the bins are not key-ordered sub-bins (hash sub-bins of clustered / sequential keys, or one bin per partition):
+// the range of a bin's keys is not known from its index, the CTA finds it with a min / max over the loaded records.
+template <bool MULTI, bool MINMAX = false>
 __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuffers b, uint32_t B, uint32_t cap) {
   constexpr int RB = 16;
   constexpr uint32_t CAP = kCapBytes / RB, NB = 2 * CAP, T = kSortThreads;
@@ -611,9 +613,11 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
   // bucket shift serves every bin.  32-bit sort key of a record inside its bin: the top 32 significant bits of
   // key - sub * q (all of them when q + S has at most 32 bits).  Its top kLogNB bits are the bucket; two records of
   // one bucket tie on it with probability 2^-20 (or are real duplicates), and only then are the 64-bit keys compared.
-  const int bits = 64 - __clzll((long long)(b.hint_q + b.hint_S));
-  const int sh0 = bits > 32 ? bits - 32 : 0, sh1 = (bits > kLogNB ? bits - kLogNB : 0) - sh0;
-  uint32_t sub = bin % b.hint_S;
+  const uint32_t hint_S = MINMAX ? 1u : b.hint_S;
+  const int bits_h = 64 - __clzll((long long)(b.hint_q + hint_S));
+  const int sh0_h = bits_h > 32 ? bits_h - 32 : 0, sh1_h = (bits_h > kLogNB ? bits_h - kLogNB : 0) - sh0_h;
+  uint32_t sub = bin % hint_S;
+  __shared__ unsigned long long s_mm[2][kSortThreads / 32];  // MINMAX: per-warp min / max of the bin's keys
   // After its first bin (blockIdx.x) a CTA takes the next bin nobody has from a ticket counter: the CTAs do not run at
   // one speed (measured: with 190 bins each the first CTA ended after 0.97 ms, the last after 1.09 ms).  Thread 0
   // fetches a ticket two bins ahead and publishes (bin, bin % S) one bin ahead, so neither the L2 round trip nor the
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
   if (tid == 0) {
     tk = gridDim.x + atomicAdd(ticket, 1u);
     s_nbin[0] = tk;
-    s_nsub[0] = tk < B ? tk % b.hint_S : 0u;
+    s_nsub[0] = tk < B ? tk % hint_S : 0u;
     if (tk < B) tk = gridDim.x + atomicAdd(ticket, 1u);
   }
   uint4 rg[ITEMS];
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
     const uint32_t nbin = s_nbin[it & 1], nsub = s_nsub[it & 1];
     if (tid == 0) {  // (read again by everybody at the top of the next iteration, behind at least one barrier)
       s_nbin[(it & 1) ^ 1] = tk;
-      s_nsub[(it & 1) ^ 1] = tk < B ? tk % b.hint_S : 0u;
+      s_nsub[(it & 1) ^ 1] = tk < B ? tk % hint_S : 0u;
       if (tk < B) tk = gridDim.x + atomicAdd(ticket, 1u);
     }
     uint64_t noff = 0;
@@ -660,7 +664,42 @@ __global__ void __launch_bounds__(kSortThreads, 2) k_sort_reduce_u64(ShuffleBuff
       if (cnt == 0 && tid == 0) b.ucount[bin] = 0;
     } else {
       ChunkOut out{b.out_keys, b.out_sums, out_start(b, bin), b.counters + CNT_ERR, b.no_reduce};
-      const uint64_t pmin = (uint64_t)sub * b.hint_q;
+      uint64_t pmin = (uint64_t)sub * b.hint_q;
+      int sh0 = sh0_h, sh1 = sh1_h;
+      if (MINMAX) {
+        unsigned long long lo = ~0ull, hi = 0ull;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++)
+          if (tid + k * T < cnt) {
+            const unsigned long long key = (unsigned long long)rg[k].x | ((unsigned long long)rg[k].y << 32);
+            lo = key < lo ? key : lo;
+            hi = key > hi ? key : hi;
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+          lo = l2 < lo ? l2 : lo;
+          hi = h2 > hi ? h2 : hi;
+        }
+        if (lane == 0) {
+          s_mm[0][warp] = lo;
+          s_mm[1][warp] = hi;
+        }
+        __syncthreads();
+        lo = lane < T / 32 ? s_mm[0][lane] : ~0ull;
+        hi = lane < T / 32 ? s_mm[1][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+          lo = l2 < lo ? l2 : lo;
+          hi = h2 > hi ? h2 : hi;
+        }
+        pmin = lo;
+        const unsigned long long range = hi - lo;
+        const int bits = range ? 64 - __clzll((long long)range) : 0;
+        sh0 = bits > 32 ? bits - 32 : 0;
+        sh1 = (bits > kLogNB ? bits - kLogNB : 0) - sh0;
+      }
       uint32_t rpack = 0;  // 4 bits per item: arrival order inside the bucket
       int over = 0;
 #pragma unroll
