@@ -248,6 +248,13 @@ def test_keys_longer_than_a_record_slot():
             m.commit()
             ctx.shuffle()
             assert [(k, v) for p in ctx.partitions() for k, v in ctx.groups(p)] == [(b"only", [1])]
+            ctx.reset()  # nothing but a long key: the device side of the shuffle is empty
+            m = ctx.map_begin(0)
+            m.emit(b"L" * 100, 2)
+            m.emit(b"L" * 100, 3)
+            m.commit()
+            ctx.shuffle()
+            assert [(k, v) for p in ctx.partitions() for k, v in ctx.groups(p)] == [(b"L" * 100, [5])]
             # the device tokeniser meets a word that does not fit: that piece of the text is tokenised on the host
             ctx.reset()
             url = b"http://" + b"x" * 300
