@@ -148,6 +148,7 @@ struct mrhbm_iter {
   std::vector<unsigned char> keys;
   std::vector<uint64_t> sums;
   std::vector<RunCursor> runs;
+  std::vector<uint32_t> heap;  // the runs that still have rows, a binary min-heap on their current key (heap.lua:29-93)
   uint64_t base = 0;
   const std::vector<LongGroup>* longs = nullptr;  // the partition's long-key groups and the next one to hand out
   size_t long_pos = 0;
@@ -2001,6 +2002,36 @@ static inline int slot_cmp(const mrhbm_ctx* c, const unsigned char* a, const uns
   return memcmp(a, b, c->kb);
 }
 
+// k-way merge of the partition's ascending runs (utils.lua:206-271 merges spill files the same way): a binary heap of
+// run indices ordered by the key each run stands on (ties: lower run first)
+static inline bool run_less(const mrhbm_iter* it, uint32_t a, uint32_t b) {
+  const mrhbm_ctx* c = it->ctx;
+  const int x = slot_cmp(c, &it->keys[it->runs[a].pos * c->kb], &it->keys[it->runs[b].pos * c->kb]);
+  return x < 0 || (x == 0 && a < b);
+}
+static inline void heap_sift_down(mrhbm_iter* it, size_t i) {
+  std::vector<uint32_t>& h = it->heap;
+  const size_t n = h.size();
+  for (;;) {
+    const size_t l = 2 * i + 1, r = l + 1;
+    size_t m = i;
+    if (l < n && run_less(it, h[l], h[m])) m = l;
+    if (r < n && run_less(it, h[r], h[m])) m = r;
+    if (m == i) return;
+    std::swap(h[i], h[m]);
+    i = m;
+  }
+}
+// the run at the top moved on (or ran dry): restore the heap
+static inline void heap_fix_top(mrhbm_iter* it) {
+  std::vector<uint32_t>& h = it->heap;
+  if (it->runs[h[0]].pos >= it->runs[h[0]].end) {
+    h[0] = h.back();
+    h.pop_back();
+  }
+  if (!h.empty()) heap_sift_down(it, 0);
+}
+
 int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
   if (!c || !out) return MRHBM_E_INVAL;
   Entry g(c);
@@ -2042,6 +2073,9 @@ int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
       }
     }
   }
+  for (uint32_t r = 0; r < it->runs.size(); r++)
+    if (it->runs[r].pos < it->runs[r].end) it->heap.push_back(r);
+  for (size_t i = it->heap.size() / 2; i-- > 0;) heap_sift_down(it, i);
   *out = it;
   return MRHBM_OK;
 }
@@ -2049,12 +2083,8 @@ int mrhbm_groups_open(mrhbm_ctx* c, uint32_t part, mrhbm_iter** out) {
 int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint64_t** values, size_t* nvalues) {
   if (!it || !key || !klen || !values || !nvalues) return MRHBM_E_INVAL;
   mrhbm_ctx* c = it->ctx;
-  // k-way merge over the ascending runs of the partition (a single run when sorted)
-  int best = -1;
-  for (size_t r = 0; r < it->runs.size(); r++) {
-    if (it->runs[r].pos >= it->runs[r].end) continue;
-    if (best < 0 || slot_cmp(c, &it->keys[it->runs[r].pos * c->kb], &it->keys[it->runs[best].pos * c->kb]) < 0) best = (int)r;
-  }
+  // k-way merge over the ascending runs of the partition (a single run when sorted): the smallest key is on top
+  const int best = it->heap.empty() ? -1 : (int)it->heap[0];
   if (it->longs && it->long_pos < it->longs->size()) {
     // a key longer than a slot comes next when it sorts before the smallest device key: both are compared as the
     // escaped byte strings a slot holds (the device key ends at its zero padding; a proper prefix sorts first)
@@ -2087,12 +2117,18 @@ int mrhbm_groups_next(mrhbm_iter* it, const void** key, size_t* klen, const uint
     // sibling runs too
     it->valbuf.clear();
     it->valbuf.push_back(it->sums[i]);
-    for (size_t r = 0; r < it->runs.size(); r++) {
-      RunCursor& rc = it->runs[r];
+    for (;;) {  // the run on top, then whichever run comes to the top with the same key
+      RunCursor& rc = it->runs[it->heap[0]];
       while (rc.pos < rc.end && slot_cmp(c, &it->keys[rc.pos * c->kb], k) == 0) it->valbuf.push_back(it->sums[rc.pos++]);
+      heap_fix_top(it);
+      if (it->heap.empty()) break;
+      const RunCursor& top = it->runs[it->heap[0]];
+      if (slot_cmp(c, &it->keys[top.pos * c->kb], k) != 0) break;
     }
     nv = it->valbuf.size();
     gathered = true;
+  } else {
+    heap_fix_top(it);
   }
   if (c->rb == 16) {
     for (int b = 0; b < 8; b++) it->keybuf[b] = k[7 - b];  // 8-byte big-endian string
