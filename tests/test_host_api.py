@@ -76,6 +76,33 @@ def corpus(tmp_path, golden_wordcount):
     return files
 
 
+class BulkStandInCtx(StandInCtx):
+    """A stand-in that also offers the bulk result calls; `long_keys` makes result_copy answer the way the library
+    does when the result holds keys longer than a slot (MRHBM_E_KEY = -4)."""
+    long_keys = False
+    copies = 0
+
+    def result_info(self):
+        class Info:
+            sorted = 1
+        return Info()
+
+    def result_copy(self):
+        import numpy as np
+        type(self).copies += 1
+        if self.long_keys:
+            e = RuntimeError("mrhbm error -4: groups have keys longer than the slots of mrhbm_result_copy")
+            e.code = -4
+            raise e
+        keys, sums, po = [], [], [0]
+        for p in range(self.P):
+            for k in sorted(self.parts.get(p, {})):
+                keys.append(k)
+                sums.append(self.parts[p][k])
+            po.append(len(keys))
+        return np.array(keys, dtype="S123"), np.array(sums, dtype=np.uint64), np.array(po, dtype=np.uint64)
+
+
 CONFIGS = {  # test.sh:9-71
     "combiner+aci": dict(reducefn=WC + ".reducefn", combinerfn=WC + ".reducefn"),
     "aci": dict(reducefn=WC + ".reducefn"),
@@ -293,3 +320,18 @@ def test_finalfn_loop_runs_another_iteration(corpus, golden_wordcount):
             want[t] = want.get(t, 0) + 1
     assert calls[1] == want
     assert all("pairs" not in j["value"] for j in s.results)  # true / "loop": results removed (server.lua:395-401)
+
+
+@pytest.mark.parametrize("long_keys", [False, True])
+def test_reduce_falls_back_to_the_iterator_when_the_bulk_copy_cannot_hold_the_keys(corpus, golden_wordcount, long_keys):
+    """job.py takes the whole result with ONE bulk copy when the built-in reducer + ACI flags allow it; a result with
+    keys longer than a slot makes the library answer MRHBM_E_KEY, and the reduce jobs then iterate group by group
+    (job.lua:264-284) -- same final result either way."""
+    BulkStandInCtx.long_keys, BulkStandInCtx.copies = long_keys, 0
+    s = run_config("aci", "bulk-%s" % long_keys, ctx_factory=BulkStandInCtx)
+    want = {}
+    for k, p, c in golden_wordcount:
+        want[k] = sum(c)
+    assert {k: v for k, v in WordCount.RESULT.items()} == want
+    assert BulkStandInCtx.copies == 1  # once per shuffle: cached on the board, also when it failed
+
